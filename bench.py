@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- poses/sec of the NLML_HPE inference hot path on B200 (one process per GPU).
+
+Contract (task statement): `python bench.py --gpus N --steps K --warmup W` (under torchrun for N>1)
+prints ONE JSON line on rank 0.  A "step" is one pass of the hot path over one batch of synthetic
+feature vectors per GPU.  Headline = the Tucker-fit half (BASELINE.json configs[3]: 1M synthetic
+samples per GPU, shipped W, ranks (5,3,3,3), T=3000); the Encoder+heads half (configs[2]) is reported in
+the same line under "mlp".  `--impl reference` times the CPU port of the reference (oracle/) instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F = 1404
+RANKS = (5, 3, 3, 3)
+T_ITERS, LR, CLIP = 3000, 1e-3, 1.0
+
+# executed FP32 work of the folded-Gram iteration, per sample:
+#   quadratic pass 216*(15+15+3)+36*3 FMA, back-substitution 52, linear term 351, features/clip ~60
+TUCKER_FMA_PER_ITER = 216 * 33 + 36 * 3 + 52 + 351 + 60
+TUCKER_FLOP_PER_POSE = 2 * (135 * F + T_ITERS * TUCKER_FMA_PER_ITER)
+TUCKER_FLOP_PER_POSE_GRAM = 2 * 135 * F + T_ITERS * (2 * 135 * 135 + 2000)
+TUCKER_FLOP_PER_POSE_REFERENCE = T_ITERS * 2 * 2 * 135 * F
+TUCKER_BYTES_PER_POSE = F * 4 + 8 * 4
+MLP_FLOP_PER_POSE = 4_714_240
+MLP_BYTES_PER_POSE = F * 4 + 3 * 4
+
+
+def load_artifacts():
+    art = dict(np.load(os.path.join(ROOT, "tests", "golden", "shipped_artifacts.npz")))
+    rows = tuple(np.ascontiguousarray(art[f"optimized_{k}"][0:3, :]) for k in ("yaw", "pitch", "roll"))
+    return art, rows
+
+
+def state_dicts(art):
+    from nlml_hpe_b200 import synthetic
+    enc = synthetic.synthetic_encoder_state_dict(art["W"], art["optimized_yaw"], art["optimized_pitch"],
+                                                 art["optimized_roll"], U_id=art["U_id"], seed=0)
+    heads = [{k.split(".", 1)[1]: v for k, v in art.items() if k.startswith(f"{h}_network.")}
+             for h in ("yaw", "pitch", "roll")]
+    return enc, heads[0], heads[1], heads[2]
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.path = gpu_index, None, None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.path or not os.path.exists(self.path):
+            return out
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+def time_steps(fn, steps, warmup, torch, dist, world):
+    """W warm-ups, then exactly K steps between barrier+synchronize, CUDA events, max over ranks."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        dist.barrier()
+        t = torch.tensor([ms, wall_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, wall_ms = t.tolist()
+    return ms, wall_ms
+
+
+def time_host_steps(fn, steps, warmup, torch, dist, world):
+    """Same for a host-buffer call (synchronous): wall clock around K calls, max over ranks."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    return ms
+
+
+def cpu_baseline_tucker(art, rows, cores, seconds_cap=40.0):
+    """oracle port of TD_Tester.optimize_with_sgd (autograd form, as the reference runs it), one sample per
+    worker process with 1 torch thread each, `cores` workers, T=3000."""
+    from concurrent.futures import ProcessPoolExecutor
+    from nlml_hpe_b200 import synthetic
+    X = synthetic.make_features(cores, art["W"], *rows, U_id=art["U_id"], seed=1234)
+    with ProcessPoolExecutor(max_workers=cores) as pool:
+        list(pool.map(_cpu_warm_worker, range(cores)))          # interpreter + torch import stay outside the timing
+        t0 = time.perf_counter()
+        list(pool.map(_cpu_tucker_worker, [(art["W"], X[i], rows) for i in range(cores)]))
+        dt = time.perf_counter() - t0
+    return {"value": cores / dt, "unit": "poses/s", "cores": cores, "kind": "port",
+            "sample": f"{cores} samples (one per worker process, 1 thread each), T={T_ITERS}, "
+                      f"oracle.tucker_oracle.sgd_reference_form = autograd restatement of TD_Tester.py:127-159; {dt:.1f} s"}
+
+
+def _cpu_warm_worker(_):
+    import torch
+    torch.set_num_threads(1)
+    from oracle import tucker_oracle  # noqa: F401
+    time.sleep(0.2)
+    return 0
+
+
+def _cpu_tucker_worker(args):
+    import torch
+    torch.set_num_threads(1)
+    from oracle import tucker_oracle
+    W, x, rows = args
+    return tucker_oracle.sgd_reference_form(W, x, *rows, lr=LR, iters=T_ITERS, clip=CLIP)
+
+
+def cpu_baseline_mlp(art, cores, n=16384, reps=3):
+    import torch
+    from nlml_hpe_b200 import synthetic
+    from oracle import mlp_oracle
+    sds = state_dicts(art)
+    rows = tuple(art[f"optimized_{k}"][0:3] for k in ("yaw", "pitch", "roll"))
+    X = synthetic.make_features(n, art["W"], *rows, U_id=art["U_id"], seed=1234)
+    torch.set_num_threads(cores)
+    mlp_oracle.forward(*sds, X[:1024])
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        mlp_oracle.forward(*sds, X)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": n / best, "unit": "poses/s", "cores": cores, "kind": "port",
+            "sample": f"{n} vectors in one batched call, best of {reps}, torch CPU f32 ({cores} threads), "
+                      "oracle.mlp_oracle.forward = restatement of NLML_HPE_Model_Builder.py:115-126"}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from nlml_hpe_b200 import NLML_HPE_Model_Builder as MB
+    from nlml_hpe_b200 import _lib, synthetic
+    from nlml_hpe_b200.tucker import TuckerFitter
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: nlml_hpe_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    art, rows = load_artifacts()
+    peaks = measured_peaks()
+    n = args.samples
+    steps, warmup = args.steps, args.warmup
+
+    # ---- inputs: resident in HBM (value) and in pinned host memory (e2e) ----
+    X = synthetic.make_features_torch(n, art["W"], *rows, U_id=art["U_id"], seed=1234 + rank, device=dev)
+    X_host = torch.empty((n, F), dtype=torch.float32, pin_memory=True)
+    X_host.copy_(X)
+    torch.cuda.synchronize()
+
+    fitter = TuckerFitter(art["W"], *rows, device=dev)
+    model = MB.build_combined_model(*state_dicts(art))
+    P = torch.empty((n, 8), dtype=torch.float32, device=dev)
+    P_host = np.empty((n, 8), dtype=np.float32)
+    Y_host = np.empty((n, 3), dtype=np.float32)
+
+    import ctypes
+    fp32_peak = ctypes.c_double()
+    _lib.check(lib.nlml_measure_fp32_tflops(local, ctypes.byref(fp32_peak)))
+    fp32_peak = fp32_peak.value
+
+    result = {}
+    with ClockSampler(local) as clocks:
+        # Tucker fit, device-resident
+        l0 = fitter.launches
+        ms, wall = time_steps(lambda: fitter.fit(X, T_ITERS, LR, CLIP, out=P), steps, warmup, torch, dist, world)
+        t_launches = (fitter.launches - l0) * steps // (steps + warmup)
+        tucker_ms = ms / steps
+        # Tucker fit, host buffers through the C ABI (H2D + fit + D2H inside the timed region)
+        e2e_steps = max(1, min(steps, args.e2e_steps))
+        ms_e2e = time_host_steps(lambda: fitter.fit_host(X_host, T_ITERS, LR, CLIP, out=P_host), e2e_steps, 1, torch, dist, world)
+        tucker_e2e_ms = ms_e2e / e2e_steps
+    clk = clocks.summary()
+
+    with ClockSampler(local) as clocks2:
+        l0 = model.launches
+        model.predict(X[:1024])
+        ms_m, _ = time_steps(lambda: model.predict(X), steps, warmup, torch, dist, world)
+        m_launches = (model.launches - l0) * steps // (steps + warmup)
+        mlp_ms = ms_m / steps
+        ms_me = time_host_steps(lambda: model.predict_host(X_host.numpy()), e2e_steps, 1, torch, dist, world)
+        mlp_e2e_ms = ms_me / e2e_steps
+    clk2 = clocks2.summary()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total = n * world
+    tucker_pps = total / (tucker_ms * 1e-3)
+    mlp_pps = total / (mlp_ms * 1e-3)
+    per_gpu_t = n / (tucker_ms * 1e-3)
+    per_gpu_m = n / (mlp_ms * 1e-3)
+    cores = os.cpu_count() or 1
+    line = {
+        "metric": "poses/sec (Tucker-fit, fixed T=3000 iterations; Encoder+MLP heads under 'mlp')",
+        "value": tucker_pps, "unit": "poses/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": tucker_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"TD_Inference batched Tucker-fit (BASELINE.json configs[3]): {n} synthetic on-manifold+noise "
+                               f"feature vectors per GPU, shipped W ranks {RANKS}, F={F}, T={T_ITERS}, lr={LR}, clip={CLIP}",
+                   "samples_per_gpu": n, "sharding": f"sample-index, {world} rank(s), no collective on the compute path",
+                   "l2": f"inputs {n * F * 4 / 1e9:.2f} GB per GPU, larger than the 126 MB L2 (no flush needed)"},
+        "e2e": {"value": total / (tucker_e2e_ms * 1e-3), "unit": "poses/s", "h2d_bytes_per_step": n * F * 4,
+                "d2h_bytes_per_step": n * 8 * 4, "steps": e2e_steps,
+                "api": "nlml_tucker_fit_host_f32 (TuckerFitter.fit_host), pinned host X -> host P"},
+        "gpu_launches": int(t_launches),
+        "roofline": {"bound": "fp32_fma", "achieved": per_gpu_t * TUCKER_FLOP_PER_POSE / 1e12, "peak": fp32_peak,
+                     "unit": "TFLOP/s", "frac": per_gpu_t * TUCKER_FLOP_PER_POSE / 1e12 / fp32_peak, "traffic": None,
+                     "kernel": "tucker_fit_tps_kernel<5,3,3,3,128,2>",
+                     "note": "3000 on-chip iterations per 5.6 KB streamed: neither HBM nor tensor pipe binds; peak = FFMA rate "
+                             "measured live by nlml_measure_fp32_tflops; flop count = executed folded-Gram work "
+                             f"({TUCKER_FLOP_PER_POSE / 1e6:.1f} MFLOP/pose; Gram form {TUCKER_FLOP_PER_POSE_GRAM / 1e6:.1f}, "
+                             f"reference einsum form {TUCKER_FLOP_PER_POSE_REFERENCE / 1e6:.0f})"},
+        "roofline_hbm": {"bound": "hbm", "achieved": per_gpu_t * TUCKER_BYTES_PER_POSE / 1e9, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": per_gpu_t * TUCKER_BYTES_PER_POSE / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                         "peak_source": peaks["source"]},
+        "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
+        "mlp": {
+            "metric": "poses/sec (Encoder + yaw/pitch/roll MLP heads forward)", "value": mlp_pps, "unit": "poses/s",
+            "ms_per_step": mlp_ms, "dtype": "f32",
+            "config": {"workload": f"BASELINE.json configs[2]: {n} synthetic feature vectors per GPU, shipped heads + synthetic encoder"},
+            "e2e": {"value": total / (mlp_e2e_ms * 1e-3), "unit": "poses/s", "h2d_bytes_per_step": n * F * 4,
+                    "d2h_bytes_per_step": n * 3 * 4, "steps": e2e_steps, "api": "nlml_mlp_forward_host_f32"},
+            "gpu_launches": int(m_launches),
+            "roofline": {"bound": "tensor", "achieved": per_gpu_m * MLP_FLOP_PER_POSE / 1e12, "peak": peaks["bf16_tflops_sustained"],
+                         "unit": "TFLOP/s", "frac": per_gpu_m * MLP_FLOP_PER_POSE / 1e12 / peaks["bf16_tflops_sustained"],
+                         "traffic": None, "peak_source": peaks["source"],
+                         "note": "algorithmic 4.714 MFLOP/pose against the sustained bf16 tensor peak"},
+            "roofline_hbm": {"bound": "hbm", "achieved": per_gpu_m * MLP_BYTES_PER_POSE / 1e9, "peak": peaks["hbm_gbs"],
+                             "unit": "GB/s", "frac": per_gpu_m * MLP_BYTES_PER_POSE / 1e9 / peaks["hbm_gbs"]},
+            "clocks": {"sm_mhz": clk2["sm_mhz"], "sm_max_mhz": clk2["sm_max_mhz"], "reasons": clk2["reasons"]},
+        },
+        "fp32_fma_peak_tflops_measured": fp32_peak,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_tucker(art, rows, cores)
+        line["mlp"]["cpu_baseline"] = cpu_baseline_mlp(art, cores)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the CPU port of the reference's own path, all host threads
+# ---------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    art, rows = load_artifacts()
+    cores = os.cpu_count() or 1
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline_tucker(art, rows, cores)
+    vals, t0 = [], time.perf_counter()
+    for _ in range(args.steps):
+        vals.append(cpu_baseline_tucker(art, rows, cores))
+        if time.perf_counter() - t0 > 150:
+            break
+    dt = time.perf_counter() - t0
+    value = cores * len(vals) / dt
+    base = dict(vals[-1], value=value)
+    mlp = cpu_baseline_mlp(art, cores)
+    line = {
+        "impl": "reference",
+        "metric": "poses/sec (Tucker-fit, fixed T=3000 iterations; Encoder+MLP heads under 'mlp')",
+        "value": value, "unit": "poses/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": min(args.warmup, 1),
+        "ms_per_step": dt / len(vals) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"TD_Inference Tucker-fit, CPU port of the reference (TD_Tester.optimize_with_sgd), shipped W ranks {RANKS}, "
+                               f"F={F}, T={T_ITERS}; each step = {cores} samples, one per host core"},
+        "cpu_baseline": base,
+        "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mlp": {"value": mlp["value"], "unit": "poses/s", "cpu_baseline": mlp,
+                "e2e": {"value": mlp["value"], "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--samples", type=int, default=1_000_000, help="feature vectors per GPU per step")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

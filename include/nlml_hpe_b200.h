@@ -1,0 +1,111 @@
+/* nlml_hpe_b200 -- C ABI of the B200-native NLML_HPE inference hot path.
+ *
+ * The reference (MahdiGhafoorian/NLML_HPE) is pure Python and has no FFI of its own; the
+ * "operator interface" of the hot path is two Python callables:
+ *
+ *   TD_Tester.optimize_with_sgd(W, x, u_id, u_id_shape, params_y, params_p, params_r,
+ *                               learning_rate=0.001, num_iterations=3000)      TD_Tester.py:127-159
+ *       (entry point TD_Tester.Test(...), TD_Tester.py:162-291, called from TD_Inference.py:56-58)
+ *   CombinedAnglePredictionModel.forward(x[B,1404]) -> (yaw[B,1], pitch[B,1], roll[B,1])
+ *                                                                 NLML_HPE_Model_Builder.py:115-126
+ *       (called from NLML_HPE_Test.py:272,327,411 and generatePose_on_video.py:210)
+ *
+ * Each entry point below is what a ctypes binding on the reference side would call in place of
+ * those two callables (INTEGRATION.md shows the stubs).  Plain pointers and sizes only; no
+ * torch / numpy types.  All functions return 0 on success and a non-zero code on failure
+ * (positive = cudaError_t, negative = NLML_E_*); nlml_last_error() returns a thread-local
+ * human-readable message for the last failure.  There is no CPU fallback: every compute entry
+ * point fails with NLML_E_NO_DEVICE when no sm_100 device is usable.
+ */
+#ifndef NLML_HPE_B200_H
+#define NLML_HPE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NLML_ABI_VERSION 1
+
+#define NLML_E_INVALID (-1)     /* bad argument (null pointer, non-positive size, unsupported rank) */
+#define NLML_E_NO_DEVICE (-2)   /* no usable CUDA device */
+#define NLML_E_UNSUPPORTED (-3) /* valid request this build cannot serve (e.g. core too large) */
+
+int nlml_abi_version(void);
+const char* nlml_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Tucker fit  (replaces TD_Tester.optimize_with_sgd, TD_Tester.py:127-159, batched over samples)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct nlml_tucker_plan nlml_tucker_plan;
+
+/* One-time preparation for a Tucker tensor W[r_id][r_y][r_p][r_r][F] (C-contiguous float32, HOST
+ * pointer; the array TD_Inference.py:47 loads from Trained_data.npz) and the cosine rows
+ * optimized_{yaw,pitch,roll}[0:r,:] (HOST, row-major [r][4] doubles = (a,b,c,d), TD_Inference.py:43-45,
+ * :56-57).  Uploads W, builds the folded Gram tensor on `device`, keeps both resident. */
+int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, int r_p, int r_r, int F,
+                            const double* rows_y, const double* rows_p, const double* rows_r,
+                            int device, nlml_tucker_plan** plan_out);
+void nlml_tucker_plan_destroy(nlml_tucker_plan* plan);
+
+/* Fit N samples.  X: DEVICE float32 [N][ldx] (first F columns used).  P_out: DEVICE float32
+ * [N][ldp], ldp >= 3 + r_id: (w_yaw, w_pitch, w_roll) in radians followed by the identity
+ * coefficients, exactly the vector optimize_with_sgd returns (TD_Tester.py:159).
+ * iters / lr / clip are num_iterations, learning_rate (TD_Tester.py:127) and the max_norm of :150.
+ * Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+ * kernel_hint: 0 = choose by N, 1 = force thread-per-sample kernel, 2 = force CTA-per-sample kernel. */
+int nlml_tucker_fit_f32(nlml_tucker_plan* plan, const float* X_dev, int64_t N, int64_t ldx,
+                        int iters, float lr, float clip, float* P_out_dev, int64_t ldp,
+                        int kernel_hint, void* stream);
+
+/* Same with HOST buffers: chunks the batch, overlaps H2D copy / kernel / D2H copy on two internal
+ * streams with pinned staging, returns when P_out_host is complete. */
+int nlml_tucker_fit_host_f32(nlml_tucker_plan* plan, const float* X_host, int64_t N, int64_t ldx,
+                             int iters, float lr, float clip, float* P_out_host, int64_t ldp);
+
+/* Number of kernel launches issued by this plan so far (for bench.py's gpu_launches). */
+int64_t nlml_tucker_launch_count(const nlml_tucker_plan* plan);
+
+/* ------------------------------------------------------------------------------------------
+ * Encoder + yaw/pitch/roll heads  (replaces CombinedAnglePredictionModel.forward,
+ * NLML_HPE_Model_Builder.py:115-126)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct nlml_mlp_plan nlml_mlp_plan;
+
+#define NLML_MLP_ENCODER_LAYERS 6 /* NLML_HPE_Model_Builder.py:33-53 */
+#define NLML_MLP_HEAD_LAYERS 5    /* NLML_HPE_Model_Builder.py:76-92 */
+#define NLML_MLP_NUM_TENSORS (NLML_MLP_ENCODER_LAYERS + 3 * NLML_MLP_HEAD_LAYERS) /* 21 Linear layers */
+
+/* weights[i] / biases[i]: HOST float32, nn.Linear layout weight[out][in], bias[out]; order =
+ * encoder.{0,2,4,6,8,10}, yaw model.{0,2,4,6,8}, pitch model.{...}, roll model.{...}
+ * (the state_dicts loaded at NLML_HPE_Model_Builder.py:202,214-216).  out_dims/in_dims give each
+ * layer's shape; the chain must be consistent (encoder out = 3 * head in).  Activations are fixed by
+ * the reference: encoder ReLU x4, Tanh, none; heads ReLU x4, none. */
+int nlml_mlp_plan_create(const float* const* weights, const float* const* biases,
+                         const int* out_dims, const int* in_dims, int device,
+                         nlml_mlp_plan** plan_out);
+void nlml_mlp_plan_destroy(nlml_mlp_plan* plan);
+
+/* X: DEVICE float32 [N][ldx]; YPR_out: DEVICE float32 [N][3] = (yaw, pitch, roll) radians.
+ * Asynchronous on `stream`. */
+int nlml_mlp_forward_f32(nlml_mlp_plan* plan, const float* X_dev, int64_t N, int64_t ldx,
+                         float* YPR_out_dev, void* stream);
+/* HOST buffers, chunked and pipelined like nlml_tucker_fit_host_f32. */
+int nlml_mlp_forward_host_f32(nlml_mlp_plan* plan, const float* X_host, int64_t N, int64_t ldx,
+                              float* YPR_out_host);
+/* Encoder output only: LAT_out DEVICE float32 [N][latent] (for stage-wise parity checks). */
+int nlml_mlp_latent_f32(nlml_mlp_plan* plan, const float* X_dev, int64_t N, int64_t ldx,
+                        float* LAT_out_dev, void* stream);
+int64_t nlml_mlp_launch_count(const nlml_mlp_plan* plan);
+
+/* ------------------------------------------------------------------------------------------
+ * Measurement helper: sustained FP32 FMA rate of the device (TFLOP/s), used by bench.py as the
+ * denominator of the Tucker-fit kernel's FP32-pipe roofline.  Runs a register-only FFMA loop.
+ * ------------------------------------------------------------------------------------------ */
+int nlml_measure_fp32_tflops(int device, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLML_HPE_B200_H */

@@ -1,0 +1,9 @@
+"""nlml_hpe_b200 -- B200-native (sm_100a) inference hot path of NLML_HPE.
+
+Two halves, both behind the reference's own Python entry points:
+  TD_Tester / TD_Inference            batched fixed-iteration Tucker-fit pose inversion
+  NLML_HPE_Model_Builder / _Test      Encoder + yaw/pitch/roll MLP-heads forward
+Host code is Python; compute is hand-written CUDA reached through the C ABI in
+include/nlml_hpe_b200.h (libnlml_hpe_b200.so, built in-tree).  No CPU fallback.
+"""
+__version__ = "0.1.0"

@@ -1,0 +1,657 @@
+// Batched fixed-iteration Tucker fit for sm_100a.
+//
+// Replaces TD_Tester.optimize_with_sgd (/root/reference/TD_Tester.py:127-159) for a whole batch of
+// feature vectors.  Two kernels, same arithmetic (tucker_math.h), chosen by batch size:
+//
+//   tucker_fit_tps_kernel  thread-per-sample, ranks fixed at compile time (5,3,3,3 = the shipped /
+//                          configured ranks, configs/config_TD_main.yaml:8-13).  A CTA owns THREADS
+//                          consecutive samples: phase A streams their rows of X once from HBM and
+//                          leaves q = W2 x in shared memory; phase B runs all T iterations with p, the
+//                          monomials and the gradient in registers, the folded Gram tensor S broadcast
+//                          from shared memory.  No global memory traffic between iterations.
+//   tucker_fit_cta_kernel  CTA-per-sample, ranks at run time (enlarged cores, BASELINE.json config 5)
+//                          and the small-N / single-image case of TD_Inference.py, where latency of
+//                          the 3000-step chain matters more than throughput.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "tucker_math.h"
+
+namespace nlml {
+
+constexpr int kMaxModeRank = 16;
+constexpr int kMaxPairs = kMaxModeRank * (kMaxModeRank + 1) / 2;  // 136
+constexpr int kMaxBCD = 8192;                                    // CTA kernel keeps T[] and ypr[] in shared memory
+
+struct TuckerArgs {
+    const float* X;
+    long long N, ldx;
+    const float* W2;  // [R][F]
+    const float* S;   // [nBCD][NAP]   thread-per-sample layout
+    const float* St;  // [nA][nBCDp]   CTA-per-sample layout
+    float* P;
+    long long ldp;
+    int F, T;
+    float lr, clip;
+    int ri, ry, rp, rr;
+    int nBCDp;
+    int vec_ok;  // X rows and W2 rows are 16-byte aligned and F % 4 == 0
+    float rows_y[4 * kMaxModeRank], rows_p[4 * kMaxModeRank], rows_r[4 * kMaxModeRank];
+};
+
+// ---------------------------------------------------------------------------------------------
+// one-time constant preparation
+// ---------------------------------------------------------------------------------------------
+__global__ void gram_kernel(const float* __restrict__ W2, int R, int F, double* __restrict__ M) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= R * R) return;
+    const int r = idx / R, c = idx % R;
+    if (c < r) return;  // symmetric: compute the upper triangle, mirror
+    const double v = gram_entry(W2, F, r, c);
+    M[(long long)r * R + c] = v;
+    M[(long long)c * R + r] = v;
+}
+
+__global__ void fold_kernel(const double* __restrict__ M, int ri, int ry, int rp, int rr, int NAP, int nBCDp,
+                            float* __restrict__ S, float* __restrict__ St) {
+    const int nA = tri(ri), nB = tri(ry), nC = tri(rp), nD = tri(rr);
+    const int nBCD = nB * nC * nD;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nA * nBCD) return;
+    const int a = idx / nBCD, bcd = idx % nBCD;
+    const int b = bcd / (nC * nD), c = (bcd / nD) % nC, d = bcd % nD;
+    const float v = fold_entry(M, ri, ry, rp, rr, a, b, c, d);
+    S[(long long)bcd * NAP + a] = v;
+    St[(long long)a * nBCDp + bcd] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// thread-per-sample kernel
+// ---------------------------------------------------------------------------------------------
+template <int RI, int RY, int RP, int RR, int THREADS>
+struct TpsCfg {
+    static constexpr int R = RI * RY * RP * RR;
+    static constexpr int RPAD = (R + 3) / 4 * 4;
+    static constexpr int NP = 3 + RI;
+    static constexpr int nA = tri(RI);
+    static constexpr int NAP = (nA + 3) / 4 * 4;
+    static constexpr int nBCD = tri(RY) * tri(RP) * tri(RR);
+    static constexpr int FC = 16;              // feature columns per staged tile
+    static constexpr int XSTR = THREADS + 2;   // == 2 (mod 8): transposed tile stores are conflict-free
+    static constexpr int S_FLOATS = nBCD * NAP;
+    static constexpr int Q_FLOATS = R * THREADS;
+    static constexpr int TILE_FLOATS = FC * XSTR + FC * RPAD;
+    static_assert(TILE_FLOATS <= Q_FLOATS, "phase-A tiles alias the q buffer");
+    static constexpr size_t SMEM_BYTES = sizeof(float) * (S_FLOATS + Q_FLOATS);
+};
+
+__device__ __forceinline__ float4 load_row4(const float* __restrict__ row, int f, int F, bool vec_ok) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec_ok && f + 3 < F) {
+        v = __ldg(reinterpret_cast<const float4*>(row + f));
+    } else {
+        if (f + 0 < F) v.x = __ldg(row + f + 0);
+        if (f + 1 < F) v.y = __ldg(row + f + 1);
+        if (f + 2 < F) v.z = __ldg(row + f + 2);
+        if (f + 3 < F) v.w = __ldg(row + f + 3);
+    }
+    return v;
+}
+
+template <int RI, int RY, int RP, int RR, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) tucker_fit_tps_kernel(const __grid_constant__ TuckerArgs a) {
+    using C = TpsCfg<RI, RY, RP, RR, THREADS>;
+    extern __shared__ __align__(16) float smem[];
+    float* S_s = smem;
+    float* q_s = smem + C::S_FLOATS;
+    float* xs = q_s;                     // [FC][XSTR]   (phase A only)
+    float* ws = q_s + C::FC * C::XSTR;   // [FC][RPAD]   (phase A only)
+
+    const int tid = threadIdx.x;
+    const long long s0 = (long long)blockIdx.x * THREADS;
+    const bool vec_ok = a.vec_ok != 0;
+    const int F = a.F;
+
+    for (int i = tid; i < C::S_FLOATS / 4; i += THREADS)
+        reinterpret_cast<float4*>(S_s)[i] = __ldg(reinterpret_cast<const float4*>(a.S) + i);
+
+    // ---- phase A: q[r] = sum_f W2[r][f] * x[f] for this thread's sample ----
+    float acc[C::RPAD];
+#pragma unroll
+    for (int r = 0; r < C::RPAD; ++r) acc[r] = 0.f;
+
+    for (int f0 = 0; f0 < F; f0 += C::FC) {
+        for (int idx = tid; idx < THREADS * (C::FC / 4); idx += THREADS) {
+            const int s = idx / (C::FC / 4), c4 = idx % (C::FC / 4);
+            const long long row = s0 + s;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < a.N) v = load_row4(a.X + row * a.ldx, f0 + 4 * c4, F, vec_ok);
+            xs[(4 * c4 + 0) * C::XSTR + s] = v.x;
+            xs[(4 * c4 + 1) * C::XSTR + s] = v.y;
+            xs[(4 * c4 + 2) * C::XSTR + s] = v.z;
+            xs[(4 * c4 + 3) * C::XSTR + s] = v.w;
+        }
+        for (int idx = tid; idx < C::RPAD * (C::FC / 4); idx += THREADS) {
+            const int r = idx / (C::FC / 4), c4 = idx % (C::FC / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < C::R) v = load_row4(a.W2 + (long long)r * F, f0 + 4 * c4, F, vec_ok);
+            ws[(4 * c4 + 0) * C::RPAD + r] = v.x;
+            ws[(4 * c4 + 1) * C::RPAD + r] = v.y;
+            ws[(4 * c4 + 2) * C::RPAD + r] = v.z;
+            ws[(4 * c4 + 3) * C::RPAD + r] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int f = 0; f < C::FC; ++f) {
+            const float xv = xs[f * C::XSTR + tid];
+#pragma unroll
+            for (int r4 = 0; r4 < C::RPAD / 4; ++r4) {
+                const float4 w = *reinterpret_cast<const float4*>(&ws[f * C::RPAD + 4 * r4]);
+                acc[4 * r4 + 0] = fmaf(xv, w.x, acc[4 * r4 + 0]);
+                acc[4 * r4 + 1] = fmaf(xv, w.y, acc[4 * r4 + 1]);
+                acc[4 * r4 + 2] = fmaf(xv, w.z, acc[4 * r4 + 2]);
+                acc[4 * r4 + 3] = fmaf(xv, w.w, acc[4 * r4 + 3]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < C::R; ++r) q_s[r * THREADS + tid] = acc[r];
+    __syncthreads();  // S_s complete, tiles dead
+
+    // ---- phase B: T iterations entirely on chip ----
+    float p[C::NP];
+#pragma unroll
+    for (int i = 0; i < C::NP; ++i) p[i] = 0.f;  // zero init, TD_Tester.py:130
+    const float lr = a.lr, clip = a.clip;
+#pragma unroll 1
+    for (int it = 0; it < a.T; ++it) {
+        float g[C::NP];
+        tucker_gradient<RI, RY, RP, RR, C::NAP>(p, S_s, q_s + tid, THREADS, a.rows_y, a.rows_p, a.rows_r, g);
+        clip_and_step<C::NP>(p, g, lr, clip);
+    }
+    if (s0 + tid < a.N) {
+        float* out = a.P + (s0 + tid) * a.ldp;
+#pragma unroll
+        for (int i = 0; i < C::NP; ++i) out[i] = p[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-per-sample kernel (run-time ranks)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct CtaLayout {
+    // offsets in floats into dynamic shared memory
+    int x, q, T, ypr, fac, dfac, prod, G, lin, p, pairs, St, total;
+};
+
+__host__ __device__ inline CtaLayout cta_layout(int F, int R, int nBCD, int nA, int nBCDp, bool st_in_smem) {
+    CtaLayout L;
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += (n + 3) / 4 * 4; return r; };
+    L.x = take(F);
+    L.q = take(R);
+    L.T = take(nBCD);
+    L.ypr = take(nBCD);
+    L.fac = take(4 * kMaxModeRank);
+    L.dfac = take(4 * kMaxModeRank);
+    L.prod = take(4 * kMaxPairs);
+    L.G = take(4 * kMaxPairs);
+    L.lin = take(4 * kMaxModeRank);
+    L.p = take(2 * (3 + kMaxModeRank));
+    L.pairs = take(4 * kMaxPairs);  // packed (i | j<<8) per mode, stored as int
+    L.St = take(st_in_smem ? nA * nBCDp : 0);
+    L.total = o;
+    return L;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) tucker_fit_cta_kernel(const __grid_constant__ TuckerArgs a, int st_in_smem) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = THREADS / 32;
+    const int dims[4] = {a.ri, a.ry, a.rp, a.rr};
+    const int R = a.ri * a.ry * a.rp * a.rr;
+    const int nP[4] = {tri(a.ri), tri(a.ry), tri(a.rp), tri(a.rr)};
+    const int nA = nP[0], nB = nP[1], nC = nP[2], nD = nP[3];
+    const int nBCD = nB * nC * nD, nBCDp = a.nBCDp;
+    const int NP = 3 + a.ri;
+    const int F = a.F;
+    const CtaLayout L = cta_layout(F, R, nBCD, nA, nBCDp, st_in_smem != 0);
+    float* xb = smem + L.x;
+    float* q = smem + L.q;
+    float* Tb = smem + L.T;
+    float* ypr = smem + L.ypr;
+    float* fac = smem + L.fac;    // [4][kMaxModeRank]: u, cy, cp, cr
+    float* dfac = smem + L.dfac;  // [4][kMaxModeRank]: -, dcy, dcp, dcr
+    float* prod = smem + L.prod;  // [4][kMaxPairs]: UU, YY, PP, RR
+    float* G = smem + L.G;        // [4][kMaxPairs]: GU, GY, GP, GR
+    float* lin = smem + L.lin;    // [4][kMaxModeRank]: d(q.z)/d(factor entry)
+    float* p = smem + L.p;
+    int* pairs = reinterpret_cast<int*>(smem + L.pairs);
+    const float* St = a.St;
+
+    const long long s = blockIdx.x;
+    const float* xrow = a.X + s * a.ldx;
+    for (int f = tid; f < F; f += THREADS) xb[f] = __ldg(xrow + f);
+    for (int idx = tid; idx < 4 * kMaxPairs; idx += THREADS) {
+        const int m = idx / kMaxPairs, k = idx % kMaxPairs;
+        int i = 0, j = 0;
+        if (k < nP[m]) unpair(k, dims[m], &i, &j);
+        pairs[idx] = i | (j << 8);
+    }
+    if (st_in_smem) {
+        float* St_s = smem + L.St;
+        for (int i = tid; i < nA * nBCDp; i += THREADS) St_s[i] = __ldg(a.St + i);
+        St = St_s;
+    }
+    if (tid < 2 * (3 + kMaxModeRank)) p[tid] = 0.f;  // zero init, TD_Tester.py:130
+    __syncthreads();
+
+    // phase A: q = W2 x, one warp per row
+    for (int r = warp; r < R; r += NW) {
+        const float* wrow = a.W2 + (long long)r * F;
+        float acc = 0.f;
+        if (a.vec_ok) {
+            for (int f = 4 * lane; f < F; f += 128) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + f));
+                const float4 x = *reinterpret_cast<const float4*>(xb + f);
+                acc = fmaf(w.x, x.x, acc);
+                acc = fmaf(w.y, x.y, acc);
+                acc = fmaf(w.z, x.z, acc);
+                acc = fmaf(w.w, x.w, acc);
+            }
+        } else {
+            for (int f = lane; f < F; f += 32) acc = fmaf(__ldg(wrow + f), xb[f], acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) q[r] = acc;
+    }
+    __syncthreads();
+
+    const int n_lin_tasks = a.ri + a.ry + a.rp + a.rr;
+    const int n_tasks = nA + nB + nC + nD + n_lin_tasks;
+
+    for (int it = 0; it < a.T; ++it) {
+        // (0) factor vectors
+        if (tid < a.ri) {
+            fac[tid] = p[3 + tid];
+        } else if (tid >= 32 && tid < 32 + a.ry + a.rp + a.rr) {
+            int k = tid - 32, m = 1;
+            const float* rows = a.rows_y;
+            if (k >= a.ry) { k -= a.ry; m = 2; rows = a.rows_p; }
+            if (m == 2 && k >= a.rp) { k -= a.rp; m = 3; rows = a.rows_r; }
+            const float w = p[m - 1];
+            const float ca = rows[4 * k], cb = rows[4 * k + 1], cc = rows[4 * k + 2], cd = rows[4 * k + 3];
+            float sn, cs;
+            sincosf(cb * w + cc, &sn, &cs);
+            fac[m * kMaxModeRank + k] = ca * cs + cd;
+            dfac[m * kMaxModeRank + k] = -(ca * cb) * sn;
+        }
+        __syncthreads();
+        // (1) symmetric products
+        for (int idx = tid; idx < 4 * kMaxPairs; idx += THREADS) {
+            const int m = idx / kMaxPairs, k = idx % kMaxPairs;
+            if (k < nP[m]) {
+                const int pr = pairs[idx];
+                prod[idx] = fac[m * kMaxModeRank + (pr & 255)] * fac[m * kMaxModeRank + (pr >> 8)];
+            }
+        }
+        __syncthreads();
+        // (2) T[bcd] = sum_a S[a,bcd] UU[a];  ypr[bcd] = YY_b PP_c RR_d
+        for (int bcd = tid; bcd < nBCD; bcd += THREADS) {
+            const int b = bcd / (nC * nD), c = (bcd / nD) % nC, d = bcd % nD;
+            ypr[bcd] = prod[kMaxPairs + b] * prod[2 * kMaxPairs + c] * prod[3 * kMaxPairs + d];
+            float t = 0.f;
+            for (int aa = 0; aa < nA; ++aa) t = fmaf(St[(long long)aa * nBCDp + bcd], prod[aa], t);
+            Tb[bcd] = t;
+        }
+        __syncthreads();
+        // (3) warp tasks: the four G vectors and the linear-term derivatives
+        for (int task = warp; task < n_tasks; task += NW) {
+            float acc = 0.f;
+            int k = task;
+            if (k < nA) {
+                const float* row = St + (long long)k * nBCDp;
+                for (int bcd = lane; bcd < nBCD; bcd += 32) acc = fmaf(row[bcd], ypr[bcd], acc);
+                acc = warp_sum(acc);
+                if (lane == 0) G[k] = acc;
+                continue;
+            }
+            k -= nA;
+            if (k < nB) {
+                for (int i = lane; i < nC * nD; i += 32) {
+                    const int c = i / nD, d = i % nD;
+                    acc = fmaf(Tb[(k * nC + c) * nD + d], prod[2 * kMaxPairs + c] * prod[3 * kMaxPairs + d], acc);
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) G[kMaxPairs + k] = acc;
+                continue;
+            }
+            k -= nB;
+            if (k < nC) {
+                for (int i = lane; i < nB * nD; i += 32) {
+                    const int b = i / nD, d = i % nD;
+                    acc = fmaf(Tb[(b * nC + k) * nD + d], prod[kMaxPairs + b] * prod[3 * kMaxPairs + d], acc);
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) G[2 * kMaxPairs + k] = acc;
+                continue;
+            }
+            k -= nC;
+            if (k < nD) {
+                for (int i = lane; i < nB * nC; i += 32) {
+                    const int b = i / nC, c = i % nC;
+                    acc = fmaf(Tb[(b * nC + c) * nD + k], prod[kMaxPairs + b] * prod[2 * kMaxPairs + c], acc);
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) G[3 * kMaxPairs + k] = acc;
+                continue;
+            }
+            k -= nD;
+            // linear term: mode m, entry e:  sum over the other three modes of q[r] * prod(other factors)
+            int m = 0;
+            while (k >= dims[m]) { k -= dims[m]; ++m; }
+            const int o0 = m == 0 ? 1 : 0, o1 = m <= 1 ? 2 : 1, o2 = m <= 2 ? 3 : 2;
+            const int n0 = dims[o0], n1 = dims[o1], n2 = dims[o2];
+            for (int i = lane; i < n0 * n1 * n2; i += 32) {
+                int idx4[4];
+                idx4[m] = k;
+                idx4[o0] = i / (n1 * n2);
+                idx4[o1] = (i / n2) % n1;
+                idx4[o2] = i % n2;
+                const int r = ((idx4[0] * a.ry + idx4[1]) * a.rp + idx4[2]) * a.rr + idx4[3];
+                const float w = fac[o0 * kMaxModeRank + idx4[o0]] * fac[o1 * kMaxModeRank + idx4[o1]] *
+                                fac[o2 * kMaxModeRank + idx4[o2]];
+                acc = fmaf(q[r], w, acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) lin[m * kMaxModeRank + k] = acc;
+        }
+        __syncthreads();
+        // (4) assemble, clip, step (one thread; O(sum of squared ranks))
+        if (tid == 0) {
+            float g[3 + kMaxModeRank];
+            for (int m = 0; m < 4; ++m) {
+                const int r = dims[m];
+                float gang = 0.f;
+                for (int e = 0; e < r; ++e) {
+                    float acc = 2.0f * G[m * kMaxPairs + pair_index(e, e, r)] * fac[m * kMaxModeRank + e];
+                    for (int i = 0; i < r; ++i) {
+                        if (i == e) continue;
+                        const int lo = i < e ? i : e, hi = i < e ? e : i;
+                        acc = fmaf(G[m * kMaxPairs + pair_index(lo, hi, r)], fac[m * kMaxModeRank + i], acc);
+                    }
+                    const float d = acc - lin[m * kMaxModeRank + e];
+                    if (m == 0) g[3 + e] = d;
+                    else gang = fmaf(d, dfac[m * kMaxModeRank + e], gang);
+                }
+                if (m > 0) g[m - 1] = gang;
+            }
+            float ss = 0.f;
+            for (int i = 0; i < NP; ++i) ss = fmaf(g[i], g[i], ss);
+            float coef = a.clip / (sqrtf(ss) + 1e-6f);
+            coef = coef < 1.0f ? coef : 1.0f;
+            for (int i = 0; i < NP; ++i) p[i] = __fsub_rn(p[i], __fmul_rn(a.lr, __fmul_rn(g[i], coef)));
+        }
+        __syncthreads();
+    }
+    if (tid < NP) a.P[s * a.ldp + tid] = p[tid];
+}
+
+// register-only FFMA loop: measures the sustained FP32 FMA rate used as a roofline denominator
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
+          a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float b = 0.999f, c = 1e-3f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace nlml
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace nlml;
+
+struct nlml_tucker_plan {
+    int device = 0;
+    int ri = 0, ry = 0, rp = 0, rr = 0, F = 0, R = 0;
+    int nA = 0, NAP = 0, nBCD = 0, nBCDp = 0;
+    float* W2 = nullptr;
+    float* S = nullptr;
+    float* St = nullptr;
+    TuckerArgs base{};
+    bool fast = false;        // ranks (5,3,3,3): thread-per-sample kernel available
+    bool st_in_smem = false;  // CTA kernel keeps St in shared memory
+    size_t cta_smem = 0;
+    int num_sms = 148;
+    int64_t launches = 0;
+    // host-buffer path
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    float* x_dev[2] = {nullptr, nullptr};
+    float* p_dev[2] = {nullptr, nullptr};
+    int64_t chunk = 0;
+};
+
+namespace {
+constexpr int kTpsThreads = 128;
+constexpr int kTpsMinBlocks = 2;
+constexpr int kCtaThreads = 128;
+using TpsDefault = TpsCfg<5, 3, 3, 3, kTpsThreads>;
+
+int launch_fit(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int iters, float lr, float clip,
+               float* P, int64_t ldp, int hint, cudaStream_t st) {
+    if (N == 0) return 0;
+    TuckerArgs a = pl->base;
+    a.X = X;
+    a.N = N;
+    a.ldx = ldx;
+    a.P = P;
+    a.ldp = ldp;
+    a.T = iters;
+    a.lr = lr;
+    a.clip = clip;
+    a.vec_ok = (pl->F % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+    // crossover: below ~one thread-per-sample wave the 3000-step chain is latency bound and the
+    // CTA-per-sample kernel finishes sooner
+    bool use_tps = pl->fast && (hint == 1 || (hint == 0 && N >= 8192));
+    if (hint == 1 && !pl->fast)
+        return set_error(NLML_E_UNSUPPORTED, "thread-per-sample kernel is built for ranks (5,3,3,3) only");
+    if (use_tps) {
+        auto kern = tucker_fit_tps_kernel<5, 3, 3, 3, kTpsThreads, kTpsMinBlocks>;
+        const unsigned grid = (unsigned)ceil_div(N, kTpsThreads);
+        kern<<<grid, kTpsThreads, TpsDefault::SMEM_BYTES, st>>>(a);
+    } else {
+        auto kern = tucker_fit_cta_kernel<kCtaThreads>;
+        kern<<<(unsigned)N, kCtaThreads, pl->cta_smem, st>>>(a, pl->st_in_smem ? 1 : 0);
+    }
+    NLML_CUDA(cudaGetLastError());
+    pl->launches += 1;
+    return 0;
+}
+}  // namespace
+
+extern "C" int nlml_abi_version(void) { return NLML_ABI_VERSION; }
+extern "C" const char* nlml_last_error(void) { return last_error_buf(); }
+
+extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, int r_p, int r_r, int F,
+                                       const double* rows_y, const double* rows_p, const double* rows_r,
+                                       int device, nlml_tucker_plan** plan_out) {
+    if (!W_host || !rows_y || !rows_p || !rows_r || !plan_out)
+        return set_error(NLML_E_INVALID, "null pointer argument");
+    if (r_id < 1 || r_y < 1 || r_p < 1 || r_r < 1 || F < 1)
+        return set_error(NLML_E_INVALID, "ranks and F must be positive");
+    if (r_id > kMaxModeRank || r_y > kMaxModeRank || r_p > kMaxModeRank || r_r > kMaxModeRank)
+        return set_error(NLML_E_UNSUPPORTED, "per-mode rank limit is %d", kMaxModeRank);
+    if (int rc = check_device(device)) return rc;
+    DeviceGuard guard(device);
+    if (!guard.ok) return set_error(NLML_E_NO_DEVICE, "cudaSetDevice(%d) failed", device);
+
+    auto* pl = new nlml_tucker_plan();
+    pl->device = device;
+    pl->ri = r_id; pl->ry = r_y; pl->rp = r_p; pl->rr = r_r; pl->F = F;
+    pl->R = r_id * r_y * r_p * r_r;
+    pl->nA = tri(r_id);
+    pl->NAP = (pl->nA + 3) / 4 * 4;
+    pl->nBCD = tri(r_y) * tri(r_p) * tri(r_r);
+    pl->nBCDp = (pl->nBCD + 31) / 32 * 32;
+    if (pl->nBCD > kMaxBCD) {
+        delete pl;
+        return set_error(NLML_E_UNSUPPORTED, "angle-mode ranks (%d,%d,%d) give %d folded entries per identity pair; limit %d",
+                         r_y, r_p, r_r, tri(r_y) * tri(r_p) * tri(r_r), kMaxBCD);
+    }
+    cudaDeviceProp prop;
+    NLML_CUDA(cudaGetDeviceProperties(&prop, device));
+    pl->num_sms = prop.multiProcessorCount;
+
+    const size_t w_bytes = sizeof(float) * (size_t)pl->R * F;
+    double* M = nullptr;
+    NLML_CUDA(cudaMalloc(&pl->W2, w_bytes));
+    NLML_CUDA(cudaMalloc(&pl->S, sizeof(float) * (size_t)pl->nBCD * pl->NAP));
+    NLML_CUDA(cudaMalloc(&pl->St, sizeof(float) * (size_t)pl->nA * pl->nBCDp));
+    NLML_CUDA(cudaMalloc(&M, sizeof(double) * (size_t)pl->R * pl->R));
+    NLML_CUDA(cudaMemcpy(pl->W2, W_host, w_bytes, cudaMemcpyHostToDevice));
+    NLML_CUDA(cudaMemset(pl->S, 0, sizeof(float) * (size_t)pl->nBCD * pl->NAP));
+    NLML_CUDA(cudaMemset(pl->St, 0, sizeof(float) * (size_t)pl->nA * pl->nBCDp));
+    {
+        const int n = pl->R * pl->R;
+        gram_kernel<<<(n + 127) / 128, 128>>>(pl->W2, pl->R, F, M);
+        const int m = pl->nA * pl->nBCD;
+        fold_kernel<<<(m + 127) / 128, 128>>>(M, r_id, r_y, r_p, r_r, pl->NAP, pl->nBCDp, pl->S, pl->St);
+        NLML_CUDA(cudaGetLastError());
+        NLML_CUDA(cudaDeviceSynchronize());
+        pl->launches += 2;
+    }
+    NLML_CUDA(cudaFree(M));
+
+    TuckerArgs& a = pl->base;
+    a.W2 = pl->W2; a.S = pl->S; a.St = pl->St;
+    a.F = F; a.ri = r_id; a.ry = r_y; a.rp = r_p; a.rr = r_r; a.nBCDp = pl->nBCDp;
+    for (int j = 0; j < 4 * r_y; ++j) a.rows_y[j] = (float)rows_y[j];  // f64 -> f32, TD_Tester.py:172-174
+    for (int j = 0; j < 4 * r_p; ++j) a.rows_p[j] = (float)rows_p[j];
+    for (int j = 0; j < 4 * r_r; ++j) a.rows_r[j] = (float)rows_r[j];
+
+    pl->fast = (r_id == 5 && r_y == 3 && r_p == 3 && r_r == 3);
+    if (pl->fast) {
+        auto kern = tucker_fit_tps_kernel<5, 3, 3, 3, kTpsThreads, kTpsMinBlocks>;
+        NLML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpsDefault::SMEM_BYTES));
+    }
+    {
+        const size_t with_st = sizeof(float) * cta_layout(F, pl->R, pl->nBCD, pl->nA, pl->nBCDp, true).total;
+        pl->st_in_smem = with_st <= 96 * 1024;
+        pl->cta_smem = sizeof(float) * cta_layout(F, pl->R, pl->nBCD, pl->nA, pl->nBCDp, pl->st_in_smem).total;
+        if (pl->cta_smem > 220 * 1024) {
+            nlml_tucker_plan_destroy(pl);
+            return set_error(NLML_E_UNSUPPORTED, "core too large for the CTA kernel's shared-memory working set");
+        }
+        NLML_CUDA(cudaFuncSetAttribute(tucker_fit_cta_kernel<kCtaThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)pl->cta_smem));
+    }
+    *plan_out = pl;
+    return 0;
+}
+
+extern "C" void nlml_tucker_plan_destroy(nlml_tucker_plan* pl) {
+    if (!pl) return;
+    DeviceGuard guard(pl->device);
+    for (int i = 0; i < 2; ++i) {
+        if (pl->streams[i]) cudaStreamDestroy(pl->streams[i]);
+        cudaFree(pl->x_dev[i]);
+        cudaFree(pl->p_dev[i]);
+    }
+    cudaFree(pl->W2);
+    cudaFree(pl->S);
+    cudaFree(pl->St);
+    delete pl;
+}
+
+extern "C" int nlml_tucker_fit_f32(nlml_tucker_plan* pl, const float* X_dev, int64_t N, int64_t ldx, int iters,
+                                   float lr, float clip, float* P_out_dev, int64_t ldp, int kernel_hint,
+                                   void* stream) {
+    if (!pl || (N > 0 && (!X_dev || !P_out_dev))) return set_error(NLML_E_INVALID, "null pointer argument");
+    if (N < 0 || ldx < pl->F || ldp < 3 + pl->ri || iters < 0)
+        return set_error(NLML_E_INVALID, "bad sizes: N=%lld ldx=%lld (F=%d) ldp=%lld (need >= %d) iters=%d",
+                         (long long)N, (long long)ldx, pl->F, (long long)ldp, 3 + pl->ri, iters);
+    if (kernel_hint < 0 || kernel_hint > 2) return set_error(NLML_E_INVALID, "kernel_hint must be 0, 1 or 2");
+    DeviceGuard guard(pl->device);
+    return launch_fit(pl, X_dev, N, ldx, iters, lr, clip, P_out_dev, ldp, kernel_hint, (cudaStream_t)stream);
+}
+
+extern "C" int nlml_tucker_fit_host_f32(nlml_tucker_plan* pl, const float* X_host, int64_t N, int64_t ldx,
+                                        int iters, float lr, float clip, float* P_out_host, int64_t ldp) {
+    if (!pl || (N > 0 && (!X_host || !P_out_host))) return set_error(NLML_E_INVALID, "null pointer argument");
+    if (N < 0 || ldx < pl->F || ldp < 3 + pl->ri || iters < 0) return set_error(NLML_E_INVALID, "bad sizes");
+    DeviceGuard guard(pl->device);
+    const int np = 3 + pl->ri;
+    if (!pl->streams[0]) {
+        // two thread-per-sample waves per chunk keeps every SM busy while the next chunk is in flight
+        pl->chunk = (int64_t)pl->num_sms * kTpsMinBlocks * kTpsThreads * 2;
+        for (int i = 0; i < 2; ++i) {
+            NLML_CUDA(cudaStreamCreateWithFlags(&pl->streams[i], cudaStreamNonBlocking));
+            NLML_CUDA(cudaMalloc(&pl->x_dev[i], sizeof(float) * (size_t)pl->chunk * pl->F));
+            NLML_CUDA(cudaMalloc(&pl->p_dev[i], sizeof(float) * (size_t)pl->chunk * np));
+        }
+    }
+    int slot = 0;
+    for (int64_t s0 = 0; s0 < N; s0 += pl->chunk, slot ^= 1) {
+        const int64_t n = std::min<int64_t>(pl->chunk, N - s0);
+        cudaStream_t st = pl->streams[slot];
+        // stream order makes the reuse of this slot's buffers safe (previous chunk on the same stream is done)
+        NLML_CUDA(cudaMemcpy2DAsync(pl->x_dev[slot], sizeof(float) * pl->F, X_host + s0 * ldx, sizeof(float) * ldx,
+                                    sizeof(float) * pl->F, (size_t)n, cudaMemcpyHostToDevice, st));
+        if (int rc = launch_fit(pl, pl->x_dev[slot], n, pl->F, iters, lr, clip, pl->p_dev[slot], np, 0, st)) return rc;
+        NLML_CUDA(cudaMemcpy2DAsync(P_out_host + s0 * ldp, sizeof(float) * ldp, pl->p_dev[slot], sizeof(float) * np,
+                                    sizeof(float) * np, (size_t)n, cudaMemcpyDeviceToHost, st));
+    }
+    NLML_CUDA(cudaStreamSynchronize(pl->streams[0]));
+    NLML_CUDA(cudaStreamSynchronize(pl->streams[1]));
+    return 0;
+}
+
+extern "C" int64_t nlml_tucker_launch_count(const nlml_tucker_plan* pl) { return pl ? pl->launches : 0; }
+
+extern "C" int nlml_measure_fp32_tflops(int device, double* tflops_out) {
+    if (!tflops_out) return set_error(NLML_E_INVALID, "null pointer argument");
+    if (int rc = check_device(device)) return rc;
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    NLML_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    float* out = nullptr;
+    NLML_CUDA(cudaMalloc(&out, sizeof(float) * blocks * threads));
+    cudaEvent_t e0, e1;
+    NLML_CUDA(cudaEventCreate(&e0));
+    NLML_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        NLML_CUDA(cudaEventRecord(e0));
+        ffma_peak_kernel<<<blocks, threads>>>(out, iters);
+        NLML_CUDA(cudaEventRecord(e1));
+        NLML_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        NLML_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops_out = best;
+    return 0;
+}

@@ -1,0 +1,70 @@
+"""CPU oracle for the Encoder + yaw/pitch/roll MLP-heads half of the hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+leg may import this; the product (nlml_hpe_b200/) never does.
+
+Parity status: PINNED -- `forward` is checked in tests/test_oracle.py against the real
+reference classes (LandmarkEncoder / AnglePredictionNetwork / CombinedAnglePredictionModel,
+eager and torch.jit.script) run in the build container by tests/golden/make_golden.py on the
+shipped models/{yaw,pitch,roll}_network.pth plus the synthetic encoder (models/Encoder.pth is
+missing from the checkout, .MISSING_LARGE_BLOBS:4).  Outputs committed under tests/golden/.
+
+What is restated (file:line into /root/reference/NLML_HPE_Model_Builder.py):
+  encoder stack   :33-53   Linear 1404-1024-512-256-128-64-9, ReLU x4, Tanh, none
+  latent split    :55-68   latent[:,0:3], [:,3:6], [:,6:9]  (matrix_dims [(1,3)]*3, squeeze(1) :118-120)
+  head stack      :76-92   Linear 3-128-256-128-64-1, ReLU x4, none
+  combined        :115-126 returns (yaw, pitch, roll), each [B,1], radians
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ENCODER_KEYS = [f"encoder.{i}" for i in (0, 2, 4, 6, 8, 10)]
+HEAD_KEYS = [f"model.{i}" for i in (0, 2, 4, 6, 8)]
+
+
+def _t(a, dtype):
+    return torch.as_tensor(np.asarray(a)).to(dtype)
+
+
+def forward(encoder_sd, yaw_sd, pitch_sd, roll_sd, X, dtype=torch.float32, threads=None):
+    """X [B,1404] -> angles [B,3] (yaw, pitch, roll) radians, on CPU in `dtype`.
+
+    dtype=float32 is the reference arithmetic (torch.nn.Linear on CPU); float64 gives the
+    error-budget reference used to state tolerances.
+    """
+    if threads is not None:
+        torch.set_num_threads(threads)
+    with torch.no_grad():
+        h = _t(X, dtype)
+        for li, key in enumerate(ENCODER_KEYS):
+            h = F.linear(h, _t(encoder_sd[key + ".weight"], dtype), _t(encoder_sd[key + ".bias"], dtype))
+            if li < 4:
+                h = torch.relu(h)
+            elif li == 4:
+                h = torch.tanh(h)
+        outs = []
+        for hi, sd in enumerate((yaw_sd, pitch_sd, roll_sd)):
+            width = _t(sd["model.0.weight"], dtype).shape[1]
+            g = h[:, hi * width:(hi + 1) * width]
+            for li, key in enumerate(HEAD_KEYS):
+                g = F.linear(g, _t(sd[key + ".weight"], dtype), _t(sd[key + ".bias"], dtype))
+                if li < 4:
+                    g = torch.relu(g)
+            outs.append(g)
+        return torch.cat(outs, 1).numpy()
+
+
+def latent(encoder_sd, X, dtype=torch.float32):
+    """Encoder output [B,9] only (for intermediate-stage checks)."""
+    with torch.no_grad():
+        h = _t(X, dtype)
+        for li, key in enumerate(ENCODER_KEYS):
+            h = F.linear(h, _t(encoder_sd[key + ".weight"], dtype), _t(encoder_sd[key + ".bias"], dtype))
+            if li < 4:
+                h = torch.relu(h)
+            elif li == 4:
+                h = torch.tanh(h)
+        return h.numpy()

@@ -1,0 +1,74 @@
+// Host build of the per-sample Tucker-fit arithmetic (nlml_hpe_b200/csrc/tucker_math.h).
+// TEST INFRASTRUCTURE ONLY: lets the CPU-only test tier execute the very statements the CUDA
+// kernels run (folded Gram tensor, gradient, clip, step) against the reference goldens.
+// The product never loads this library.
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "../../nlml_hpe_b200/csrc/tucker_math.h"
+
+using namespace nlml;
+
+extern "C" int hostcheck_tucker_fit_5333(const float* W2, int F, const double* rows_y, const double* rows_p,
+                                         const double* rows_r, const float* X, int64_t N, int64_t ldx, int T,
+                                         float lr, float clip, float* P /*[N][8]*/) {
+    constexpr int RI = 5, RY = 3, RP = 3, RR = 3, R = RI * RY * RP * RR, NP = 3 + RI;
+    constexpr int nA = tri(RI), NAP = (nA + 3) / 4 * 4, nBCD = tri(RY) * tri(RP) * tri(RR);
+    std::vector<double> M((size_t)R * R);
+    for (int r = 0; r < R; ++r)
+        for (int c = r; c < R; ++c) M[(size_t)r * R + c] = M[(size_t)c * R + r] = gram_entry(W2, F, r, c);
+    std::vector<float> S((size_t)nBCD * NAP, 0.f);
+    for (int a = 0; a < nA; ++a)
+        for (int b = 0; b < tri(RY); ++b)
+            for (int c = 0; c < tri(RP); ++c)
+                for (int d = 0; d < tri(RR); ++d)
+                    S[(size_t)((b * tri(RP) + c) * tri(RR) + d) * NAP + a] = fold_entry(M.data(), RI, RY, RP, RR, a, b, c, d);
+    float ry[12], rp[12], rr[12];
+    for (int i = 0; i < 12; ++i) { ry[i] = (float)rows_y[i]; rp[i] = (float)rows_p[i]; rr[i] = (float)rows_r[i]; }
+    for (int64_t s = 0; s < N; ++s) {
+        float q[R];
+        for (int r = 0; r < R; ++r) {
+            float acc = 0.f;
+            for (int f = 0; f < F; ++f) acc = fmaf(W2[(size_t)r * F + f], X[s * ldx + f], acc);
+            q[r] = acc;
+        }
+        float p[NP] = {0};
+        for (int it = 0; it < T; ++it) {
+            float g[NP];
+            tucker_gradient<RI, RY, RP, RR, NAP>(p, S.data(), q, 1, ry, rp, rr, g);
+            clip_and_step<NP>(p, g, lr, clip);
+        }
+        for (int i = 0; i < NP; ++i) P[s * NP + i] = p[i];
+    }
+    return 0;
+}
+
+// gradient only, at given parameter points (checked against autograd of the reference objective)
+extern "C" int hostcheck_tucker_grad_5333(const float* W2, int F, const double* rows_y, const double* rows_p,
+                                          const double* rows_r, const float* X, int64_t N, int64_t ldx,
+                                          const float* Pin /*[N][8]*/, float* G /*[N][8]*/) {
+    constexpr int RI = 5, RY = 3, RP = 3, RR = 3, R = RI * RY * RP * RR, NP = 3 + RI;
+    constexpr int nA = tri(RI), NAP = (nA + 3) / 4 * 4, nBCD = tri(RY) * tri(RP) * tri(RR);
+    std::vector<double> M((size_t)R * R);
+    for (int r = 0; r < R; ++r)
+        for (int c = r; c < R; ++c) M[(size_t)r * R + c] = M[(size_t)c * R + r] = gram_entry(W2, F, r, c);
+    std::vector<float> S((size_t)nBCD * NAP, 0.f);
+    for (int a = 0; a < nA; ++a)
+        for (int b = 0; b < tri(RY); ++b)
+            for (int c = 0; c < tri(RP); ++c)
+                for (int d = 0; d < tri(RR); ++d)
+                    S[(size_t)((b * tri(RP) + c) * tri(RR) + d) * NAP + a] = fold_entry(M.data(), RI, RY, RP, RR, a, b, c, d);
+    float ry[12], rp[12], rr[12];
+    for (int i = 0; i < 12; ++i) { ry[i] = (float)rows_y[i]; rp[i] = (float)rows_p[i]; rr[i] = (float)rows_r[i]; }
+    for (int64_t s = 0; s < N; ++s) {
+        float q[R];
+        for (int r = 0; r < R; ++r) {
+            float acc = 0.f;
+            for (int f = 0; f < F; ++f) acc = fmaf(W2[(size_t)r * F + f], X[s * ldx + f], acc);
+            q[r] = acc;
+        }
+        tucker_gradient<RI, RY, RP, RR, NAP>(Pin + s * NP, S.data(), q, 1, ry, rp, rr, G + s * NP);
+    }
+    return 0;
+}

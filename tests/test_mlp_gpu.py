@@ -1,0 +1,114 @@
+"""Parity of the CUDA Encoder+heads forward (through the C ABI) with the reference goldens and the oracle.
+
+Tolerance (BASELINE.json north_star): <= 1e-3 degrees on the predicted Euler angles.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mlp_oracle
+
+pytestmark = pytest.mark.gpu
+DEG = 180.0 / np.pi
+TOL_DEG = 1e-3
+
+
+@pytest.fixture(scope="module")
+def model(state_dicts, cuda_lib):
+    from nlml_hpe_b200 import NLML_HPE_Model_Builder as MB
+    return MB.build_combined_model(*state_dicts)
+
+
+def _gpu(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def test_golden_1k(model, X1k, mlp_golden):
+    """BASELINE.json config 1: shipped heads (+ synthetic encoder) on 1k synthetic feature vectors."""
+    with torch.no_grad():
+        yaw, pitch, roll = model(_gpu(X1k))
+    assert yaw.shape == pitch.shape == roll.shape == (1000, 1) and yaw.is_cuda
+    out = torch.cat([yaw, pitch, roll], 1).cpu().numpy()
+    assert np.abs(out - mlp_golden["angles_jit"]).max() * DEG < TOL_DEG
+    assert np.abs(out - mlp_golden["angles_f64"]).max() * DEG < TOL_DEG   # and no further from exact than the reference
+
+
+def test_latent_stage(model, X1k, mlp_golden):
+    lat = model.latent(_gpu(X1k)).cpu().numpy()
+    assert np.abs(lat - mlp_golden["latent"]).max() < 2e-5
+
+
+def test_edge_inputs(model, mlp_golden):
+    out = model.predict(_gpu(mlp_golden["edge_X"])).cpu().numpy()
+    assert np.abs(out - mlp_golden["edge_angles"]).max() * DEG < TOL_DEG
+
+
+def test_reference_style_batch1_loop(model, X1k, mlp_golden):
+    """NLML_HPE_Test.py:326-328: one sample per call, .item(), degrees rounded to 3 decimals."""
+    from nlml_hpe_b200.NLML_HPE_Test import predict_degrees
+    for i in range(8):
+        x = torch.from_numpy(X1k[i]).unsqueeze(0).float().to("cuda")
+        with torch.no_grad():
+            y, p, r = model(x)
+        got = np.array([y.item(), p.item(), r.item()])
+        assert np.abs(got - mlp_golden["angles_b1"][i]).max() * DEG < TOL_DEG
+    tuples, keep = predict_degrees(model, np.concatenate([X1k[:4], np.zeros((1, 1404), np.float32)]))
+    assert len(tuples) == 4 and keep.tolist() == [True] * 4 + [False]
+    want = np.round(np.degrees(mlp_golden["angles_jit"][:4].astype(np.float64)), 3)
+    assert np.abs(np.array(tuples) - want).max() <= 2e-3
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 127, 128, 129, 1000])
+def test_ragged_batch_sizes(model, X1k, n):
+    full = model.predict(_gpu(X1k))
+    part = model.predict(_gpu(X1k[:n]))
+    assert part.shape == (n, 3)
+    if n:
+        assert (part - full[:n]).abs().max().item() * DEG < 1e-4
+
+
+def test_chunk_boundaries_and_oracle_fresh_seed(model, state_dicts, art, rows):
+    """More samples than one internal chunk (16384), fresh seed, checked against the oracle on a subset."""
+    from nlml_hpe_b200 import synthetic
+    X = synthetic.make_features(2048, art["W"], *rows, U_id=art["U_id"], seed=99)
+    big = _gpu(X).repeat(9, 1)[:16384 + 777].contiguous()
+    out = model.predict(big).cpu().numpy()
+    ref = mlp_oracle.forward(*state_dicts, X)
+    assert np.abs(out[:2048] - ref).max() * DEG < TOL_DEG
+    assert np.abs(out[16384:16384 + 777] - ref[:777]).max() * DEG < TOL_DEG
+
+
+def test_host_path_equals_device_path(model, X1k):
+    dev = model.predict(_gpu(X1k)).cpu().numpy()
+    host = model.predict_host(X1k)
+    assert np.array_equal(dev, host)
+    y, p, r = model(torch.from_numpy(X1k))          # CPU tensor in -> CPU tensors out, through the GPU
+    assert not y.is_cuda and np.array_equal(torch.cat([y, p, r], 1).numpy(), dev)
+
+
+def test_random_weights_and_inputs(cuda_lib):
+    """Not just the shipped weights: random nets, N(0,1) inputs, checked against the oracle."""
+    from nlml_hpe_b200 import NLML_HPE_Model_Builder as MB
+    torch.manual_seed(3)
+    enc = MB.LandmarkEncoder(1404, [(1, 3)] * 3)
+    heads = [MB.AnglePredictionNetwork(3) for _ in range(3)]
+    model = MB.CombinedAnglePredictionModel(enc, *heads).eval()
+    sds = [{k: v.numpy() for k, v in m.state_dict().items()} for m in (enc, *heads)]
+    X = torch.randn(513, 1404)
+    out = model.predict(X.cuda()).cpu().numpy()
+    ref = mlp_oracle.forward(*sds, X.numpy())
+    assert np.abs(out - ref).max() < 2e-5
+
+
+def test_full_size_properties_1M(model, art, rows):
+    """BASELINE.json config 3 size (1M vectors): periodic input => periodic output."""
+    from nlml_hpe_b200 import synthetic
+    n = 1_000_000
+    base = _gpu(synthetic.make_features(4096, art["W"], *rows, U_id=art["U_id"], seed=55))
+    X = base.repeat(n // 4096 + 1, 1)[:n].contiguous()
+    out = model.predict(X)
+    torch.cuda.synchronize()
+    small = model.predict(base)
+    assert out.shape == (n, 3) and torch.isfinite(out).all()
+    assert (out[:4096] - small).abs().max().item() * DEG < 1e-4
+    assert (out[4096 * 200:4096 * 201] - small).abs().max().item() * DEG < 1e-4
