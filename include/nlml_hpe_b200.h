@@ -54,7 +54,8 @@ void nlml_tucker_plan_destroy(nlml_tucker_plan* plan);
  * coefficients, exactly the vector optimize_with_sgd returns (TD_Tester.py:159).
  * iters / lr / clip are num_iterations, learning_rate (TD_Tester.py:127) and the max_norm of :150.
  * Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
- * kernel_hint: 0 = choose by N, 1 = force thread-per-sample kernel, 2 = force CTA-per-sample kernel. */
+ * kernel_hint: 0 = choose by N and ranks, 1 = thread-per-sample kernel (throughput, ranks 5,3,3,3),
+ * 2 = CTA-per-sample kernel (run-time ranks), 3 = warp-per-sample kernel (latency, ranks 5,3,3,3). */
 int nlml_tucker_fit_f32(nlml_tucker_plan* plan, const float* X_dev, int64_t N, int64_t ldx,
                         int iters, float lr, float clip, float* P_out_dev, int64_t ldp,
                         int kernel_hint, void* stream);

@@ -81,9 +81,10 @@ struct TpsCfg {
     static constexpr int XSTR = THREADS + 2;   // == 2 (mod 8): transposed tile stores are conflict-free
     static constexpr int S_FLOATS = nBCD * NAP;
     static constexpr int Q_FLOATS = R * THREADS;
+    static constexpr int SCR_FLOATS = tri(RY) * tri(RP) * THREADS;  // per-thread scratch column of tucker_gradient
     static constexpr int TILE_FLOATS = FC * XSTR + FC * RPAD;
     static_assert(TILE_FLOATS <= Q_FLOATS, "phase-A tiles alias the q buffer");
-    static constexpr size_t SMEM_BYTES = sizeof(float) * (S_FLOATS + Q_FLOATS);
+    static constexpr size_t SMEM_BYTES = sizeof(float) * (S_FLOATS + Q_FLOATS + SCR_FLOATS);
 };
 
 __device__ __forceinline__ float4 load_row4(const float* __restrict__ row, int f, int F, bool vec_ok) {
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(THREADS, MINB) tucker_fit_tps_kernel(const __g
     extern __shared__ __align__(16) float smem[];
     float* S_s = smem;
     float* q_s = smem + C::S_FLOATS;
+    float* scr_s = q_s + C::Q_FLOATS;
     float* xs = q_s;                     // [FC][XSTR]   (phase A only)
     float* ws = q_s + C::FC * C::XSTR;   // [FC][RPAD]   (phase A only)
 
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(THREADS, MINB) tucker_fit_tps_kernel(const __g
             ws[(4 * c4 + 3) * C::RPAD + r] = v.w;
         }
         __syncthreads();
-#pragma unroll
+#pragma unroll 4
         for (int f = 0; f < C::FC; ++f) {
             const float xv = xs[f * C::XSTR + tid];
 #pragma unroll
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(THREADS, MINB) tucker_fit_tps_kernel(const __g
 #pragma unroll 1
     for (int it = 0; it < a.T; ++it) {
         float g[C::NP];
-        tucker_gradient<RI, RY, RP, RR, C::NAP>(p, S_s, q_s + tid, THREADS, a.rows_y, a.rows_p, a.rows_r, g);
+        tucker_gradient<RI, RY, RP, RR, C::NAP>(p, S_s, q_s + tid, THREADS, scr_s + tid, THREADS, a.rows_y, a.rows_p, a.rows_r, g);
         clip_and_step<C::NP>(p, g, lr, clip);
     }
     if (s0 + tid < a.N) {
@@ -406,6 +408,190 @@ __global__ void __launch_bounds__(THREADS) tucker_fit_cta_kernel(const __grid_co
     if (tid < NP) a.P[s * a.ldp + tid] = p[tid];
 }
 
+// ---------------------------------------------------------------------------------------------
+// warp-per-sample kernel (compile-time ranks): the small-batch / single-image case.
+// The 3000-step chain is a latency problem there, so one sample is spread over the 32 lanes of a warp:
+// the folded Gram tensor lives in REGISTERS (each lane owns 7 of the 216 (b,c,d) rows), every lane keeps
+// an identical copy of p, partial gradients are combined with one xor-butterfly of 8 values per step
+// (bitwise identical in all lanes), and nothing but two tiny per-warp tables touches shared memory.
+// ---------------------------------------------------------------------------------------------
+template <int RI, int RY, int RP, int RR, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) tucker_fit_wps_kernel(const __grid_constant__ TuckerArgs a) {
+    constexpr int R = RI * RY * RP * RR, NP = 3 + RI;
+    constexpr int nA = tri(RI), NAP = (nA + 3) / 4 * 4, nB = tri(RY), nC = tri(RP), nD = tri(RR);
+    constexpr int nBCD = nB * nC * nD, ROWS = (nBCD + 31) / 32, JKL = RY * RP * RR;
+    constexpr int NANG = RY + RP + RR, NPAIR = nB + nC + nD;
+    static_assert(JKL <= 32 && NANG <= 32 && NPAIR <= 32, "one lane per angle-mode entry");
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int F = a.F, Fp = (F + 3) / 4 * 4;
+    static_assert(2 * NANG + 2 * NPAIR <= 64, "table space");
+    float* xb = smem + warp * (Fp + 64);  // this warp's x row (16B aligned), then its two tables
+    float* fac = xb + Fp;          // [2*NANG]: c_y,c_p,c_r then dc_y,dc_p,dc_r
+    float* tab = fac + 2 * NANG;   // [2*NPAIR]: YY,PP,RR then dYY/dw_y, dPP/dw_p, dRR/dw_r
+    const long long s = (long long)blockIdx.x * WARPS + warp;
+    const bool live = s < a.N;     // warp-uniform
+
+    // ---- static per-lane roles ----
+    // (i) cosine row of lanes < NANG
+    float ra = 0.f, rb = 0.f, rc = 0.f, rd = 0.f;
+    int my_angle = 0;
+    if (lane < NANG) {
+        const float* rows = lane < RY ? a.rows_y + 4 * lane
+                          : lane < RY + RP ? a.rows_p + 4 * (lane - RY) : a.rows_r + 4 * (lane - RY - RP);
+        ra = rows[0]; rb = rows[1]; rc = rows[2]; rd = rows[3];
+        my_angle = lane < RY ? 0 : (lane < RY + RP ? 1 : 2);
+    }
+    // (ii) symmetric pair of lanes < NPAIR (index into fac[])
+    int pj0 = 0, pj1 = 0;
+    if (lane < NPAIR) {
+        int m = lane < nB ? 0 : (lane < nB + nC ? 1 : 2);
+        int e = lane - (m == 0 ? 0 : (m == 1 ? nB : nB + nC));
+        int r = m == 0 ? RY : (m == 1 ? RP : RR), base = m == 0 ? 0 : (m == 1 ? RY : RY + RP);
+        int i, j;
+        unpair(e, r, &i, &j);
+        pj0 = base + i; pj1 = base + j;
+    }
+    // (iii) the lane's rows of the folded Gram tensor and their (b,c,d)
+    float Srow[ROWS][nA];
+    int rb_[ROWS], rc_[ROWS], rd_[ROWS];
+#pragma unroll
+    for (int m = 0; m < ROWS; ++m) {
+        const int bcd = lane + 32 * m;
+        const bool ok = bcd < nBCD;
+        rb_[m] = ok ? bcd / (nC * nD) : 0;
+        rc_[m] = ok ? nB + (bcd / nD) % nC : 0;
+        rd_[m] = ok ? nB + nC + bcd % nD : 0;
+#pragma unroll
+        for (int aa = 0; aa < nA; ++aa) Srow[m][aa] = ok ? __ldg(a.S + (long long)bcd * NAP + aa) : 0.f;
+    }
+    // (iv) linear-term role of lanes < JKL: entry (j,k,l) and q[i][jkl]
+    const int lj = lane < JKL ? lane / (RP * RR) : 0, lk = lane < JKL ? RY + (lane / RR) % RP : 0,
+              ll = lane < JKL ? RY + RP + lane % RR : 0;
+    float q[RI];
+#pragma unroll
+    for (int i = 0; i < RI; ++i) q[i] = 0.f;
+
+    // ---- phase A: q = W2 x (warp-cooperative dot products, x staged in shared memory) ----
+    if (live) {
+        const float* xrow = a.X + s * a.ldx;
+        for (int f = lane; f < Fp; f += 32) xb[f] = f < F ? __ldg(xrow + f) : 0.f;
+    }
+    __syncwarp();
+    if (live) {
+        for (int jkl = 0; jkl < JKL; ++jkl) {
+#pragma unroll
+            for (int i = 0; i < RI; ++i) {
+                const float* wrow = a.W2 + (long long)(i * JKL + jkl) * F;
+                float acc = 0.f;
+                if (a.vec_ok) {
+                    for (int f = 4 * lane; f < F; f += 128) {
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + f));
+                        const float4 x = *reinterpret_cast<const float4*>(xb + f);
+                        acc = fmaf(w.x, x.x, acc); acc = fmaf(w.y, x.y, acc);
+                        acc = fmaf(w.z, x.z, acc); acc = fmaf(w.w, x.w, acc);
+                    }
+                } else {
+                    for (int f = lane; f < F; f += 32) acc = fmaf(__ldg(wrow + f), xb[f], acc);
+                }
+                acc = warp_sum(acc);
+                if (lane == jkl) q[i] = acc;
+            }
+        }
+    }
+
+    // ---- phase B ----
+    float p[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) p[i] = 0.f;  // zero init, TD_Tester.py:130
+    const float lr = a.lr, clip = a.clip;
+    const int T = live ? a.T : 0;
+#pragma unroll 1
+    for (int it = 0; it < T; ++it) {
+        // cosine features: lane j < NANG evaluates row j once, shares through the per-warp table
+        {
+            const float w = my_angle == 0 ? p[0] : (my_angle == 1 ? p[1] : p[2]);
+            float sn, cs;
+            sincosf(rb * w + rc, &sn, &cs);
+            if (lane < NANG) {
+                fac[lane] = ra * cs + rd;
+                fac[NANG + lane] = -(ra * rb) * sn;
+            }
+        }
+        __syncwarp();
+        if (lane < NPAIR) {
+            const float x0 = fac[pj0], x1 = fac[pj1], d0 = fac[NANG + pj0], d1 = fac[NANG + pj1];
+            tab[lane] = x0 * x1;
+            tab[NPAIR + lane] = fmaf(d0, x1, x0 * d1);   // d(x0*x1)/dw
+        }
+        __syncwarp();
+        float u[RI], UU[nA];
+#pragma unroll
+        for (int i = 0; i < RI; ++i) u[i] = p[3 + i];
+        sym_products<RI>(u, UU);
+
+        float GU[nA];
+#pragma unroll
+        for (int aa = 0; aa < nA; ++aa) GU[aa] = 0.f;
+        float g[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) g[i] = 0.f;
+#pragma unroll
+        for (int m = 0; m < ROWS; ++m) {
+            const float y = tab[rb_[m]], pp = tab[rc_[m]], r = tab[rd_[m]];
+            const float dy = tab[NPAIR + rb_[m]], dp = tab[NPAIR + rc_[m]], dr = tab[NPAIR + rd_[m]];
+            const float ypr = y * pp * r;
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int aa = 0; aa < nA; ++aa) {
+                const float sv = Srow[m][aa];
+                if (aa % 3 == 0) t0 = fmaf(sv, UU[aa], t0);
+                else if (aa % 3 == 1) t1 = fmaf(sv, UU[aa], t1);
+                else t2 = fmaf(sv, UU[aa], t2);
+                GU[aa] = fmaf(sv, ypr, GU[aa]);
+            }
+            const float t = (t0 + t1) + t2;
+            g[0] = fmaf(t, dy * pp * r, g[0]);
+            g[1] = fmaf(t, y * dp * r, g[1]);
+            g[2] = fmaf(t, y * pp * dr, g[2]);
+        }
+        {
+            float du[RI];
+            sym_backprop<RI>(GU, u, du);
+#pragma unroll
+            for (int i = 0; i < RI; ++i) g[3 + i] = du[i];
+        }
+        // linear term -q.z : lane jkl owns q[:, jkl]
+        {
+            const float cyj = fac[lj], cpk = fac[lk], crl = fac[ll];
+            const float dyj = fac[NANG + lj], dpk = fac[NANG + lk], drl = fac[NANG + ll];
+            const float tj = cyj * cpk * crl;
+            float e = 0.f;
+#pragma unroll
+            for (int i = 0; i < RI; ++i) {
+                e = fmaf(u[i], q[i], e);
+                g[3 + i] = fmaf(-q[i], tj, g[3 + i]);
+            }
+            g[0] = fmaf(-e, dyj * cpk * crl, g[0]);
+            g[1] = fmaf(-e, cyj * dpk * crl, g[1]);
+            g[2] = fmaf(-e, cyj * cpk * drl, g[2]);
+        }
+        // xor butterfly: every lane ends with the same bits (fp add commutes, pairs swap operands)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < NP; ++i) g[i] += __shfl_xor_sync(0xffffffffu, g[i], o);
+        clip_and_step<NP>(p, g, lr, clip);
+        __syncwarp();   // tables are rewritten next step
+    }
+    if (live && lane < NP) {
+        float v = p[0];
+#pragma unroll
+        for (int i = 1; i < NP; ++i) v = lane == i ? p[i] : v;
+        a.P[s * a.ldp + lane] = v;
+    }
+}
+
 // register-only FFMA loop: measures the sustained FP32 FMA rate used as a roofline denominator
 __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
@@ -453,7 +639,10 @@ namespace {
 constexpr int kTpsThreads = 128;
 constexpr int kTpsMinBlocks = 2;
 constexpr int kCtaThreads = 128;
+constexpr int kWpsWarps = 4;
+constexpr int64_t kWpsCrossover = 8192;  // below this the warp-per-sample kernel finishes sooner (profiles/)
 using TpsDefault = TpsCfg<5, 3, 3, 3, kTpsThreads>;
+size_t wps_smem_bytes(int F) { return sizeof(float) * kWpsWarps * ((F + 3) / 4 * 4 + 64); }
 
 int launch_fit(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int iters, float lr, float clip,
                float* P, int64_t ldp, int hint, cudaStream_t st) {
@@ -470,10 +659,15 @@ int launch_fit(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int
     a.vec_ok = (pl->F % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
     // crossover: below ~one thread-per-sample wave the 3000-step chain is latency bound and the
     // CTA-per-sample kernel finishes sooner
-    bool use_tps = pl->fast && (hint == 1 || (hint == 0 && N >= 8192));
-    if (hint == 1 && !pl->fast)
-        return set_error(NLML_E_UNSUPPORTED, "thread-per-sample kernel is built for ranks (5,3,3,3) only");
-    if (use_tps) {
+    const bool use_tps = pl->fast && (hint == 1 || (hint == 0 && N >= kWpsCrossover));
+    const bool use_wps = pl->fast && (hint == 3 || (hint == 0 && N < kWpsCrossover));
+    if ((hint == 1 || hint == 3) && !pl->fast)
+        return set_error(NLML_E_UNSUPPORTED, "thread/warp-per-sample kernels are built for ranks (5,3,3,3) only");
+    if (use_wps) {
+        auto kern = tucker_fit_wps_kernel<5, 3, 3, 3, kWpsWarps>;
+        const unsigned grid = (unsigned)ceil_div(N, kWpsWarps);
+        kern<<<grid, 32 * kWpsWarps, wps_smem_bytes(pl->F), st>>>(a);
+    } else if (use_tps) {
         auto kern = tucker_fit_tps_kernel<5, 3, 3, 3, kTpsThreads, kTpsMinBlocks>;
         const unsigned grid = (unsigned)ceil_div(N, kTpsThreads);
         kern<<<grid, kTpsThreads, TpsDefault::SMEM_BYTES, st>>>(a);
@@ -551,6 +745,10 @@ extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, i
     if (pl->fast) {
         auto kern = tucker_fit_tps_kernel<5, 3, 3, 3, kTpsThreads, kTpsMinBlocks>;
         NLML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpsDefault::SMEM_BYTES));
+        if (wps_smem_bytes(F) > 200 * 1024) pl->fast = false;
+        else
+            NLML_CUDA(cudaFuncSetAttribute(tucker_fit_wps_kernel<5, 3, 3, 3, kWpsWarps>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wps_smem_bytes(F)));
     }
     {
         const size_t with_st = sizeof(float) * cta_layout(F, pl->R, pl->nBCD, pl->nA, pl->nBCDp, true).total;
@@ -588,7 +786,7 @@ extern "C" int nlml_tucker_fit_f32(nlml_tucker_plan* pl, const float* X_dev, int
     if (N < 0 || ldx < pl->F || ldp < 3 + pl->ri || iters < 0)
         return set_error(NLML_E_INVALID, "bad sizes: N=%lld ldx=%lld (F=%d) ldp=%lld (need >= %d) iters=%d",
                          (long long)N, (long long)ldx, pl->F, (long long)ldp, 3 + pl->ri, iters);
-    if (kernel_hint < 0 || kernel_hint > 2) return set_error(NLML_E_INVALID, "kernel_hint must be 0, 1 or 2");
+    if (kernel_hint < 0 || kernel_hint > 3) return set_error(NLML_E_INVALID, "kernel_hint must be 0..3");
     DeviceGuard guard(pl->device);
     return launch_fit(pl, X_dev, N, ldx, iters, lr, clip, P_out_dev, ldp, kernel_hint, (cudaStream_t)stream);
 }

@@ -111,10 +111,12 @@ NLML_HD void clip_and_step(float* p, float* g, float lr, float clip) {
 //   S : folded Gram tensor laid out [nB*nC*nD][NAP] (NAP = nA padded to a multiple of 4), read-only,
 //       identical for all samples (shared-memory broadcast on the GPU).
 //   q : this sample's q = W2 x, element r at q[r*qstride].
+//   scr : nB*nC floats of per-sample scratch, element k at scr[k*sstride] (a shared-memory column on the GPU).
 //   rows_* : cosine rows of the three angle factors.
 // Writes g[3+RI].
 template <int RI, int RY, int RP, int RR, int NAP>
 NLML_HD void tucker_gradient(const float* p, const float* __restrict__ S, const float* q, int qstride,
+                             float* scr, int sstride,
                              const float* rows_y, const float* rows_p, const float* rows_r, float* g) {
     constexpr int nA = tri(RI), nB = tri(RY), nC = tri(RP), nD = tri(RR);
     float cy[RY], dcy[RY], cp[RP], dcp[RP], cr[RR], dcr[RR], u[RI];
@@ -140,31 +142,46 @@ NLML_HD void tucker_gradient(const float* p, const float* __restrict__ S, const 
 #pragma unroll
     for (int d = 0; d < nD; ++d) GR[d] = 0.f;
 
-    // quadratic term: one pass over S feeds both contractions
+    // quadratic term: one pass over S feeds both contractions.  The (b,c) loop is a REAL loop (36 trips at
+    // ranks 3,3) so its body stays inside the instruction cache; the per-thread values indexed by the loop
+    // counter (YY_b*PP_c in, sum_d T[b,c,d]*RR_d out) go through the caller's scratch column instead of
+    // registers.  The T dot product is split in three chains to shorten the dependent-FMA latency.
 #pragma unroll
-    for (int b = 0; b < nB; ++b) {
+    for (int b = 0; b < nB; ++b)
+#pragma unroll
+        for (int c = 0; c < nC; ++c) scr[(b * nC + c) * sstride] = YY[b] * PP[c];
+#pragma unroll 1
+    for (int bc = 0; bc < nB * nC; ++bc) {
+        const float yp = scr[bc * sstride];
+        const float* __restrict__ rows = S + bc * (nD * NAP);
+        float tr = 0.f;  // sum_d T[b,c,d] * RR_d
+#pragma unroll
+        for (int d = 0; d < nD; ++d) {
+            const float* __restrict__ row = rows + d * NAP;
+            const float ypr = yp * RRv[d];
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int a = 0; a < nA; ++a) {
+                const float s = row[a];
+                if (a % 3 == 0) t0 = fmaf(s, UU[a], t0);
+                else if (a % 3 == 1) t1 = fmaf(s, UU[a], t1);
+                else t2 = fmaf(s, UU[a], t2);
+                GU[a] = fmaf(s, ypr, GU[a]);
+            }
+            const float t = (t0 + t1) + t2;
+            GR[d] = fmaf(t, yp, GR[d]);
+            tr = fmaf(t, RRv[d], tr);
+        }
+        scr[bc * sstride] = tr;
+    }
+#pragma unroll
+    for (int b = 0; b < nB; ++b)
 #pragma unroll
         for (int c = 0; c < nC; ++c) {
-            const float yp = YY[b] * PP[c];
-            float tr = 0.f;  // sum_d T[b,c,d] * RR_d
-#pragma unroll
-            for (int d = 0; d < nD; ++d) {
-                const float* __restrict__ row = S + ((b * nC + c) * nD + d) * NAP;
-                const float ypr = yp * RRv[d];
-                float t = 0.f;
-#pragma unroll
-                for (int a = 0; a < nA; ++a) {
-                    const float s = row[a];
-                    t = fmaf(s, UU[a], t);
-                    GU[a] = fmaf(s, ypr, GU[a]);
-                }
-                GR[d] = fmaf(t, yp, GR[d]);
-                tr = fmaf(t, RRv[d], tr);
-            }
+            const float tr = scr[(b * nC + c) * sstride];
             GY[b] = fmaf(tr, PP[c], GY[b]);
             GP[c] = fmaf(tr, YY[b], GP[c]);
         }
-    }
     float du[RI], dy[RY], dp[RP], dr[RR];
     sym_backprop<RI>(GU, u, du);
     sym_backprop<RY>(GY, cy, dy);

@@ -36,7 +36,8 @@ extern "C" int hostcheck_tucker_fit_5333(const float* W2, int F, const double* r
         float p[NP] = {0};
         for (int it = 0; it < T; ++it) {
             float g[NP];
-            tucker_gradient<RI, RY, RP, RR, NAP>(p, S.data(), q, 1, ry, rp, rr, g);
+            float scr[tri(RY) * tri(RP)];
+            tucker_gradient<RI, RY, RP, RR, NAP>(p, S.data(), q, 1, scr, 1, ry, rp, rr, g);
             clip_and_step<NP>(p, g, lr, clip);
         }
         for (int i = 0; i < NP; ++i) P[s * NP + i] = p[i];
@@ -68,7 +69,8 @@ extern "C" int hostcheck_tucker_grad_5333(const float* W2, int F, const double* 
             for (int f = 0; f < F; ++f) acc = fmaf(W2[(size_t)r * F + f], X[s * ldx + f], acc);
             q[r] = acc;
         }
-        tucker_gradient<RI, RY, RP, RR, NAP>(Pin + s * NP, S.data(), q, 1, ry, rp, rr, G + s * NP);
+        float scr[tri(RY) * tri(RP)];
+        tucker_gradient<RI, RY, RP, RR, NAP>(Pin + s * NP, S.data(), q, 1, scr, 1, ry, rp, rr, G + s * NP);
     }
     return 0;
 }
