@@ -99,6 +99,10 @@ int nlml_mlp_forward_host_f32(nlml_mlp_plan* plan, const float* X_host, int64_t 
 int nlml_mlp_latent_f32(nlml_mlp_plan* plan, const float* X_dev, int64_t N, int64_t ldx,
                         float* LAT_out_dev, void* stream);
 int64_t nlml_mlp_launch_count(const nlml_mlp_plan* plan);
+/* Kernel generation used for the wide layers: 0 (default) = tcgen05 tensor-core chain (FP16 hi/lo operand
+ * split, 3 MMAs per MAC, FP32 TMEM accumulation) wherever a layer is a real dense contraction; 1 = FP32
+ * CUDA-core chain for every layer (the exact-arithmetic path the tensor-core chain is validated against). */
+int nlml_mlp_set_path(nlml_mlp_plan* plan, int path);
 
 /* ------------------------------------------------------------------------------------------
  * Measurement helper: sustained FP32 FMA rate of the device (TFLOP/s), used by bench.py as the

@@ -137,11 +137,18 @@ class CombinedAnglePredictionModel(nn.Module):
         if self._plan is None or self._plan.device_index != device_index:
             self.invalidate()
             self._plan = _Plan(self._all_linears(), device_index)
+            _lib.check(self._plan.lib.nlml_mlp_set_path(self._plan.h, getattr(self, "_path", 0)))
         return self._plan
 
     @property
     def launches(self):
         return 0 if self._plan is None else int(self._plan.lib.nlml_mlp_launch_count(self._plan.h))
+
+    def set_path(self, path, device=None):
+        """'tensor_core' (default: tcgen05 chain for the wide layers) or 'fp32' (CUDA-core chain everywhere)."""
+        self._path = {"tensor_core": 0, "fp32": 1}[path]
+        if self._plan is not None:
+            _lib.check(self._plan.lib.nlml_mlp_set_path(self._plan.h, self._path))
 
     def predict(self, x):
         """x CUDA float32 [B,input_size] -> CUDA [B,3] (yaw, pitch, roll) radians, asynchronous."""

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "mlp_tc.cuh"
 
 namespace nlml {
 
@@ -24,7 +25,9 @@ struct LinearArgs {
     const float* X[3];
     const float* W[3];
     const float* B[3];
-    float* Y[3];
+    float* Y[3];        // FP32 output, or null when only the split planes are wanted
+    __half* Yhi[3];     // optional FP16 hi/lo planes of the output (input format of a tensor-core layer)
+    __half* Ylo[3];
     long long ldx, ldy;
     long long N;  // rows (samples)
     int in, out;
@@ -141,6 +144,8 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(const __grid_constant_
 
     const float* __restrict__ Bv = a.B[z];
     float* __restrict__ Y = a.Y[z];
+    __half* __restrict__ Yhi = a.Yhi[z];
+    __half* __restrict__ Ylo = a.Ylo[z];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const long long row = m0 + ty * 4 + (i & 3) + (i >> 2) * 64;
@@ -148,7 +153,15 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(const __grid_constant_
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
             const int col = n0 + tx * 4 + (j & 3) + (j >> 2) * 64;
-            if (col < a.out) Y[row * a.ldy + col] = apply_act(acc[i][j] + __ldg(Bv + col), a.act);
+            if (col < a.out) {
+                const float v = apply_act(acc[i][j] + __ldg(Bv + col), a.act);
+                if (Y) Y[row * a.ldy + col] = v;
+                if (Yhi) {
+                    const __half h = __float2half_rn(v);
+                    Yhi[row * a.ldy + col] = h;
+                    Ylo[row * a.ldy + col] = __float2half_rn(v - __half2float(h));
+                }
+            }
         }
     }
 }
@@ -160,31 +173,72 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(const __grid_constant_
 // =============================================================================================
 using namespace nlml;
 
+namespace {
+constexpr int kEnc = NLML_MLP_ENCODER_LAYERS, kHead = NLML_MLP_HEAD_LAYERS, kNumT = NLML_MLP_NUM_TENSORS;
+
+struct Workspace {
+    float* f32[2] = {nullptr, nullptr};   // FP32 activations, ping-pong by layer parity
+    __half* hi[2] = {nullptr, nullptr};   // FP16 hi/lo planes, ping-pong by layer parity
+    __half* lo[2] = {nullptr, nullptr};
+    float* lat = nullptr;                 // [chunk][latent]
+};
+}  // namespace
+
 struct nlml_mlp_plan {
     int device = 0;
-    int out_dims[NLML_MLP_NUM_TENSORS];
-    int in_dims[NLML_MLP_NUM_TENSORS];
-    float* W[NLML_MLP_NUM_TENSORS] = {};
-    float* B[NLML_MLP_NUM_TENSORS] = {};
+    int out_dims[kNumT];
+    int in_dims[kNumT];
+    float* W[kNumT] = {};
+    float* B[kNumT] = {};
+    // tensor-core form of the eligible layers
+    bool tc[kNumT] = {};
+    __half* Whi[kNumT] = {};
+    __half* Wlo[kNumT] = {};
+    float inv_scale[kNumT] = {};
+    int Kp[kNumT] = {};
+    CUtensorMap wmap_hi[kNumT], wmap_lo[kNumT];
+    int path = 0;  // 0 = tensor-core chain where eligible, 1 = FP32 CUDA-core chain everywhere
     int input_size = 0, latent = 0, head_in = 0;
-    int64_t chunk = 16384;  // samples per pass; activations of a chunk stay L2-resident
-    float* bufA = nullptr;  // [chunk][max even-layer width]
-    float* bufB = nullptr;  // [chunk][max odd-layer width]
-    float* lat = nullptr;   // [chunk][latent]
-    size_t widthA = 0, widthB = 0;
+    int64_t chunk = 148 * 128;  // samples per pass: 148 M-tiles = whole waves of the persistent GEMMs
+    size_t f32_width[2] = {0, 0}, plane_width[2] = {0, 0};
+    Workspace ws[2];
+    int num_sms = 148;
     int64_t launches = 0;
     cudaStream_t streams[2] = {nullptr, nullptr};
     float* x_dev[2] = {nullptr, nullptr};
     float* y_dev[2] = {nullptr, nullptr};
-    // second workspace set so the two host-path streams do not share activations
-    float* bufA2 = nullptr;
-    float* bufB2 = nullptr;
-    float* lat2 = nullptr;
 };
 
 namespace {
 
-int launch_linear(nlml_mlp_plan* pl, LinearArgs& a, int nz, cudaStream_t st) {
+inline int enc_t(int li) { return li; }
+inline int head_t(int h, int li) { return kEnc + h * kHead + li; }
+inline int act_of(int t) {
+    if (t < kEnc) return t < 4 ? ACT_RELU : (t == 4 ? ACT_TANH : ACT_NONE);
+    return ((t - kEnc) % kHead) < kHead - 1 ? ACT_RELU : ACT_NONE;
+}
+inline bool use_tc(const nlml_mlp_plan* pl, int t) { return pl->path == 0 && pl->tc[t]; }
+
+int alloc_workspace(nlml_mlp_plan* pl, Workspace& w) {
+    if (w.lat) return 0;
+    for (int i = 0; i < 2; ++i) {
+        NLML_CUDA(cudaMalloc(&w.f32[i], sizeof(float) * pl->chunk * pl->f32_width[i]));
+        if (pl->plane_width[i]) {
+            NLML_CUDA(cudaMalloc(&w.hi[i], sizeof(__half) * pl->chunk * pl->plane_width[i]));
+            NLML_CUDA(cudaMalloc(&w.lo[i], sizeof(__half) * pl->chunk * pl->plane_width[i]));
+            // pad columns of the input planes are written by split_planes_kernel; everything else is fully overwritten
+        }
+    }
+    NLML_CUDA(cudaMalloc(&w.lat, sizeof(float) * pl->chunk * pl->latent));
+    return 0;
+}
+void free_workspace(Workspace& w) {
+    for (int i = 0; i < 2; ++i) { cudaFree(w.f32[i]); cudaFree(w.hi[i]); cudaFree(w.lo[i]); }
+    cudaFree(w.lat);
+    w = Workspace();
+}
+
+int launch_simt(nlml_mlp_plan* pl, LinearArgs& a, int nz, cudaStream_t st) {
     auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     a.vec_w = (a.in % 4 == 0);
     a.vec_x = (a.in % 4 == 0) && (a.ldx % 4 == 0);
@@ -201,54 +255,140 @@ int launch_linear(nlml_mlp_plan* pl, LinearArgs& a, int nz, cudaStream_t st) {
     return 0;
 }
 
+// one tensor-core layer: A planes [n][Kp] -> planes and/or FP32
+int launch_tc(nlml_mlp_plan* pl, int t, const __half* Ahi, const __half* Alo, int64_t n, __half* Yhi, __half* Ylo,
+              float* Yf32, cudaStream_t st) {
+    const int out = pl->out_dims[t], Kp = pl->Kp[t];
+    CUtensorMap ma_hi, ma_lo;
+    if (int rc = tc::make_plane_map(&ma_hi, Ahi, n, Kp, Kp, tc::BM)) return rc;
+    if (int rc = tc::make_plane_map(&ma_lo, Alo, n, Kp, Kp, tc::BM)) return rc;
+    tc::LinearTcArgs a{};
+    a.N = n; a.out = out; a.Kp = Kp; a.act = act_of(t); a.inv_scale = pl->inv_scale[t]; a.bias = pl->B[t];
+    a.Yhi = Yhi; a.Ylo = Ylo; a.Yf32 = Yf32; a.ldy = out;
+    const int64_t tiles_m = ceil_div(n, tc::BM);
+    if (out % 256 == 0) {
+        const unsigned grid = (unsigned)std::min<int64_t>(tiles_m * (out / 256), pl->num_sms);
+        tc::linear_tc_kernel<256><<<grid, tc::kThreads, tc::Cfg<256>::SMEM_BYTES, st>>>(ma_hi, ma_lo, pl->wmap_hi[t], pl->wmap_lo[t], a);
+    } else {
+        const unsigned grid = (unsigned)std::min<int64_t>(tiles_m * (out / 128), pl->num_sms);
+        tc::linear_tc_kernel<128><<<grid, tc::kThreads, tc::Cfg<128>::SMEM_BYTES, st>>>(ma_hi, ma_lo, pl->wmap_hi[t], pl->wmap_lo[t], a);
+    }
+    NLML_CUDA(cudaGetLastError());
+    pl->launches += 1;
+    return 0;
+}
+
 // one chunk (n <= pl->chunk samples) through the whole chain
-int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, float* YPR, float* LAT_out,
-                  float* bufA, float* bufB, float* lat, cudaStream_t st) {
-    const float* cur = X;
-    long long ld = ldx;
-    for (int li = 0; li < NLML_MLP_ENCODER_LAYERS; ++li) {
-        LinearArgs a{};
-        const bool last = li == NLML_MLP_ENCODER_LAYERS - 1;
-        float* dst = last ? (LAT_out ? LAT_out : lat) : (li % 2 == 0 ? bufA : bufB);
-        a.X[0] = cur; a.W[0] = pl->W[li]; a.B[0] = pl->B[li]; a.Y[0] = dst;
-        a.ldx = ld; a.ldy = pl->out_dims[li]; a.N = n; a.in = pl->in_dims[li]; a.out = pl->out_dims[li];
-        a.act = li < 4 ? ACT_RELU : (li == 4 ? ACT_TANH : ACT_NONE);
-        if (int rc = launch_linear(pl, a, 1, st)) return rc;
-        cur = dst;
-        ld = pl->out_dims[li];
+int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, float* YPR, float* LAT_out, Workspace& w,
+                  cudaStream_t st) {
+    if (n == 0) return 0;
+    // ---- encoder ----
+    const float* cur_f32 = X;
+    long long cur_ld = ldx;
+    const __half *cur_hi = nullptr, *cur_lo = nullptr;
+    if (use_tc(pl, enc_t(0))) {
+        const int K = pl->in_dims[0], Kp = pl->Kp[0];
+        const int vec_ok = (K % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+        const long long total = n * (Kp / 4);
+        const unsigned grid = (unsigned)std::min<long long>(ceil_div(total, 256), (long long)pl->num_sms * 16);
+        tc::split_planes_kernel<<<grid, 256, 0, st>>>(X, n, ldx, K, Kp, vec_ok, w.hi[1], w.lo[1]);
+        NLML_CUDA(cudaGetLastError());
+        pl->launches += 1;
+        cur_hi = w.hi[1]; cur_lo = w.lo[1];
+    }
+    for (int li = 0; li < kEnc; ++li) {
+        const int t = enc_t(li), par = li & 1;
+        const bool last = li == kEnc - 1;
+        const bool next_tc = !last && use_tc(pl, enc_t(li + 1));
+        float* yf = last ? (LAT_out ? LAT_out : w.lat) : (next_tc ? nullptr : w.f32[par]);
+        __half* yh = next_tc ? w.hi[par] : nullptr;
+        __half* yl = next_tc ? w.lo[par] : nullptr;
+        if (use_tc(pl, t)) {
+            if (int rc = launch_tc(pl, t, cur_hi, cur_lo, n, yh, yl, yf, st)) return rc;
+        } else {
+            LinearArgs a{};
+            a.X[0] = cur_f32; a.W[0] = pl->W[t]; a.B[0] = pl->B[t]; a.Y[0] = yf; a.Yhi[0] = yh; a.Ylo[0] = yl;
+            a.ldx = cur_ld; a.ldy = pl->out_dims[t]; a.N = n; a.in = pl->in_dims[t]; a.out = pl->out_dims[t];
+            a.act = act_of(t);
+            if (int rc = launch_simt(pl, a, 1, st)) return rc;
+        }
+        cur_f32 = yf; cur_ld = pl->out_dims[t]; cur_hi = yh; cur_lo = yl;
     }
     if (LAT_out) return 0;
-    // heads: three problems per launch; activations for head h at offset h*chunk*width
+    // ---- heads: activations of head h live at offset h * chunk * width of the ping-pong buffers ----
     const float* hx[3];
+    const __half *hh[3] = {nullptr, nullptr, nullptr}, *hl[3] = {nullptr, nullptr, nullptr};
     long long hld = pl->latent;
-    for (int h = 0; h < 3; ++h) hx[h] = lat + h * pl->head_in;
-    for (int li = 0; li < NLML_MLP_HEAD_LAYERS; ++li) {
-        LinearArgs a{};
-        const bool last = li == NLML_MLP_HEAD_LAYERS - 1;
-        float* base = (li % 2 == 0) ? bufA : bufB;
-        const int t0 = NLML_MLP_ENCODER_LAYERS + li;
+    for (int h = 0; h < 3; ++h) hx[h] = w.lat + h * pl->head_in;
+    for (int li = 0; li < kHead; ++li) {
+        const int t0 = head_t(0, li), par = li & 1;
         const int out = pl->out_dims[t0];
+        const bool last = li == kHead - 1;
+        const bool next_tc = !last && use_tc(pl, head_t(0, li + 1));
+        float* yf[3]; __half* yh[3]; __half* yl[3];
         for (int h = 0; h < 3; ++h) {
-            const int t = NLML_MLP_ENCODER_LAYERS + h * NLML_MLP_HEAD_LAYERS + li;
-            a.X[h] = hx[h]; a.W[h] = pl->W[t]; a.B[h] = pl->B[t];
-            a.Y[h] = last ? YPR + h : base + (size_t)h * pl->chunk * out;
+            const size_t off = (size_t)h * pl->chunk * out;
+            yf[h] = last ? YPR + h : (next_tc ? nullptr : w.f32[par] + off);
+            yh[h] = next_tc ? w.hi[par] + off : nullptr;
+            yl[h] = next_tc ? w.lo[par] + off : nullptr;
         }
-        a.ldx = hld; a.ldy = last ? 3 : out; a.N = n; a.in = pl->in_dims[t0]; a.out = out;
-        a.act = last ? ACT_NONE : ACT_RELU;
-        if (int rc = launch_linear(pl, a, 3, st)) return rc;
-        for (int h = 0; h < 3; ++h) hx[h] = a.Y[h];
+        if (use_tc(pl, t0)) {
+            for (int h = 0; h < 3; ++h)
+                if (int rc = launch_tc(pl, head_t(h, li), hh[h], hl[h], n, yh[h], yl[h], yf[h], st)) return rc;
+        } else {
+            LinearArgs a{};
+            for (int h = 0; h < 3; ++h) {
+                const int t = head_t(h, li);
+                a.X[h] = hx[h]; a.W[h] = pl->W[t]; a.B[h] = pl->B[t]; a.Y[h] = yf[h]; a.Yhi[h] = yh[h]; a.Ylo[h] = yl[h];
+            }
+            a.ldx = hld; a.ldy = last ? 3 : out; a.N = n; a.in = pl->in_dims[t0]; a.out = out; a.act = act_of(t0);
+            if (int rc = launch_simt(pl, a, 3, st)) return rc;
+        }
+        for (int h = 0; h < 3; ++h) { hx[h] = yf[h]; hh[h] = yh[h]; hl[h] = yl[h]; }
         hld = out;
     }
     return 0;
 }
 
 int forward_device(nlml_mlp_plan* pl, const float* X, int64_t N, int64_t ldx, float* YPR, float* LAT, cudaStream_t st) {
+    if (int rc = alloc_workspace(pl, pl->ws[0])) return rc;
     for (int64_t s0 = 0; s0 < N; s0 += pl->chunk) {
         const int64_t n = std::min<int64_t>(pl->chunk, N - s0);
         if (int rc = forward_chunk(pl, X + s0 * ldx, n, ldx, YPR ? YPR + s0 * 3 : nullptr,
-                                   LAT ? LAT + s0 * pl->latent : nullptr, pl->bufA, pl->bufB, pl->lat, st))
+                                   LAT ? LAT + s0 * pl->latent : nullptr, pl->ws[0], st))
             return rc;
     }
+    return 0;
+}
+
+// W[out][in] FP32 -> power-of-two-scaled FP16 hi/lo planes [out][Kp]
+int prepare_tc_layer(nlml_mlp_plan* pl, int t, const float* Wh) {
+    const int out = pl->out_dims[t], in = pl->in_dims[t], Kp = (in + tc::BK - 1) / tc::BK * tc::BK;
+    float maxabs = 0.f;
+    for (size_t i = 0; i < (size_t)out * in; ++i) maxabs = std::max(maxabs, std::fabs(Wh[i]));
+    // scale so the largest weight sits in [256, 512): the lo plane then stays in FP16's normal range
+    int e = 0;
+    if (maxabs > 0.f && std::isfinite(maxabs)) e = 8 - (int)std::floor(std::log2(maxabs));
+    e = std::max(-14, std::min(e, 24));
+    const float scale = std::ldexp(1.0f, e);
+    std::vector<__half> hi((size_t)out * Kp, __float2half_rn(0.f)), lo((size_t)out * Kp, __float2half_rn(0.f));
+    for (int o = 0; o < out; ++o)
+        for (int k = 0; k < in; ++k) {
+            const float v = Wh[(size_t)o * in + k] * scale;
+            const __half h = __float2half_rn(v);
+            hi[(size_t)o * Kp + k] = h;
+            lo[(size_t)o * Kp + k] = __float2half_rn(v - __half2float(h));
+        }
+    const size_t bytes = sizeof(__half) * (size_t)out * Kp;
+    NLML_CUDA(cudaMalloc(&pl->Whi[t], bytes));
+    NLML_CUDA(cudaMalloc(&pl->Wlo[t], bytes));
+    NLML_CUDA(cudaMemcpy(pl->Whi[t], hi.data(), bytes, cudaMemcpyHostToDevice));
+    NLML_CUDA(cudaMemcpy(pl->Wlo[t], lo.data(), bytes, cudaMemcpyHostToDevice));
+    pl->Kp[t] = Kp;
+    pl->inv_scale[t] = std::ldexp(1.0f, -e);
+    const int box_rows = out % 256 == 0 ? 256 : 128;
+    if (int rc = tc::make_plane_map(&pl->wmap_hi[t], pl->Whi[t], out, Kp, Kp, box_rows)) return rc;
+    if (int rc = tc::make_plane_map(&pl->wmap_lo[t], pl->Wlo[t], out, Kp, Kp, box_rows)) return rc;
     return 0;
 }
 
@@ -257,23 +397,22 @@ int forward_device(nlml_mlp_plan* pl, const float* X, int64_t N, int64_t ldx, fl
 extern "C" int nlml_mlp_plan_create(const float* const* weights, const float* const* biases, const int* out_dims,
                                     const int* in_dims, int device, nlml_mlp_plan** plan_out) {
     if (!weights || !biases || !out_dims || !in_dims || !plan_out) return set_error(NLML_E_INVALID, "null pointer argument");
-    for (int t = 0; t < NLML_MLP_NUM_TENSORS; ++t) {
+    for (int t = 0; t < kNumT; ++t) {
         if (!weights[t] || !biases[t]) return set_error(NLML_E_INVALID, "null tensor %d", t);
         if (out_dims[t] < 1 || in_dims[t] < 1) return set_error(NLML_E_INVALID, "tensor %d has non-positive shape", t);
     }
-    for (int li = 1; li < NLML_MLP_ENCODER_LAYERS; ++li)
+    for (int li = 1; li < kEnc; ++li)
         if (in_dims[li] != out_dims[li - 1]) return set_error(NLML_E_INVALID, "encoder layer %d input %d != previous output %d", li, in_dims[li], out_dims[li - 1]);
-    const int latent = out_dims[NLML_MLP_ENCODER_LAYERS - 1];
-    const int head_in = in_dims[NLML_MLP_ENCODER_LAYERS];
+    const int latent = out_dims[kEnc - 1];
+    const int head_in = in_dims[kEnc];
     if (latent != 3 * head_in) return set_error(NLML_E_INVALID, "latent width %d != 3 x head input %d", latent, head_in);
     for (int h = 0; h < 3; ++h)
-        for (int li = 0; li < NLML_MLP_HEAD_LAYERS; ++li) {
-            const int t = NLML_MLP_ENCODER_LAYERS + h * NLML_MLP_HEAD_LAYERS + li;
-            const int t0 = NLML_MLP_ENCODER_LAYERS + li;
+        for (int li = 0; li < kHead; ++li) {
+            const int t = head_t(h, li), t0 = head_t(0, li);
             if (out_dims[t] != out_dims[t0] || in_dims[t] != in_dims[t0]) return set_error(NLML_E_INVALID, "heads must share one architecture");
             if (li > 0 && in_dims[t] != out_dims[t - 1]) return set_error(NLML_E_INVALID, "head layer %d shape mismatch", li);
         }
-    if (out_dims[NLML_MLP_NUM_TENSORS - 1] != 1) return set_error(NLML_E_INVALID, "head output width must be 1");
+    if (out_dims[kNumT - 1] != 1) return set_error(NLML_E_INVALID, "head output width must be 1");
     if (int rc = check_device(device)) return rc;
     DeviceGuard guard(device);
     if (!guard.ok) return set_error(NLML_E_NO_DEVICE, "cudaSetDevice(%d) failed", device);
@@ -283,7 +422,10 @@ extern "C" int nlml_mlp_plan_create(const float* const* weights, const float* co
     pl->input_size = in_dims[0];
     pl->latent = latent;
     pl->head_in = head_in;
-    for (int t = 0; t < NLML_MLP_NUM_TENSORS; ++t) {
+    cudaDeviceProp prop;
+    NLML_CUDA(cudaGetDeviceProperties(&prop, device));
+    pl->num_sms = prop.multiProcessorCount;
+    for (int t = 0; t < kNumT; ++t) {
         pl->out_dims[t] = out_dims[t];
         pl->in_dims[t] = in_dims[t];
         const size_t wb = sizeof(float) * (size_t)out_dims[t] * in_dims[t];
@@ -292,17 +434,32 @@ extern "C" int nlml_mlp_plan_create(const float* const* weights, const float* co
         NLML_CUDA(cudaMemcpy(pl->W[t], weights[t], wb, cudaMemcpyHostToDevice));
         NLML_CUDA(cudaMemcpy(pl->B[t], biases[t], sizeof(float) * out_dims[t], cudaMemcpyHostToDevice));
     }
-    for (int li = 0; li < NLML_MLP_ENCODER_LAYERS - 1; ++li) {
-        size_t& w = (li % 2 == 0) ? pl->widthA : pl->widthB;
-        w = std::max<size_t>(w, out_dims[li]);
+    // tensor-core eligibility: a real dense contraction (wide output, deep reduction) whose operand planes
+    // line up with the 64-element k-blocks; the first encoder layer gets its planes from split_planes_kernel
+    // (which pads), every other layer from its producer's epilogue (so in must already be a multiple of 64)
+    for (int t = 0; t < kNumT; ++t) {
+        const bool first = t == 0;
+        pl->tc[t] = out_dims[t] % 128 == 0 && in_dims[t] >= 64 && (first || in_dims[t] % 64 == 0);
     }
-    for (int li = 0; li < NLML_MLP_HEAD_LAYERS - 1; ++li) {
-        size_t& w = (li % 2 == 0) ? pl->widthA : pl->widthB;
-        w = std::max<size_t>(w, 3 * (size_t)out_dims[NLML_MLP_ENCODER_LAYERS + li]);
+    for (int h = 1; h < 3; ++h)
+        for (int li = 0; li < kHead; ++li) pl->tc[head_t(h, li)] = pl->tc[head_t(0, li)];
+    for (int t = 0; t < kNumT; ++t)
+        if (pl->tc[t])
+            if (int rc = prepare_tc_layer(pl, t, weights[t])) { nlml_mlp_plan_destroy(pl); return rc; }
+    NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<256>::SMEM_BYTES));
+    NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<128>::SMEM_BYTES));
+    // workspace widths (elements per sample) by layer parity, sized for either path
+    for (int li = 0; li < kEnc - 1; ++li) {
+        pl->f32_width[li & 1] = std::max<size_t>(pl->f32_width[li & 1], out_dims[li]);
+        if (pl->tc[enc_t(li + 1)]) pl->plane_width[li & 1] = std::max<size_t>(pl->plane_width[li & 1], out_dims[li]);
     }
-    NLML_CUDA(cudaMalloc(&pl->bufA, sizeof(float) * pl->chunk * pl->widthA));
-    NLML_CUDA(cudaMalloc(&pl->bufB, sizeof(float) * pl->chunk * pl->widthB));
-    NLML_CUDA(cudaMalloc(&pl->lat, sizeof(float) * pl->chunk * latent));
+    if (pl->tc[0]) pl->plane_width[1] = std::max<size_t>(pl->plane_width[1], pl->Kp[0]);
+    for (int li = 0; li < kHead - 1; ++li) {
+        const size_t w3 = 3 * (size_t)out_dims[head_t(0, li)];
+        pl->f32_width[li & 1] = std::max(pl->f32_width[li & 1], w3);
+        if (pl->tc[head_t(0, li + 1)]) pl->plane_width[li & 1] = std::max(pl->plane_width[li & 1], w3);
+    }
+    for (int i = 0; i < 2; ++i) pl->f32_width[i] = std::max<size_t>(pl->f32_width[i], 4);
     *plan_out = pl;
     return 0;
 }
@@ -310,18 +467,22 @@ extern "C" int nlml_mlp_plan_create(const float* const* weights, const float* co
 extern "C" void nlml_mlp_plan_destroy(nlml_mlp_plan* pl) {
     if (!pl) return;
     DeviceGuard guard(pl->device);
-    for (int t = 0; t < NLML_MLP_NUM_TENSORS; ++t) {
-        cudaFree(pl->W[t]);
-        cudaFree(pl->B[t]);
+    for (int t = 0; t < kNumT; ++t) {
+        cudaFree(pl->W[t]); cudaFree(pl->B[t]); cudaFree(pl->Whi[t]); cudaFree(pl->Wlo[t]);
     }
     for (int i = 0; i < 2; ++i) {
         if (pl->streams[i]) cudaStreamDestroy(pl->streams[i]);
         cudaFree(pl->x_dev[i]);
         cudaFree(pl->y_dev[i]);
+        free_workspace(pl->ws[i]);
     }
-    cudaFree(pl->bufA); cudaFree(pl->bufB); cudaFree(pl->lat);
-    cudaFree(pl->bufA2); cudaFree(pl->bufB2); cudaFree(pl->lat2);
     delete pl;
+}
+
+extern "C" int nlml_mlp_set_path(nlml_mlp_plan* pl, int path) {
+    if (!pl || path < 0 || path > 1) return set_error(NLML_E_INVALID, "path must be 0 (tensor-core chain) or 1 (FP32 CUDA-core chain)");
+    pl->path = path;
+    return 0;
 }
 
 extern "C" int nlml_mlp_forward_f32(nlml_mlp_plan* pl, const float* X_dev, int64_t N, int64_t ldx, float* YPR_out_dev,
@@ -352,19 +513,16 @@ extern "C" int nlml_mlp_forward_host_f32(nlml_mlp_plan* pl, const float* X_host,
             NLML_CUDA(cudaMalloc(&pl->x_dev[i], sizeof(float) * pl->chunk * F));
             NLML_CUDA(cudaMalloc(&pl->y_dev[i], sizeof(float) * pl->chunk * 3));
         }
-        NLML_CUDA(cudaMalloc(&pl->bufA2, sizeof(float) * pl->chunk * pl->widthA));
-        NLML_CUDA(cudaMalloc(&pl->bufB2, sizeof(float) * pl->chunk * pl->widthB));
-        NLML_CUDA(cudaMalloc(&pl->lat2, sizeof(float) * pl->chunk * pl->latent));
     }
+    for (int i = 0; i < 2; ++i)
+        if (int rc = alloc_workspace(pl, pl->ws[i])) return rc;
     int slot = 0;
     for (int64_t s0 = 0; s0 < N; s0 += pl->chunk, slot ^= 1) {
         const int64_t n = std::min<int64_t>(pl->chunk, N - s0);
         cudaStream_t st = pl->streams[slot];
         NLML_CUDA(cudaMemcpy2DAsync(pl->x_dev[slot], sizeof(float) * F, X_host + s0 * ldx, sizeof(float) * ldx,
                                     sizeof(float) * F, (size_t)n, cudaMemcpyHostToDevice, st));
-        if (int rc = forward_chunk(pl, pl->x_dev[slot], n, F, pl->y_dev[slot], nullptr, slot ? pl->bufA2 : pl->bufA,
-                                   slot ? pl->bufB2 : pl->bufB, slot ? pl->lat2 : pl->lat, st))
-            return rc;
+        if (int rc = forward_chunk(pl, pl->x_dev[slot], n, F, pl->y_dev[slot], nullptr, pl->ws[slot], st)) return rc;
         NLML_CUDA(cudaMemcpyAsync(YPR_out_host + s0 * 3, pl->y_dev[slot], sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
     }
     NLML_CUDA(cudaStreamSynchronize(pl->streams[0]));

@@ -1,0 +1,365 @@
+// Tensor-core linear layer for sm_100a: y = act((A W^T) * inv_scale + b) with FP32-grade accuracy from
+// FP16 tensor-core passes.
+//
+// The reference computes every Linear in FP32 (torch.nn.Linear on CPU, NLML_HPE_Model_Builder.py:33-53,
+// 76-92) and the parity budget is 1e-3 degrees, which no single-pass 16-bit or TF32 product meets
+// (SURVEY.md section 7).  Each FP32 operand is therefore carried as two FP16 planes, v = hi + lo with
+// hi = fp16(v), lo = fp16(v - hi), and one algorithmic MAC becomes three tcgen05 MMAs into the same FP32
+// TMEM accumulator:  hi*hi + lo*hi + hi*lo  (the lo*lo term is below FP32 resolution).
+//
+// Kernel anatomy (one CTA per SM, persistent over output tiles, 320 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of the four operand planes (A_hi, A_lo, W_hi,
+//               W_lo), 128-byte swizzle, into a ring of shared-memory stages guarded by full/empty mbarriers
+//   warp 1      MMA issuer: allocates TMEM, one elected lane issues tcgen05.mma.kind::f16 (M=128, N=BN,
+//               K=16) x 3 passes x 4 k-steps per stage, tcgen05.commit releases the stage / publishes the tile
+//   warps 2-9   promotion + epilogue: tcgen05.ld every k-block's partial 128 x BN FP32 tile (double-buffered in
+//               TMEM so the next k-block's MMAs overlap) and add it into FP32 registers with round-to-nearest;
+//               after the last k-block scale + bias + activation, then either re-split into FP16 hi/lo planes
+//               for the next tensor-core layer or store FP32 for the CUDA-core tail
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace nlml {
+namespace tc {
+
+constexpr int BM = 128;   // samples per tile (TMEM lanes)
+constexpr int BK = 64;    // fp16 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kEpilogueWarps = 8;
+constexpr int kThreads = 32 * (2 + kEpilogueWarps);   // TMA warp, MMA warp, 8 promotion/epilogue warps
+
+template <int BN>
+struct Cfg {
+    static constexpr int STAGES = BN == 256 ? 2 : 3;
+    static constexpr int A_BYTES = BM * BK * 2;           // one plane of the A tile
+    static constexpr int W_BYTES = BN * BK * 2;           // one plane of the W tile
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;              // two accumulator buffers
+    static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+};
+
+struct LinearTcArgs {
+    long long N;        // rows (samples)
+    int out, Kp;        // output features (multiple of BN), padded reduction length (multiple of BK)
+    int act;            // 0 none, 1 relu, 2 tanh
+    float inv_scale;    // 1 / (power-of-two scale folded into the W planes)
+    const float* bias;  // [out]
+    __half* Yhi;        // [N][ldy] or null
+    __half* Ylo;
+    float* Yf32;        // [N][ldy] or null
+    long long ldy;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c_inner, int c_outer, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c_inner), "r"(c_outer), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile, 128-byte swizzle, rows 128 B apart, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D=F32, A=B=F16, both K-major (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return tanhf(v);
+    return v;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                 const __grid_constant__ LinearTcArgs a) {
+    using C = Cfg<BN>;
+    constexpr int HALF = BN / 2;   // columns owned by one epilogue warp
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
+    uint64_t* full = bars;                    // [STAGES]  operand stage landed
+    uint64_t* empty = bars + C::STAGES;       // [STAGES]  operand stage consumed by the MMAs
+    uint64_t* tfull = bars + 2 * C::STAGES;   // [2]  partial accumulator of one k-block complete
+    uint64_t* tempty = tfull + 2;             // [2]  partial accumulator drained into registers
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = a.Kp / BK;
+    const int tiles_n = a.out / BN;
+    const long long tiles_m = (a.N + BM - 1) / BM;
+    const long long num_tiles = tiles_m * tiles_n;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpilogueWarps); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m0 = (int)(t / tiles_n) * BM, n0 = (int)(t % tiles_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* st = stage_base + (size_t)stage * C::STAGE_BYTES;
+                    mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+                    tma_load_2d(st, &map_a_hi, kb * BK, m0, &full[stage]);
+                    tma_load_2d(st + C::A_BYTES, &map_a_lo, kb * BK, m0, &full[stage]);
+                    tma_load_2d(st + 2 * C::A_BYTES, &map_w_hi, kb * BK, n0, &full[stage]);
+                    tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &map_w_lo, kb * BK, n0, &full[stage]);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        // The tensor core's FP32 accumulate truncates instead of rounding, which biases long accumulation
+        // chains (measured: 3.6e-3 deg at the output when all K/16*3 steps of a layer went into one TMEM
+        // accumulator).  So one TMEM accumulator only ever sums ONE k-block (4 k-steps x 3 passes = 12 MMAs);
+        // the epilogue warps promote each partial tile into FP32 registers with round-to-nearest adds.
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&tempty[acc], acc_phase ^ 1);
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    const uint32_t st = smem_u32(stage_base + (size_t)stage * C::STAGE_BYTES);
+                    const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + C::A_BYTES);
+                    const uint64_t w_hi = make_smem_desc(st + 2 * C::A_BYTES), w_lo = make_smem_desc(st + 2 * C::A_BYTES + C::W_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per k-step inside the swizzle row
+                        umma_f16(d_tmem, a_lo + adv, w_hi + adv, idesc, k != 0);          // small terms first
+                        umma_f16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                        umma_f16(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+                    }
+                    umma_commit(&empty[stage]);   // operand stage free once these MMAs have read it
+                    umma_commit(&tfull[acc]);     // partial tile ready for promotion
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lane quadrant = warp id % 4, column half = (warp - 2) / 4 =====
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const long long row = (t / tiles_n) * BM + quad * 32 + lane;
+            const int n0 = (int)(t % tiles_n) * BN + half * HALF;
+            float sum[HALF];
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) sum[j] = 0.f;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
+#pragma unroll
+                for (int c0 = 0; c0 < HALF; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if (row < a.N) {
+#pragma unroll
+                for (int c0 = 0; c0 < HALF; c0 += 32) {
+                    float y[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        y[j] = act_apply(fmaf(sum[c0 + j], a.inv_scale, __ldg(a.bias + n0 + c0 + j)), a.act);
+                    if (a.Yf32) {
+                        float4* dst = reinterpret_cast<float4*>(a.Yf32 + row * a.ldy + n0 + c0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                    }
+                    if (a.Yhi) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const __half h0 = __float2half_rn(y[2 * j]), h1 = __float2half_rn(y[2 * j + 1]);
+                            const __half l0 = __float2half_rn(y[2 * j] - __half2float(h0));
+                            const __half l1 = __float2half_rn(y[2 * j + 1] - __half2float(h1));
+                            hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                            lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                        }
+                        uint4* dh = reinterpret_cast<uint4*>(a.Yhi + row * a.ldy + n0 + c0);
+                        uint4* dl = reinterpret_cast<uint4*>(a.Ylo + row * a.ldy + n0 + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                            dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// FP32 -> (hi, lo) FP16 planes, rows padded with zeros to Kp columns
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ X, long long N, long long ldx, int K,
+                                                          int Kp, int vec_ok, __half* __restrict__ Xhi, __half* __restrict__ Xlo) {
+    const int groups = Kp / 4;
+    const long long total = N * groups;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long row = idx / groups;
+        const int k = (int)(idx % groups) * 4;
+        const float* src = X + row * ldx;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec_ok && k + 3 < K) {
+            v = __ldcs(reinterpret_cast<const float4*>(src + k));
+        } else {
+            if (k + 0 < K) v.x = __ldg(src + k + 0);
+            if (k + 1 < K) v.y = __ldg(src + k + 1);
+            if (k + 2 < K) v.z = __ldg(src + k + 2);
+            if (k + 3 < K) v.w = __ldg(src + k + 3);
+        }
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        uint32_t h[2], l[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const __half h0 = __float2half_rn(f[2 * j]), h1 = __float2half_rn(f[2 * j + 1]);
+            const __half l0 = __float2half_rn(f[2 * j] - __half2float(h0)), l1 = __float2half_rn(f[2 * j + 1] - __half2float(h1));
+            h[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            l[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        }
+        *reinterpret_cast<uint2*>(Xhi + row * Kp + k) = make_uint2(h[0], h[1]);
+        *reinterpret_cast<uint2*>(Xlo + row * Kp + k) = make_uint2(l[0], l[1]);
+    }
+}
+
+// ---- host side: tensor maps --------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2D map over a row-major fp16 plane [rows][pitch_elems] (first `cols` columns addressable), box = [BK cols][box_rows rows]
+inline int make_plane_map(CUtensorMap* map, const __half* base, long long rows, int cols, long long pitch_elems, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return set_error(NLML_E_UNSUPPORTED, "cuTensorMapEncodeTiled entry point not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(NLML_E_INVALID, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+}  // namespace tc
+}  // namespace nlml

@@ -13,10 +13,14 @@ DEG = 180.0 / np.pi
 TOL_DEG = 1e-3
 
 
-@pytest.fixture(scope="module")
-def model(state_dicts, cuda_lib):
+@pytest.fixture(scope="module", params=["tensor_core", "fp32"])
+def model(request, state_dicts, cuda_lib):
+    """Both kernel generations must meet the same parity bar: the tcgen05 chain (default) and the FP32
+    CUDA-core chain it is validated against."""
     from nlml_hpe_b200 import NLML_HPE_Model_Builder as MB
-    return MB.build_combined_model(*state_dicts)
+    m = MB.build_combined_model(*state_dicts)
+    m.set_path(request.param)
+    return m
 
 
 def _gpu(x):
@@ -84,6 +88,18 @@ def test_host_path_equals_device_path(model, X1k):
     assert np.array_equal(dev, host)
     y, p, r = model(torch.from_numpy(X1k))          # CPU tensor in -> CPU tensors out, through the GPU
     assert not y.is_cuda and np.array_equal(torch.cat([y, p, r], 1).numpy(), dev)
+
+
+def test_tensor_core_chain_matches_fp32_chain(state_dicts, X1k, cuda_lib):
+    from nlml_hpe_b200 import NLML_HPE_Model_Builder as MB
+    m = MB.build_combined_model(*state_dicts)
+    x = _gpu(X1k)
+    m.set_path("fp32")
+    a, la = m.predict(x), m.latent(x)
+    m.set_path("tensor_core")
+    b, lb = m.predict(x), m.latent(x)
+    assert (la - lb).abs().max().item() < 2e-5
+    assert (a - b).abs().max().item() * DEG < TOL_DEG
 
 
 def test_random_weights_and_inputs(cuda_lib):
