@@ -197,6 +197,7 @@ struct nlml_mlp_plan {
     float inv_scale[kNumT] = {};
     int Kp[kNumT] = {};
     CUtensorMap wmap_hi[kNumT], wmap_lo[kNumT];
+    float* Wt[kNumT] = {};   // transposed FP32 copies [in][out] for the fused narrow-layer kernels
     int path = 0;  // 0 = tensor-core chain where eligible, 1 = FP32 CUDA-core chain everywhere
     int input_size = 0, latent = 0, head_in = 0;
     int64_t chunk = 148 * 128;  // samples per pass: 148 M-tiles = whole waves of the persistent GEMMs
@@ -255,33 +256,56 @@ int launch_simt(nlml_mlp_plan* pl, LinearArgs& a, int nz, cudaStream_t st) {
     return 0;
 }
 
-// one tensor-core layer: A planes [n][Kp] -> planes and/or FP32
-int launch_tc(nlml_mlp_plan* pl, int t, const __half* Ahi, const __half* Alo, int64_t n, __half* Yhi, __half* Ylo,
-              float* Yf32, cudaStream_t st) {
-    const int out = pl->out_dims[t], Kp = pl->Kp[t];
-    CUtensorMap ma_hi, ma_lo;
-    if (int rc = tc::make_plane_map(&ma_hi, Ahi, n, Kp, Kp, tc::BM)) return rc;
-    if (int rc = tc::make_plane_map(&ma_lo, Alo, n, Kp, Kp, tc::BM)) return rc;
+// one tensor-core layer for `nz` problems of identical shape (1 = encoder layer, 3 = the heads):
+// A planes [n][Kp] -> planes and/or FP32
+int launch_tc(nlml_mlp_plan* pl, const int* t, int nz, const __half* const* Ahi, const __half* const* Alo, int64_t n,
+              __half* const* Yhi, __half* const* Ylo, float* const* Yf32, cudaStream_t st) {
+    const int out = pl->out_dims[t[0]], Kp = pl->Kp[t[0]];
+    tc::TcMaps maps;
     tc::LinearTcArgs a{};
-    a.N = n; a.out = out; a.Kp = Kp; a.act = act_of(t); a.inv_scale = pl->inv_scale[t]; a.bias = pl->B[t];
-    a.Yhi = Yhi; a.Ylo = Ylo; a.Yf32 = Yf32; a.ldy = out;
+    a.N = n; a.out = out; a.Kp = Kp; a.act = act_of(t[0]); a.problems = nz; a.ldy = out;
+    for (int z = 0; z < nz; ++z) {
+        if (int rc = tc::make_plane_map(&maps.a_hi[z], Ahi[z], n, Kp, Kp, tc::BM)) return rc;
+        if (int rc = tc::make_plane_map(&maps.a_lo[z], Alo[z], n, Kp, Kp, tc::BM)) return rc;
+        maps.w_hi[z] = pl->wmap_hi[t[z]];
+        maps.w_lo[z] = pl->wmap_lo[t[z]];
+        a.inv_scale[z] = pl->inv_scale[t[z]]; a.bias[z] = pl->B[t[z]];
+        a.Yhi[z] = Yhi[z]; a.Ylo[z] = Ylo[z]; a.Yf32[z] = Yf32[z];
+    }
+    for (int z = nz; z < tc::kMaxProblems; ++z) {
+        maps.a_hi[z] = maps.a_hi[0]; maps.a_lo[z] = maps.a_lo[0]; maps.w_hi[z] = maps.w_hi[0]; maps.w_lo[z] = maps.w_lo[0];
+    }
     const int64_t tiles_m = ceil_div(n, tc::BM);
     if (out % 256 == 0) {
-        const unsigned grid = (unsigned)std::min<int64_t>(tiles_m * (out / 256), pl->num_sms);
-        tc::linear_tc_kernel<256><<<grid, tc::kThreads, tc::Cfg<256>::SMEM_BYTES, st>>>(ma_hi, ma_lo, pl->wmap_hi[t], pl->wmap_lo[t], a);
+        const unsigned grid = (unsigned)std::min<int64_t>(tiles_m * (out / 256) * nz, pl->num_sms);
+        tc::linear_tc_kernel<256><<<grid, tc::kThreads, tc::Cfg<256>::SMEM_BYTES, st>>>(maps, a);
     } else {
-        const unsigned grid = (unsigned)std::min<int64_t>(tiles_m * (out / 128), pl->num_sms);
-        tc::linear_tc_kernel<128><<<grid, tc::kThreads, tc::Cfg<128>::SMEM_BYTES, st>>>(ma_hi, ma_lo, pl->wmap_hi[t], pl->wmap_lo[t], a);
+        const unsigned grid = (unsigned)std::min<int64_t>(tiles_m * (out / 128) * nz, pl->num_sms);
+        tc::linear_tc_kernel<128><<<grid, tc::kThreads, tc::Cfg<128>::SMEM_BYTES, st>>>(maps, a);
     }
     NLML_CUDA(cudaGetLastError());
     pl->launches += 1;
     return 0;
 }
 
+// the reference architecture's narrow layers have dedicated fused kernels
+constexpr int kNeckIn = 128, kNeckMid = 64, kNeckLat = 9, kHeadIn = 3, kHeadW = 128, kTailMid = 64;
+inline bool neck_fusable(const nlml_mlp_plan* pl) {
+    return pl->in_dims[4] == kNeckIn && pl->out_dims[4] == kNeckMid && pl->out_dims[5] == kNeckLat &&
+           pl->head_in == kHeadIn && pl->out_dims[head_t(0, 0)] == kHeadW;
+}
+inline bool tail_fusable(const nlml_mlp_plan* pl) {
+    return pl->in_dims[head_t(0, 3)] == kHeadW && pl->out_dims[head_t(0, 3)] == kTailMid;
+}
+constexpr size_t kNeckSmem = sizeof(float) * (kNeckIn * kNeckMid + tc::kRowsPerBlock * (kNeckIn + 4) + kNeckLat * kNeckMid +
+                                              3 * kHeadW * kHeadIn + kNeckMid + kNeckLat + 3 * kHeadW);
+constexpr size_t kTailSmem = sizeof(float) * (kHeadW * kTailMid + tc::kRowsPerBlock * (kHeadW + 4) + 2 * kTailMid + 4);
+
 // one chunk (n <= pl->chunk samples) through the whole chain
 int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, float* YPR, float* LAT_out, Workspace& w,
                   cudaStream_t st) {
     if (n == 0) return 0;
+    const bool fuse_neck = pl->path == 0 && neck_fusable(pl), fuse_tail = pl->path == 0 && tail_fusable(pl);
     // ---- encoder ----
     const float* cur_f32 = X;
     long long cur_ld = ldx;
@@ -296,15 +320,16 @@ int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, flo
         pl->launches += 1;
         cur_hi = w.hi[1]; cur_lo = w.lo[1];
     }
-    for (int li = 0; li < kEnc; ++li) {
+    const int enc_layers = fuse_neck ? 4 : kEnc;   // the neck kernel takes encoder.8 / encoder.10 / model.0
+    for (int li = 0; li < enc_layers; ++li) {
         const int t = enc_t(li), par = li & 1;
         const bool last = li == kEnc - 1;
-        const bool next_tc = !last && use_tc(pl, enc_t(li + 1));
+        const bool next_tc = !last && !(fuse_neck && li == 3) && use_tc(pl, enc_t(li + 1));
         float* yf = last ? (LAT_out ? LAT_out : w.lat) : (next_tc ? nullptr : w.f32[par]);
         __half* yh = next_tc ? w.hi[par] : nullptr;
         __half* yl = next_tc ? w.lo[par] : nullptr;
         if (use_tc(pl, t)) {
-            if (int rc = launch_tc(pl, t, cur_hi, cur_lo, n, yh, yl, yf, st)) return rc;
+            if (int rc = launch_tc(pl, &t, 1, &cur_hi, &cur_lo, n, &yh, &yl, &yf, st)) return rc;
         } else {
             LinearArgs a{};
             a.X[0] = cur_f32; a.W[0] = pl->W[t]; a.B[0] = pl->B[t]; a.Y[0] = yf; a.Yhi[0] = yh; a.Ylo[0] = yl;
@@ -314,17 +339,52 @@ int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, flo
         }
         cur_f32 = yf; cur_ld = pl->out_dims[t]; cur_hi = yh; cur_lo = yl;
     }
-    if (LAT_out) return 0;
     // ---- heads: activations of head h live at offset h * chunk * width of the ping-pong buffers ----
     const float* hx[3];
     const __half *hh[3] = {nullptr, nullptr, nullptr}, *hl[3] = {nullptr, nullptr, nullptr};
     long long hld = pl->latent;
-    for (int h = 0; h < 3; ++h) hx[h] = w.lat + h * pl->head_in;
-    for (int li = 0; li < kHead; ++li) {
+    int first_head_layer = 0;
+    if (fuse_neck) {
+        tc::NeckArgs a{};
+        a.X = cur_f32; a.N = n;
+        a.W4t = pl->Wt[4]; a.B4 = pl->B[4]; a.W5 = pl->W[5]; a.B5 = pl->B[5];
+        a.LAT = LAT_out ? LAT_out : w.lat;
+        const bool next_tc = use_tc(pl, head_t(0, 1));
+        for (int h = 0; h < 3; ++h) {
+            const size_t off = (size_t)h * pl->chunk * kHeadW;
+            a.Wh[h] = pl->W[head_t(h, 0)]; a.Bh[h] = pl->B[head_t(h, 0)];
+            a.Hhi[h] = (!LAT_out && next_tc) ? w.hi[0] + off : nullptr;
+            a.Hlo[h] = (!LAT_out && next_tc) ? w.lo[0] + off : nullptr;
+            a.Hf32[h] = (!LAT_out && !next_tc) ? w.f32[0] + off : nullptr;
+            hx[h] = a.Hf32[h]; hh[h] = a.Hhi[h]; hl[h] = a.Hlo[h];
+        }
+        tc::neck_kernel<kNeckIn, kNeckMid, kNeckLat, kHeadIn, kHeadW><<<(unsigned)ceil_div(n, tc::kRowsPerBlock), tc::kNarrowThreads, kNeckSmem, st>>>(a);
+        NLML_CUDA(cudaGetLastError());
+        pl->launches += 1;
+        hld = kHeadW;
+        first_head_layer = 1;
+    } else {
+        for (int h = 0; h < 3; ++h) hx[h] = w.lat + h * pl->head_in;
+    }
+    if (LAT_out) return 0;
+    for (int li = first_head_layer; li < kHead; ++li) {
         const int t0 = head_t(0, li), par = li & 1;
         const int out = pl->out_dims[t0];
         const bool last = li == kHead - 1;
-        const bool next_tc = !last && use_tc(pl, head_t(0, li + 1));
+        if (fuse_tail && li == 3) {
+            tc::HeadTailArgs a{};
+            a.N = n; a.YPR = YPR;
+            for (int h = 0; h < 3; ++h) {
+                a.X[h] = hx[h];
+                a.W3t[h] = pl->Wt[head_t(h, 3)]; a.B3[h] = pl->B[head_t(h, 3)];
+                a.W4[h] = pl->W[head_t(h, 4)]; a.B4[h] = pl->B[head_t(h, 4)];
+            }
+            tc::head_tail_kernel<kHeadW, kTailMid><<<dim3((unsigned)ceil_div(n, tc::kRowsPerBlock), 3), tc::kNarrowThreads, kTailSmem, st>>>(a);
+            NLML_CUDA(cudaGetLastError());
+            pl->launches += 1;
+            break;
+        }
+        const bool next_tc = !last && !(fuse_tail && li == 2) && use_tc(pl, head_t(0, li + 1));
         float* yf[3]; __half* yh[3]; __half* yl[3];
         for (int h = 0; h < 3; ++h) {
             const size_t off = (size_t)h * pl->chunk * out;
@@ -333,8 +393,8 @@ int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, flo
             yl[h] = next_tc ? w.lo[par] + off : nullptr;
         }
         if (use_tc(pl, t0)) {
-            for (int h = 0; h < 3; ++h)
-                if (int rc = launch_tc(pl, head_t(h, li), hh[h], hl[h], n, yh[h], yl[h], yf[h], st)) return rc;
+            const int ts[3] = {head_t(0, li), head_t(1, li), head_t(2, li)};
+            if (int rc = launch_tc(pl, ts, 3, hh, hl, n, yh, yl, yf, st)) return rc;
         } else {
             LinearArgs a{};
             for (int h = 0; h < 3; ++h) {
@@ -434,6 +494,17 @@ extern "C" int nlml_mlp_plan_create(const float* const* weights, const float* co
         NLML_CUDA(cudaMemcpy(pl->W[t], weights[t], wb, cudaMemcpyHostToDevice));
         NLML_CUDA(cudaMemcpy(pl->B[t], biases[t], sizeof(float) * out_dims[t], cudaMemcpyHostToDevice));
     }
+    // transposed copies [in][out] of the layers the fused narrow-layer kernels broadcast from shared memory
+    for (int t = 0; t < kNumT; ++t) {
+        const bool neck_l = t == 4, tail_l = t >= kEnc && (t - kEnc) % kHead == 3;
+        if (!neck_l && !tail_l) continue;
+        const int o = out_dims[t], in = in_dims[t];
+        std::vector<float> tr((size_t)o * in);
+        for (int j = 0; j < o; ++j)
+            for (int k = 0; k < in; ++k) tr[(size_t)k * o + j] = weights[t][(size_t)j * in + k];
+        NLML_CUDA(cudaMalloc(&pl->Wt[t], sizeof(float) * tr.size()));
+        NLML_CUDA(cudaMemcpy(pl->Wt[t], tr.data(), sizeof(float) * tr.size(), cudaMemcpyHostToDevice));
+    }
     // tensor-core eligibility: a real dense contraction (wide output, deep reduction) whose operand planes
     // line up with the 64-element k-blocks; the first encoder layer gets its planes from split_planes_kernel
     // (which pads), every other layer from its producer's epilogue (so in must already be a multiple of 64)
@@ -448,6 +519,8 @@ extern "C" int nlml_mlp_plan_create(const float* const* weights, const float* co
             if (int rc = prepare_tc_layer(pl, t, weights[t])) { nlml_mlp_plan_destroy(pl); return rc; }
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<256>::SMEM_BYTES));
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<128>::SMEM_BYTES));
+    NLML_CUDA(cudaFuncSetAttribute(tc::neck_kernel<kNeckIn, kNeckMid, kNeckLat, kHeadIn, kHeadW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNeckSmem));
+    NLML_CUDA(cudaFuncSetAttribute(tc::head_tail_kernel<kHeadW, kTailMid>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmem));
     // workspace widths (elements per sample) by layer parity, sized for either path
     for (int li = 0; li < kEnc - 1; ++li) {
         pl->f32_width[li & 1] = std::max<size_t>(pl->f32_width[li & 1], out_dims[li]);
@@ -468,7 +541,7 @@ extern "C" void nlml_mlp_plan_destroy(nlml_mlp_plan* pl) {
     if (!pl) return;
     DeviceGuard guard(pl->device);
     for (int t = 0; t < kNumT; ++t) {
-        cudaFree(pl->W[t]); cudaFree(pl->B[t]); cudaFree(pl->Whi[t]); cudaFree(pl->Wlo[t]);
+        cudaFree(pl->W[t]); cudaFree(pl->B[t]); cudaFree(pl->Whi[t]); cudaFree(pl->Wlo[t]); cudaFree(pl->Wt[t]);
     }
     for (int i = 0; i < 2; ++i) {
         if (pl->streams[i]) cudaStreamDestroy(pl->streams[i]);

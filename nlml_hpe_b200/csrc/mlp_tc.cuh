@@ -41,16 +41,24 @@ struct Cfg {
     static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
 };
 
+constexpr int kMaxProblems = 3;   // the three heads ride one launch
+
 struct LinearTcArgs {
     long long N;        // rows (samples)
     int out, Kp;        // output features (multiple of BN), padded reduction length (multiple of BK)
     int act;            // 0 none, 1 relu, 2 tanh
-    float inv_scale;    // 1 / (power-of-two scale folded into the W planes)
-    const float* bias;  // [out]
-    __half* Yhi;        // [N][ldy] or null
-    __half* Ylo;
-    float* Yf32;        // [N][ldy] or null
+    int problems;       // independent problems of identical shape (1 for the encoder, 3 for the heads)
+    float inv_scale[kMaxProblems];    // 1 / (power-of-two scale folded into the W planes)
+    const float* bias[kMaxProblems];  // [out]
+    __half* Yhi[kMaxProblems];        // [N][ldy] or null
+    __half* Ylo[kMaxProblems];
+    float* Yf32[kMaxProblems];        // [N][ldy] or null
     long long ldy;
+};
+
+// operand maps of up to three problems: A_hi, A_lo, W_hi, W_lo each
+struct TcMaps {
+    CUtensorMap a_hi[kMaxProblems], a_lo[kMaxProblems], w_hi[kMaxProblems], w_lo[kMaxProblems];
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
@@ -145,9 +153,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                 const __grid_constant__ LinearTcArgs a) {
+linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ LinearTcArgs a) {
     using C = Cfg<BN>;
     constexpr int HALF = BN / 2;   // columns owned by one epilogue warp
     extern __shared__ uint8_t smem_raw[];
@@ -164,10 +170,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     const int num_kb = a.Kp / BK;
     const int tiles_n = a.out / BN;
     const long long tiles_m = (a.N + BM - 1) / BM;
-    const long long num_tiles = tiles_m * tiles_n;
+    const long long tiles_per_problem = tiles_m * tiles_n;
+    const long long num_tiles = tiles_per_problem * a.problems;
 
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
+        for (int z = 0; z < a.problems; ++z) {
+            prefetch_tmap(&maps.a_hi[z]); prefetch_tmap(&maps.a_lo[z]); prefetch_tmap(&maps.w_hi[z]); prefetch_tmap(&maps.w_lo[z]);
+        }
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpilogueWarps); }
         fence_barrier_init();
@@ -183,15 +192,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int m0 = (int)(t / tiles_n) * BM, n0 = (int)(t % tiles_n) * BN;
+                const int z = (int)(t / tiles_per_problem);
+                const long long tt = t % tiles_per_problem;
+                const int m0 = (int)(tt / tiles_n) * BM, n0 = (int)(tt % tiles_n) * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* st = stage_base + (size_t)stage * C::STAGE_BYTES;
                     mbar_expect_tx(&full[stage], C::STAGE_BYTES);
-                    tma_load_2d(st, &map_a_hi, kb * BK, m0, &full[stage]);
-                    tma_load_2d(st + C::A_BYTES, &map_a_lo, kb * BK, m0, &full[stage]);
-                    tma_load_2d(st + 2 * C::A_BYTES, &map_w_hi, kb * BK, n0, &full[stage]);
-                    tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &map_w_lo, kb * BK, n0, &full[stage]);
+                    tma_load_2d(st, &maps.a_hi[z], kb * BK, m0, &full[stage]);
+                    tma_load_2d(st + C::A_BYTES, &maps.a_lo[z], kb * BK, m0, &full[stage]);
+                    tma_load_2d(st + 2 * C::A_BYTES, &maps.w_hi[z], kb * BK, n0, &full[stage]);
+                    tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &maps.w_lo[z], kb * BK, n0, &full[stage]);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -234,8 +245,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         const int quad = warp & 3, half = (warp - 2) >> 2;
         int acc = 0; uint32_t acc_phase = 0;
         for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            const long long row = (t / tiles_n) * BM + quad * 32 + lane;
-            const int n0 = (int)(t % tiles_n) * BN + half * HALF;
+            const int z = (int)(t / tiles_per_problem);
+            const long long tt = t % tiles_per_problem;
+            const long long row = (tt / tiles_n) * BM + quad * 32 + lane;
+            const int n0 = (int)(tt % tiles_n) * BN + half * HALF;
+            const float inv_scale = a.inv_scale[z];
+            const float* __restrict__ bias = a.bias[z];
+            float* __restrict__ Yf32 = a.Yf32[z];
+            __half* __restrict__ Yhi = a.Yhi[z];
+            __half* __restrict__ Ylo = a.Ylo[z];
             float sum[HALF];
 #pragma unroll
             for (int j = 0; j < HALF; ++j) sum[j] = 0.f;
@@ -262,13 +280,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                     float y[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        y[j] = act_apply(fmaf(sum[c0 + j], a.inv_scale, __ldg(a.bias + n0 + c0 + j)), a.act);
-                    if (a.Yf32) {
-                        float4* dst = reinterpret_cast<float4*>(a.Yf32 + row * a.ldy + n0 + c0);
+                        y[j] = act_apply(fmaf(sum[c0 + j], inv_scale, __ldg(bias + n0 + c0 + j)), a.act);
+                    if (Yf32) {
+                        float4* dst = reinterpret_cast<float4*>(Yf32 + row * a.ldy + n0 + c0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
                     }
-                    if (a.Yhi) {
+                    if (Yhi) {
                         uint32_t hi[16], lo[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
@@ -278,8 +296,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                             hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
                             lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
                         }
-                        uint4* dh = reinterpret_cast<uint4*>(a.Yhi + row * a.ldy + n0 + c0);
-                        uint4* dl = reinterpret_cast<uint4*>(a.Ylo + row * a.ldy + n0 + c0);
+                        uint4* dh = reinterpret_cast<uint4*>(Yhi + row * a.ldy + n0 + c0);
+                        uint4* dl = reinterpret_cast<uint4*>(Ylo + row * a.ldy + n0 + c0);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
@@ -328,6 +346,191 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
         *reinterpret_cast<uint2*>(Xhi + row * Kp + k) = make_uint2(h[0], h[1]);
         *reinterpret_cast<uint2*>(Xlo + row * Kp + k) = make_uint2(l[0], l[1]);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Narrow layers (not dense contractions worth a tensor-core tile): thread-per-sample CUDA-core kernels with
+// the weights broadcast from shared memory, several layers fused per launch.
+// ---------------------------------------------------------------------------------------------------------
+
+constexpr int kRowsPerBlock = 64;   // samples per block of the fused narrow-layer kernels
+constexpr int kLanesPerRow = 1;     // lanes sharing one sample (1 measured faster than 4: the weight broadcast then
+                                    // costs one shared-memory wavefront set per warp instead of one per quarter-warp)
+constexpr int kNarrowThreads = kRowsPerBlock * kLanesPerRow;
+
+// Stage kRowsPerBlock rows of IN floats into shared memory with coalesced 128-bit loads.  Row pitch IN+4
+// floats keeps the later 128-bit reads of 8 different rows per warp conflict-free.
+template <int IN>
+__device__ __forceinline__ void stage_rows(const float* __restrict__ X, long long row0, long long N, float* xs) {
+    constexpr int V = IN / 4, PITCH = IN + 4;
+    for (int idx = threadIdx.x; idx < kRowsPerBlock * V; idx += kNarrowThreads) {
+        const int r = idx / V, c4 = idx % V;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < N) v = __ldg(reinterpret_cast<const float4*>(X + (row0 + r) * IN) + c4);
+        *reinterpret_cast<float4*>(xs + r * PITCH + 4 * c4) = v;
+    }
+}
+
+// acc[j] += sum_k Wt[k][j0 + j] * x[k], j < OUTQ: one lane's quarter of a row's outputs.  Wt is the transposed
+// weight in shared memory (row pitch WP floats) so the j index is contiguous; x is the staged row.
+template <int IN, int OUTQ, int WP>
+__device__ __forceinline__ void row_gemv(const float* __restrict__ xrow, const float* __restrict__ Wt_q, float (&acc)[OUTQ]) {
+    static_assert(IN % 4 == 0 && OUTQ % 4 == 0, "vector widths");
+#pragma unroll 4
+    for (int k4 = 0; k4 < IN / 4; ++k4) {
+        const float4 xv = *(reinterpret_cast<const float4*>(xrow) + k4);
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const float4* wrow = reinterpret_cast<const float4*>(Wt_q + (4 * k4 + kk) * WP);
+#pragma unroll
+            for (int j4 = 0; j4 < OUTQ / 4; ++j4) {
+                const float4 w = wrow[j4];
+                acc[4 * j4 + 0] = fmaf(xs[kk], w.x, acc[4 * j4 + 0]);
+                acc[4 * j4 + 1] = fmaf(xs[kk], w.y, acc[4 * j4 + 1]);
+                acc[4 * j4 + 2] = fmaf(xs[kk], w.z, acc[4 * j4 + 2]);
+                acc[4 * j4 + 3] = fmaf(xs[kk], w.w, acc[4 * j4 + 3]);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float quad_sum(float v) {
+#pragma unroll
+    for (int o = kLanesPerRow / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct NeckArgs {
+    const float* X;      // [N][D_IN]   output of the last wide encoder layer (ReLU applied)
+    long long N;
+    const float *W4t, *B4;  // [D_IN][D_MID] (pre-transposed), [D_MID]     encoder.8  (Tanh)
+    const float *W5, *B5;   // [D_LAT][D_MID], [D_LAT]    encoder.10 (none)
+    const float* Wh[3];     // [HW][HIN]                  model.0 of yaw / pitch / roll (ReLU)
+    const float* Bh[3];
+    float* LAT;             // [N][D_LAT] or null
+    __half* Hhi[3];         // [N][HW] planes of the head's first hidden layer, or null
+    __half* Hlo[3];
+    float* Hf32[3];         // [N][HW] FP32 instead (CUDA-core head path), or null
+};
+
+// encoder.8 (128->64, tanh) + encoder.10 (64->9) + latent split + model.0 of the three heads (3->128, ReLU)
+template <int D_IN, int D_MID, int D_LAT, int HIN, int HW>
+__global__ void __launch_bounds__(kNarrowThreads) neck_kernel(const __grid_constant__ NeckArgs a) {
+    static_assert(D_LAT == 3 * HIN, "latent splits into three head inputs");
+    constexpr int MQ = D_MID / kLanesPerRow, HQ = HW / kLanesPerRow;
+    static_assert(MQ % 4 == 0 && HQ % 8 == 0, "quarter widths");
+    extern __shared__ __align__(16) float nsm[];
+    float* W4t = nsm;                       // [D_IN][D_MID]
+    float* xs = W4t + D_IN * D_MID;         // [kRowsPerBlock][D_IN + 4]
+    float* W5s = xs + kRowsPerBlock * (D_IN + 4);   // [D_LAT][D_MID]
+    float* Whs = W5s + D_LAT * D_MID;       // [3][HW][HIN]
+    float* Bs = Whs + 3 * HW * HIN;         // B4[D_MID], B5[D_LAT], Bh[3][HW]
+    const long long row0 = (long long)blockIdx.x * kRowsPerBlock;
+    stage_rows<D_IN>(a.X, row0, a.N, xs);
+    for (int i = threadIdx.x; i < D_IN * D_MID / 4; i += kNarrowThreads)
+        reinterpret_cast<float4*>(W4t)[i] = __ldg(reinterpret_cast<const float4*>(a.W4t) + i);
+    for (int i = threadIdx.x; i < D_LAT * D_MID; i += kNarrowThreads) W5s[i] = __ldg(a.W5 + i);
+    for (int i = threadIdx.x; i < 3 * HW * HIN; i += kNarrowThreads) Whs[i] = __ldg(a.Wh[i / (HW * HIN)] + i % (HW * HIN));
+    for (int i = threadIdx.x; i < D_MID; i += kNarrowThreads) Bs[i] = __ldg(a.B4 + i);
+    for (int i = threadIdx.x; i < D_LAT; i += kNarrowThreads) Bs[D_MID + i] = __ldg(a.B5 + i);
+    for (int i = threadIdx.x; i < 3 * HW; i += kNarrowThreads) Bs[D_MID + D_LAT + i] = __ldg(a.Bh[i / HW] + i % HW);
+    __syncthreads();
+    const int s = threadIdx.x / kLanesPerRow, q = threadIdx.x % kLanesPerRow;
+    const long long row = row0 + s;
+    const bool valid = row < a.N;   // invalid rows compute on zeros and store nothing (the quad shuffles need all lanes)
+
+    float h[MQ];
+#pragma unroll
+    for (int j = 0; j < MQ; ++j) h[j] = Bs[q * MQ + j];
+    row_gemv<D_IN, MQ, D_MID>(xs + s * (D_IN + 4), W4t + q * MQ, h);
+#pragma unroll
+    for (int j = 0; j < MQ; ++j) h[j] = tanhf(h[j]);
+    float lat[D_LAT];
+#pragma unroll
+    for (int l = 0; l < D_LAT; ++l) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < MQ; ++j) acc = fmaf(W5s[l * D_MID + q * MQ + j], h[j], acc);
+        lat[l] = quad_sum(acc) + Bs[D_MID + l];
+    }
+    if (a.LAT && valid && q == 0) {
+#pragma unroll
+        for (int l = 0; l < D_LAT; ++l) a.LAT[row * D_LAT + l] = lat[l];
+    }
+    if (!valid) return;
+#pragma unroll
+    for (int z = 0; z < 3; ++z) {
+        if (!a.Hhi[z] && !a.Hf32[z]) continue;
+#pragma unroll 1
+        for (int j0 = q * HQ; j0 < (q + 1) * HQ; j0 += 8) {
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float acc = Bs[D_MID + D_LAT + z * HW + j0 + j];
+#pragma unroll
+                for (int i = 0; i < HIN; ++i) acc = fmaf(Whs[(z * HW + j0 + j) * HIN + i], lat[z * HIN + i], acc);
+                y[j] = fmaxf(acc, 0.f);
+            }
+            if (a.Hf32[z]) {
+                float4* d = reinterpret_cast<float4*>(a.Hf32[z] + row * HW + j0);
+                d[0] = make_float4(y[0], y[1], y[2], y[3]);
+                d[1] = make_float4(y[4], y[5], y[6], y[7]);
+            }
+            if (a.Hhi[z]) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const __half h0 = __float2half_rn(y[2 * j]), h1 = __float2half_rn(y[2 * j + 1]);
+                    const __half l0 = __float2half_rn(y[2 * j] - __half2float(h0)), l1 = __float2half_rn(y[2 * j + 1] - __half2float(h1));
+                    hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                    lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                }
+                *reinterpret_cast<uint4*>(a.Hhi[z] + row * HW + j0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(a.Hlo[z] + row * HW + j0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+    }
+}
+
+struct HeadTailArgs {
+    const float* X[3];      // [N][D_IN]  output of model.4 (ReLU applied) per head
+    long long N;
+    const float *W3t[3], *B3[3];  // [D_IN][D_MID] (pre-transposed), [D_MID]   model.6 (ReLU)
+    const float *W4[3], *B4[3];   // [1][D_MID], [1]          model.8 (none)
+    float* YPR;                   // [N][3]
+};
+
+// model.6 (128->64, ReLU) + model.8 (64->1) of one head per blockIdx.y
+template <int D_IN, int D_MID>
+__global__ void __launch_bounds__(kNarrowThreads) head_tail_kernel(const __grid_constant__ HeadTailArgs a) {
+    constexpr int MQ = D_MID / kLanesPerRow;
+    extern __shared__ __align__(16) float hsm[];
+    float* W3t = hsm;                   // [D_IN][D_MID]
+    float* xs = W3t + D_IN * D_MID;     // [kRowsPerBlock][D_IN + 4]
+    float* rest = xs + kRowsPerBlock * (D_IN + 4);   // B3[D_MID], W4[D_MID], B4[1]
+    const int z = blockIdx.y;
+    const long long row0 = (long long)blockIdx.x * kRowsPerBlock;
+    stage_rows<D_IN>(a.X[z], row0, a.N, xs);
+    for (int i = threadIdx.x; i < D_IN * D_MID / 4; i += kNarrowThreads)
+        reinterpret_cast<float4*>(W3t)[i] = __ldg(reinterpret_cast<const float4*>(a.W3t[z]) + i);
+    for (int i = threadIdx.x; i < D_MID; i += kNarrowThreads) {
+        rest[i] = __ldg(a.B3[z] + i);
+        rest[D_MID + i] = __ldg(a.W4[z] + i);
+    }
+    if (threadIdx.x == 0) rest[2 * D_MID] = __ldg(a.B4[z]);
+    __syncthreads();
+    const int s = threadIdx.x / kLanesPerRow, q = threadIdx.x % kLanesPerRow;
+    const long long row = row0 + s;
+    float h[MQ];
+#pragma unroll
+    for (int j = 0; j < MQ; ++j) h[j] = rest[q * MQ + j];
+    row_gemv<D_IN, MQ, D_MID>(xs + s * (D_IN + 4), W3t + q * MQ, h);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < MQ; ++j) acc = fmaf(rest[D_MID + q * MQ + j], fmaxf(h[j], 0.f), acc);
+    acc = quad_sum(acc) + rest[2 * D_MID];
+    if (row < a.N && q == 0) a.YPR[row * 3 + z] = acc;
 }
 
 // ---- host side: tensor maps --------------------------------------------------------------------------
