@@ -11,6 +11,7 @@
 // fused in the epilogue, launched once per layer; the three heads ride blockIdx.z of one launch per
 // head layer.  The batch is processed in chunks whose activations stay L2-resident.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -199,6 +200,7 @@ struct nlml_mlp_plan {
     CUtensorMap wmap_hi[kNumT], wmap_lo[kNumT];
     float* Wt[kNumT] = {};   // transposed FP32 copies [in][out] for the fused narrow-layer kernels
     int path = 0;  // 0 = tensor-core chain where eligible, 1 = FP32 CUDA-core chain everywhere
+    bool two_cta = true;   // 256-wide layers: cta_group::2 kernel (false: 1-CTA MMAs with W multicast; NLML_TC_1CTA=1)
     int input_size = 0, latent = 0, head_in = 0;
     int64_t chunk = 148 * 128;  // samples per pass: 148 M-tiles = whole waves of the persistent GEMMs
     size_t f32_width[2] = {0, 0}, plane_width[2] = {0, 0};
@@ -277,11 +279,21 @@ int launch_tc(nlml_mlp_plan* pl, const int* t, int nz, const __half* const* Ahi,
     }
     const int64_t tiles_m = ceil_div(n, tc::BM);
     if (out % 256 == 0) {
-        const unsigned grid = (unsigned)std::min<int64_t>(tiles_m * (out / 256) * nz, pl->num_sms);
-        tc::linear_tc_kernel<256><<<grid, tc::kThreads, tc::Cfg<256>::SMEM_BYTES, st>>>(maps, a);
+        // clusters of 2 CTAs share each W tile by TMA multicast (W maps of 256-wide layers have 128-row boxes)
+        const int64_t work = ceil_div(tiles_m, 2) * (out / 256) * nz;
+        const unsigned grid = 2 * (unsigned)std::min<int64_t>(work, pl->num_sms / 2);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc::kThreads);
+        cfg.dynamicSmemBytes = pl->two_cta ? tc::Cfg2::SMEM_BYTES : tc::Cfg<256>::SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (pl->two_cta) NLML_CUDA(cudaLaunchKernelEx(&cfg, tc::linear_tc2_kernel, maps, a));
+        else NLML_CUDA(cudaLaunchKernelEx(&cfg, tc::linear_tc_kernel<256, 2>, maps, a));
     } else {
         const unsigned grid = (unsigned)std::min<int64_t>(tiles_m * (out / 128) * nz, pl->num_sms);
-        tc::linear_tc_kernel<128><<<grid, tc::kThreads, tc::Cfg<128>::SMEM_BYTES, st>>>(maps, a);
+        tc::linear_tc_kernel<128, 1><<<grid, tc::kThreads, tc::Cfg<128>::SMEM_BYTES, st>>>(maps, a);
     }
     NLML_CUDA(cudaGetLastError());
     pl->launches += 1;
@@ -446,7 +458,7 @@ int prepare_tc_layer(nlml_mlp_plan* pl, int t, const float* Wh) {
     NLML_CUDA(cudaMemcpy(pl->Wlo[t], lo.data(), bytes, cudaMemcpyHostToDevice));
     pl->Kp[t] = Kp;
     pl->inv_scale[t] = std::ldexp(1.0f, -e);
-    const int box_rows = out % 256 == 0 ? 256 : 128;
+    const int box_rows = 128;   // 256-wide tiles are loaded as two 128-row halves, one per CTA of the cluster
     if (int rc = tc::make_plane_map(&pl->wmap_hi[t], pl->Whi[t], out, Kp, Kp, box_rows)) return rc;
     if (int rc = tc::make_plane_map(&pl->wmap_lo[t], pl->Wlo[t], out, Kp, Kp, box_rows)) return rc;
     return 0;
@@ -517,8 +529,10 @@ extern "C" int nlml_mlp_plan_create(const float* const* weights, const float* co
     for (int t = 0; t < kNumT; ++t)
         if (pl->tc[t])
             if (int rc = prepare_tc_layer(pl, t, weights[t])) { nlml_mlp_plan_destroy(pl); return rc; }
-    NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<256>::SMEM_BYTES));
-    NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<128>::SMEM_BYTES));
+    NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg2::SMEM_BYTES));
+    if (const char* e = std::getenv("NLML_TC_1CTA")) pl->two_cta = !(e[0] == '1');
+    NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<256>::SMEM_BYTES));
+    NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<128>::SMEM_BYTES));
     NLML_CUDA(cudaFuncSetAttribute(tc::neck_kernel<kNeckIn, kNeckMid, kNeckLat, kHeadIn, kHeadW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNeckSmem));
     NLML_CUDA(cudaFuncSetAttribute(tc::head_tail_kernel<kHeadW, kTailMid>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmem));
     // workspace widths (elements per sample) by layer parity, sized for either path

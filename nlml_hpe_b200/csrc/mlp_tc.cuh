@@ -93,6 +93,26 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c_inner), "r"(c_outer), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* map, int c_inner, int c_outer, uint64_t* bar,
+                                                  uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c_inner), "r"(c_outer), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -151,10 +171,16 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     return v;
 }
 
-template <int BN>
+// CL = CTAs per cluster (1 or 2).  With CL = 2 the two CTAs of a cluster work on M-tiles (2p, 2p+1) of the same
+// N-tile: each loads its own A planes and HALF of the W tile, multicast into both CTAs' shared memory, which cuts
+// the L2->SMEM operand traffic per MMA by a third (the wide layers are L2-bandwidth bound at 128x256 tiles).
+template <int BN, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ LinearTcArgs a) {
     using C = Cfg<BN>;
+    static_assert(CL == 1 || CL == 2, "cluster size");
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
     constexpr int HALF = BN / 2;   // columns owned by one epilogue warp
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -169,21 +195,23 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = a.Kp / BK;
     const int tiles_n = a.out / BN;
-    const long long tiles_m = (a.N + BM - 1) / BM;
+    const long long tiles_m = ((a.N + BM - 1) / BM + CL - 1) / CL;   // M-tile groups: CL consecutive M-tiles per cluster
     const long long tiles_per_problem = tiles_m * tiles_n;
-    const long long num_tiles = tiles_per_problem * a.problems;
+    const long long num_tiles = tiles_per_problem * a.problems;    // work items per cluster
+    const long long first = blockIdx.x / CL, step = gridDim.x / CL;
 
     if (warp == 0 && lane == 0) {
         for (int z = 0; z < a.problems; ++z) {
             prefetch_tmap(&maps.a_hi[z]); prefetch_tmap(&maps.a_lo[z]); prefetch_tmap(&maps.w_hi[z]); prefetch_tmap(&maps.w_lo[z]);
         }
-        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kEpilogueWarps); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // the peer's barriers must exist before anything is multicast into them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -191,18 +219,25 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (long long t = first; t < num_tiles; t += step) {
                 const int z = (int)(t / tiles_per_problem);
                 const long long tt = t % tiles_per_problem;
-                const int m0 = (int)(tt / tiles_n) * BM, n0 = (int)(tt % tiles_n) * BN;
+                const int m0 = (int)((tt / tiles_n) * CL + crank) * BM, n0 = (int)(tt % tiles_n) * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_wait(&empty[stage], phase ^ 1);   // CL > 1: every CTA of the cluster has consumed this stage
                     uint8_t* st = stage_base + (size_t)stage * C::STAGE_BYTES;
                     mbar_expect_tx(&full[stage], C::STAGE_BYTES);
                     tma_load_2d(st, &maps.a_hi[z], kb * BK, m0, &full[stage]);
                     tma_load_2d(st + C::A_BYTES, &maps.a_lo[z], kb * BK, m0, &full[stage]);
-                    tma_load_2d(st + 2 * C::A_BYTES, &maps.w_hi[z], kb * BK, n0, &full[stage]);
-                    tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &maps.w_lo[z], kb * BK, n0, &full[stage]);
+                    if (CL == 1) {
+                        tma_load_2d(st + 2 * C::A_BYTES, &maps.w_hi[z], kb * BK, n0, &full[stage]);
+                        tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &maps.w_lo[z], kb * BK, n0, &full[stage]);
+                    } else {
+                        // this CTA's slice of the W tile (BN/CL rows), delivered to every CTA of the cluster
+                        const int rows = BN / CL, off = (int)crank * rows * (BK * 2);
+                        tma_load_2d_mcast(st + 2 * C::A_BYTES + off, &maps.w_hi[z], kb * BK, n0 + (int)crank * rows, &full[stage], kMask);
+                        tma_load_2d_mcast(st + 2 * C::A_BYTES + C::W_BYTES + off, &maps.w_lo[z], kb * BK, n0 + (int)crank * rows, &full[stage], kMask);
+                    }
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -217,7 +252,7 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
             constexpr uint32_t idesc = make_idesc_f16(BM, BN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (long long t = first; t < num_tiles; t += step) {
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&tempty[acc], acc_phase ^ 1);
                     mbar_wait(&full[stage], phase);
@@ -233,7 +268,9 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
                         umma_f16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
                         umma_f16(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
                     }
-                    umma_commit(&empty[stage]);   // operand stage free once these MMAs have read it
+                    // operand stage free once these MMAs have read it (told to every CTA that writes into it)
+                    if (CL == 1) umma_commit(&empty[stage]);
+                    else umma_commit_mcast(&empty[stage], kMask);
                     umma_commit(&tfull[acc]);     // partial tile ready for promotion
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -244,10 +281,10 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
         // ===== epilogue warps: TMEM lane quadrant = warp id % 4, column half = (warp - 2) / 4 =====
         const int quad = warp & 3, half = (warp - 2) >> 2;
         int acc = 0; uint32_t acc_phase = 0;
-        for (long long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (long long t = first; t < num_tiles; t += step) {
             const int z = (int)(t / tiles_per_problem);
             const long long tt = t % tiles_per_problem;
-            const long long row = (tt / tiles_n) * BM + quad * 32 + lane;
+            const long long row = ((tt / tiles_n) * CL + crank) * BM + quad * 32 + lane;
             const int n0 = (int)(tt % tiles_n) * BN + half * HALF;
             const float inv_scale = a.inv_scale[z];
             const float* __restrict__ bias = a.bias[z];
@@ -310,9 +347,226 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // no CTA may exit while its peer can still multicast into it
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 2-CTA variant for the 256-wide layers: a cluster of two CTAs (one SM pair) computes a 256 x 256 output tile
+// with tcgen05.mma.cta_group::2.  Each CTA stages its own 128 rows of A and only HALF of the W tile, so a
+// pipeline stage is 64 KB instead of 96 KB: three stages fit (the 2-stage ring of the 1-CTA kernel could not
+// hide the TMA latency: tensor pipe 46 % busy) and each SM ingests a third less operand data per MMA.
+// The leader CTA (cluster rank 0) issues every MMA; accumulators land in each CTA's own TMEM (its 128 rows),
+// and each CTA's eight epilogue warps promote / finish their half exactly as in the 1-CTA kernel.
+// ---------------------------------------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's even CTA
+
+struct Cfg2 {
+    static constexpr int BN = 256;
+    static constexpr int STAGES = 3;
+    static constexpr int A_BYTES = BM * BK * 2;            // one plane of this CTA's A tile (128 rows)
+    static constexpr int W_BYTES = (BN / 2) * BK * 2;      // one plane of this CTA's half of the W tile (128 rows)
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;   // 64 KB
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256;
+};
+
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int c_inner, int c_outer, uint64_t* leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c_inner), "r"(c_outer),
+          "r"(smem_u32(leader_bar) & kPeerBitMask)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ LinearTcArgs a) {
+    using C = Cfg2;
+    constexpr int BN = C::BN, HALF = BN / 2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
+    uint64_t* full = bars;                    // [STAGES]  (leader's copy is the live one) both CTAs' operand stage landed
+    uint64_t* empty = bars + C::STAGES;       // [STAGES]  (own) stage consumed by the pair's MMAs
+    uint64_t* tfull = bars + 2 * C::STAGES;   // [2]  (own) partial accumulator of one k-block complete
+    uint64_t* tempty = tfull + 2;             // [2]  (leader's copy) drained by all 16 epilogue warps of the pair
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const bool leader = crank == 0;
+    const int num_kb = a.Kp / BK;
+    const int tiles_n = a.out / BN;
+    const long long tiles_m = ((a.N + BM - 1) / BM + 1) / 2;          // pairs of 128-row tiles
+    const long long tiles_per_problem = tiles_m * tiles_n;
+    const long long num_tiles = tiles_per_problem * a.problems;
+    const long long first = blockIdx.x / 2, step = gridDim.x / 2;
+
+    if (warp == 0 && lane == 0) {
+        for (int z = 0; z < a.problems; ++z) {
+            prefetch_tmap(&maps.a_hi[z]); prefetch_tmap(&maps.a_lo[z]); prefetch_tmap(&maps.w_hi[z]); prefetch_tmap(&maps.w_lo[z]);
+        }
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * kEpilogueWarps); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, C::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own A rows, own half of the W tile; bytes are counted on the leader's barrier =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (long long t = first; t < num_tiles; t += step) {
+                const int z = (int)(t / tiles_per_problem);
+                const long long tt = t % tiles_per_problem;
+                const int m0 = (int)((tt / tiles_n) * 2 + crank) * BM;
+                const int n0 = (int)(tt % tiles_n) * BN + (int)crank * HALF;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* st = stage_base + (size_t)stage * C::STAGE_BYTES;
+                    if (leader) mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+                    tma_load_2d_2sm(st, &maps.a_hi[z], kb * BK, m0, &full[stage]);
+                    tma_load_2d_2sm(st + C::A_BYTES, &maps.a_lo[z], kb * BK, m0, &full[stage]);
+                    tma_load_2d_2sm(st + 2 * C::A_BYTES, &maps.w_hi[z], kb * BK, n0, &full[stage]);
+                    tma_load_2d_2sm(st + 2 * C::A_BYTES + C::W_BYTES, &maps.w_lo[z], kb * BK, n0, &full[stage]);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only; one instruction drives both SMs' tensor cores) =====
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(2 * BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (long long t = first; t < num_tiles; t += step) {
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&tempty[acc], acc_phase ^ 1);
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    const uint32_t st = smem_u32(stage_base + (size_t)stage * C::STAGE_BYTES);
+                    const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + C::A_BYTES);
+                    const uint64_t w_hi = make_smem_desc(st + 2 * C::A_BYTES), w_lo = make_smem_desc(st + 2 * C::A_BYTES + C::W_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                        umma_f16_2sm(d_tmem, a_lo + adv, w_hi + adv, idesc, k != 0);
+                        umma_f16_2sm(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                        umma_f16_2sm(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+                    }
+                    umma_commit_2sm(&empty[stage], 3);   // both CTAs' producers may refill the stage
+                    umma_commit_2sm(&tfull[acc], 3);     // both CTAs' epilogue warps may promote their half
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps of this CTA: rows of its own 128-row half =====
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (long long t = first; t < num_tiles; t += step) {
+            const int z = (int)(t / tiles_per_problem);
+            const long long tt = t % tiles_per_problem;
+            const long long row = ((tt / tiles_n) * 2 + crank) * BM + quad * 32 + lane;
+            const int n0 = (int)(tt % tiles_n) * BN + half * HALF;
+            const float inv_scale = a.inv_scale[z];
+            const float* __restrict__ bias = a.bias[z];
+            float* __restrict__ Yf32 = a.Yf32[z];
+            __half* __restrict__ Yhi = a.Yhi[z];
+            __half* __restrict__ Ylo = a.Ylo[z];
+            float sum[HALF];
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) sum[j] = 0.f;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
+#pragma unroll
+                for (int c0 = 0; c0 < HALF; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if (row < a.N) {
+#pragma unroll
+                for (int c0 = 0; c0 < HALF; c0 += 32) {
+                    float y[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        y[j] = act_apply(fmaf(sum[c0 + j], inv_scale, __ldg(bias + n0 + c0 + j)), a.act);
+                    if (Yf32) {
+                        float4* dst = reinterpret_cast<float4*>(Yf32 + row * a.ldy + n0 + c0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                    }
+                    if (Yhi) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const __half h0 = __float2half_rn(y[2 * j]), h1 = __float2half_rn(y[2 * j + 1]);
+                            const __half l0 = __float2half_rn(y[2 * j] - __half2float(h0));
+                            const __half l1 = __float2half_rn(y[2 * j + 1] - __half2float(h1));
+                            hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                            lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                        }
+                        uint4* dh = reinterpret_cast<uint4*>(Yhi + row * a.ldy + n0 + c0);
+                        uint4* dl = reinterpret_cast<uint4*>(Ylo + row * a.ldy + n0 + c0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                            dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
     }
 }
 

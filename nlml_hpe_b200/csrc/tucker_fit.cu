@@ -69,7 +69,7 @@ __global__ void fold_kernel(const double* __restrict__ M, int ri, int ry, int rp
 // ---------------------------------------------------------------------------------------------
 // thread-per-sample kernel
 // ---------------------------------------------------------------------------------------------
-template <int RI, int RY, int RP, int RR, int THREADS>
+template <int RI, int RY, int RP, int RR, int THREADS, int NS>
 struct TpsCfg {
     static constexpr int R = RI * RY * RP * RR;
     static constexpr int RPAD = (R + 3) / 4 * 4;
@@ -80,10 +80,11 @@ struct TpsCfg {
     static constexpr int FC = 16;              // feature columns per staged tile
     static constexpr int XSTR = THREADS + 2;   // == 2 (mod 8): transposed tile stores are conflict-free
     static constexpr int S_FLOATS = nBCD * NAP;
-    static constexpr int Q_FLOATS = R * THREADS;
-    static constexpr int SCR_FLOATS = tri(RY) * tri(RP) * THREADS;  // per-thread scratch column of tucker_gradient
+    static constexpr int SAMPLES = THREADS * NS;   // samples per CTA; thread t owns samples t, t+THREADS, ...
+    static constexpr int Q_FLOATS = R * SAMPLES;   // [NS][R][THREADS]
+    static constexpr int SCR_FLOATS = tri(RY) * tri(RP) * SAMPLES;  // [NS][nB*nC][THREADS] scratch of tucker_gradient
     static constexpr int TILE_FLOATS = FC * XSTR + FC * RPAD;
-    static_assert(TILE_FLOATS <= Q_FLOATS, "phase-A tiles alias the q buffer");
+
     static constexpr size_t SMEM_BYTES = sizeof(float) * (S_FLOATS + Q_FLOATS + SCR_FLOATS);
 };
 
@@ -100,25 +101,32 @@ __device__ __forceinline__ float4 load_row4(const float* __restrict__ row, int f
     return v;
 }
 
-template <int RI, int RY, int RP, int RR, int THREADS, int MINB>
+template <int RI, int RY, int RP, int RR, int THREADS, int NS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) tucker_fit_tps_kernel(const __grid_constant__ TuckerArgs a) {
-    using C = TpsCfg<RI, RY, RP, RR, THREADS>;
+    using C = TpsCfg<RI, RY, RP, RR, THREADS, NS>;
     extern __shared__ __align__(16) float smem[];
     float* S_s = smem;
     float* q_s = smem + C::S_FLOATS;
     float* scr_s = q_s + C::Q_FLOATS;
     float* xs = q_s;                     // [FC][XSTR]   (phase A only)
     float* ws = q_s + C::FC * C::XSTR;   // [FC][RPAD]   (phase A only)
+    static_assert(C::TILE_FLOATS <= C::R * THREADS, "phase-A tiles must fit inside one sample slab of q");
 
     const int tid = threadIdx.x;
-    const long long s0 = (long long)blockIdx.x * THREADS;
+    const long long s0 = (long long)blockIdx.x * C::SAMPLES;
     const bool vec_ok = a.vec_ok != 0;
     const int F = a.F;
 
     for (int i = tid; i < C::S_FLOATS / 4; i += THREADS)
         reinterpret_cast<float4*>(S_s)[i] = __ldg(reinterpret_cast<const float4*>(a.S) + i);
 
-    // ---- phase A: q[r] = sum_f W2[r][f] * x[f] for this thread's sample ----
+    // ---- phase A: q[r] = sum_f W2[r][f] * x[f], one pass per sample owned by this thread ----
+    // (the tiles alias the q buffer of the pass in flight only: pass n stages its tiles in q slab n)
+#pragma unroll 1
+    for (int n = 0; n < NS; ++n) {
+    float* qn_s = q_s + n * (C::R * THREADS);
+    xs = qn_s;
+    ws = qn_s + C::FC * C::XSTR;
     float acc[C::RPAD];
 #pragma unroll
     for (int r = 0; r < C::RPAD; ++r) acc[r] = 0.f;
@@ -126,7 +134,7 @@ __global__ void __launch_bounds__(THREADS, MINB) tucker_fit_tps_kernel(const __g
     for (int f0 = 0; f0 < F; f0 += C::FC) {
         for (int idx = tid; idx < THREADS * (C::FC / 4); idx += THREADS) {
             const int s = idx / (C::FC / 4), c4 = idx % (C::FC / 4);
-            const long long row = s0 + s;
+            const long long row = s0 + n * THREADS + s;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row < a.N) v = load_row4(a.X + row * a.ldx, f0 + 4 * c4, F, vec_ok);
             xs[(4 * c4 + 0) * C::XSTR + s] = v.x;
@@ -159,24 +167,33 @@ __global__ void __launch_bounds__(THREADS, MINB) tucker_fit_tps_kernel(const __g
         __syncthreads();
     }
 #pragma unroll
-    for (int r = 0; r < C::R; ++r) q_s[r * THREADS + tid] = acc[r];
+    for (int r = 0; r < C::R; ++r) qn_s[r * THREADS + tid] = acc[r];
     __syncthreads();  // S_s complete, tiles dead
+    }
 
     // ---- phase B: T iterations entirely on chip ----
-    float p[C::NP];
+    float p[NS][C::NP];
 #pragma unroll
-    for (int i = 0; i < C::NP; ++i) p[i] = 0.f;  // zero init, TD_Tester.py:130
+    for (int n = 0; n < NS; ++n)
+#pragma unroll
+        for (int i = 0; i < C::NP; ++i) p[n][i] = 0.f;  // zero init, TD_Tester.py:130
     const float lr = a.lr, clip = a.clip;
 #pragma unroll 1
     for (int it = 0; it < a.T; ++it) {
-        float g[C::NP];
-        tucker_gradient<RI, RY, RP, RR, C::NAP>(p, S_s, q_s + tid, THREADS, scr_s + tid, THREADS, a.rows_y, a.rows_p, a.rows_r, g);
-        clip_and_step<C::NP>(p, g, lr, clip);
-    }
-    if (s0 + tid < a.N) {
-        float* out = a.P + (s0 + tid) * a.ldp;
+        float g[NS][C::NP];
+        tucker_gradient<RI, RY, RP, RR, C::NAP, NS>(p, S_s, q_s + tid, THREADS, C::R * THREADS, scr_s + tid, THREADS,
+                                                    tri(RY) * tri(RP) * THREADS, a.rows_y, a.rows_p, a.rows_r, g);
 #pragma unroll
-        for (int i = 0; i < C::NP; ++i) out[i] = p[i];
+        for (int n = 0; n < NS; ++n) clip_and_step<C::NP>(p[n], g[n], lr, clip);
+    }
+#pragma unroll
+    for (int n = 0; n < NS; ++n) {
+        const long long row = s0 + n * THREADS + tid;
+        if (row < a.N) {
+            float* out = a.P + row * a.ldp;
+#pragma unroll
+            for (int i = 0; i < C::NP; ++i) out[i] = p[n][i];
+        }
     }
 }
 
@@ -636,12 +653,14 @@ struct nlml_tucker_plan {
 };
 
 namespace {
-constexpr int kTpsThreads = 128;
+constexpr int kTpsThreads = 128;   // threads per CTA of the thread-per-sample kernel
+constexpr int kTpsSamples = 1;     // samples per thread.  2 halves the shared-memory wavefronts per sample but the q
+                                   // buffer then limits the SM to 4 warps: measured 740 k poses/s against 919 k at 1.
 constexpr int kTpsMinBlocks = 2;
 constexpr int kCtaThreads = 128;
 constexpr int kWpsWarps = 4;
 constexpr int64_t kWpsCrossover = 8192;  // below this the warp-per-sample kernel finishes sooner (profiles/)
-using TpsDefault = TpsCfg<5, 3, 3, 3, kTpsThreads>;
+using TpsDefault = TpsCfg<5, 3, 3, 3, kTpsThreads, kTpsSamples>;
 size_t wps_smem_bytes(int F) { return sizeof(float) * kWpsWarps * ((F + 3) / 4 * 4 + 64); }
 
 int launch_fit(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int iters, float lr, float clip,
@@ -668,8 +687,8 @@ int launch_fit(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int
         const unsigned grid = (unsigned)ceil_div(N, kWpsWarps);
         kern<<<grid, 32 * kWpsWarps, wps_smem_bytes(pl->F), st>>>(a);
     } else if (use_tps) {
-        auto kern = tucker_fit_tps_kernel<5, 3, 3, 3, kTpsThreads, kTpsMinBlocks>;
-        const unsigned grid = (unsigned)ceil_div(N, kTpsThreads);
+        auto kern = tucker_fit_tps_kernel<5, 3, 3, 3, kTpsThreads, kTpsSamples, kTpsMinBlocks>;
+        const unsigned grid = (unsigned)ceil_div(N, TpsDefault::SAMPLES);
         kern<<<grid, kTpsThreads, TpsDefault::SMEM_BYTES, st>>>(a);
     } else {
         auto kern = tucker_fit_cta_kernel<kCtaThreads>;
@@ -743,7 +762,7 @@ extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, i
 
     pl->fast = (r_id == 5 && r_y == 3 && r_p == 3 && r_r == 3);
     if (pl->fast) {
-        auto kern = tucker_fit_tps_kernel<5, 3, 3, 3, kTpsThreads, kTpsMinBlocks>;
+        auto kern = tucker_fit_tps_kernel<5, 3, 3, 3, kTpsThreads, kTpsSamples, kTpsMinBlocks>;
         NLML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpsDefault::SMEM_BYTES));
         if (wps_smem_bytes(F) > 200 * 1024) pl->fast = false;
         else
@@ -799,7 +818,7 @@ extern "C" int nlml_tucker_fit_host_f32(nlml_tucker_plan* pl, const float* X_hos
     const int np = 3 + pl->ri;
     if (!pl->streams[0]) {
         // two thread-per-sample waves per chunk keeps every SM busy while the next chunk is in flight
-        pl->chunk = (int64_t)pl->num_sms * kTpsMinBlocks * kTpsThreads * 2;
+        pl->chunk = (int64_t)pl->num_sms * kTpsMinBlocks * TpsDefault::SAMPLES * 2;
         for (int i = 0; i < 2; ++i) {
             NLML_CUDA(cudaStreamCreateWithFlags(&pl->streams[i], cudaStreamNonBlocking));
             NLML_CUDA(cudaMalloc(&pl->x_dev[i], sizeof(float) * (size_t)pl->chunk * pl->F));

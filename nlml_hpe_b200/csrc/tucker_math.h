@@ -107,133 +107,155 @@ NLML_HD void clip_and_step(float* p, float* g, float lr, float clip) {
     for (int i = 0; i < NP; ++i) p[i] = sub_rn(p[i], mul_rn(lr, mul_rn(g[i], coef)));
 }
 
-// One full gradient evaluation at p for fixed small ranks, thread-per-sample form.
-//   S : folded Gram tensor laid out [nB*nC*nD][NAP] (NAP = nA padded to a multiple of 4), read-only,
-//       identical for all samples (shared-memory broadcast on the GPU).
-//   q : this sample's q = W2 x, element r at q[r*qstride].
-//   scr : nB*nC floats of per-sample scratch, element k at scr[k*sstride] (a shared-memory column on the GPU).
+// One full gradient evaluation for NS samples held by one thread (fixed small ranks).
+//   S : folded Gram tensor laid out [nB*nC*nD][NAP] (NAP = nA padded to a multiple of 4), read-only, identical
+//       for all samples (shared-memory broadcast on the GPU).  Every element loaded from S feeds 2*NS FMAs,
+//       which is what keeps the kernel off the shared-memory wavefront limit.
+//   q : q = W2 x of sample n, element r at q[n*qsample + r*qstride].
+//   scr : nB*nC floats of scratch per sample, element k of sample n at scr[n*ssample + k*sstride]
+//         (a shared-memory column on the GPU).
 //   rows_* : cosine rows of the three angle factors.
-// Writes g[3+RI].
-template <int RI, int RY, int RP, int RR, int NAP>
-NLML_HD void tucker_gradient(const float* p, const float* __restrict__ S, const float* q, int qstride,
-                             float* scr, int sstride,
-                             const float* rows_y, const float* rows_p, const float* rows_r, float* g) {
+// Reads p[n][3+RI], writes g[n][3+RI].
+template <int RI, int RY, int RP, int RR, int NAP, int NS>
+NLML_HD void tucker_gradient(const float (&p)[NS][3 + RI], const float* __restrict__ S, const float* q, int qstride,
+                             int qsample, float* scr, int sstride, int ssample, const float* rows_y,
+                             const float* rows_p, const float* rows_r, float (&g)[NS][3 + RI]) {
     constexpr int nA = tri(RI), nB = tri(RY), nC = tri(RP), nD = tri(RR);
-    float cy[RY], dcy[RY], cp[RP], dcp[RP], cr[RR], dcr[RR], u[RI];
-    cos_features<RY>(p[0], rows_y, cy, dcy);
-    cos_features<RP>(p[1], rows_p, cp, dcp);
-    cos_features<RR>(p[2], rows_r, cr, dcr);
+    float cy[NS][RY], dcy[NS][RY], cp[NS][RP], dcp[NS][RP], cr[NS][RR], dcr[NS][RR], u[NS][RI];
+    float UU[NS][nA], YY[NS][nB], PP[NS][nC], RRv[NS][nD];
+    float GU[NS][nA], GY[NS][nB], GP[NS][nC], GR[NS][nD];
 #pragma unroll
-    for (int i = 0; i < RI; ++i) u[i] = p[3 + i];
+    for (int n = 0; n < NS; ++n) {
+        cos_features<RY>(p[n][0], rows_y, cy[n], dcy[n]);
+        cos_features<RP>(p[n][1], rows_p, cp[n], dcp[n]);
+        cos_features<RR>(p[n][2], rows_r, cr[n], dcr[n]);
+#pragma unroll
+        for (int i = 0; i < RI; ++i) u[n][i] = p[n][3 + i];
+        sym_products<RI>(u[n], UU[n]);
+        sym_products<RY>(cy[n], YY[n]);
+        sym_products<RP>(cp[n], PP[n]);
+        sym_products<RR>(cr[n], RRv[n]);
+#pragma unroll
+        for (int a = 0; a < nA; ++a) GU[n][a] = 0.f;
+#pragma unroll
+        for (int b = 0; b < nB; ++b) GY[n][b] = 0.f;
+#pragma unroll
+        for (int c = 0; c < nC; ++c) GP[n][c] = 0.f;
+#pragma unroll
+        for (int d = 0; d < nD; ++d) GR[n][d] = 0.f;
+        // per-sample values indexed by the (b,c) loop counter go through the scratch column
+#pragma unroll
+        for (int b = 0; b < nB; ++b)
+#pragma unroll
+            for (int c = 0; c < nC; ++c) scr[n * ssample + (b * nC + c) * sstride] = YY[n][b] * PP[n][c];
+    }
 
-    float UU[nA], YY[nB], PP[nC], RRv[nD];
-    sym_products<RI>(u, UU);
-    sym_products<RY>(cy, YY);
-    sym_products<RP>(cp, PP);
-    sym_products<RR>(cr, RRv);
-
-    float GU[nA], GY[nB], GP[nC], GR[nD];
-#pragma unroll
-    for (int a = 0; a < nA; ++a) GU[a] = 0.f;
-#pragma unroll
-    for (int b = 0; b < nB; ++b) GY[b] = 0.f;
-#pragma unroll
-    for (int c = 0; c < nC; ++c) GP[c] = 0.f;
-#pragma unroll
-    for (int d = 0; d < nD; ++d) GR[d] = 0.f;
-
-    // quadratic term: one pass over S feeds both contractions.  The (b,c) loop is a REAL loop (36 trips at
-    // ranks 3,3) so its body stays inside the instruction cache; the per-thread values indexed by the loop
-    // counter (YY_b*PP_c in, sum_d T[b,c,d]*RR_d out) go through the caller's scratch column instead of
-    // registers.  The T dot product is split in three chains to shorten the dependent-FMA latency.
-#pragma unroll
-    for (int b = 0; b < nB; ++b)
-#pragma unroll
-        for (int c = 0; c < nC; ++c) scr[(b * nC + c) * sstride] = YY[b] * PP[c];
+    // quadratic term: one pass over S feeds both contractions of all NS samples.  The (b,c) loop is a REAL
+    // loop (36 trips at ranks 3,3) so its body stays inside the instruction cache.  The T dot product is split
+    // in three chains to shorten the dependent-FMA latency.
 #pragma unroll 1
     for (int bc = 0; bc < nB * nC; ++bc) {
-        const float yp = scr[bc * sstride];
         const float* __restrict__ rows = S + bc * (nD * NAP);
-        float tr = 0.f;  // sum_d T[b,c,d] * RR_d
+        float yp[NS], tr[NS];
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+            yp[n] = scr[n * ssample + bc * sstride];
+            tr[n] = 0.f;  // sum_d T[b,c,d] * RR_d
+        }
 #pragma unroll
         for (int d = 0; d < nD; ++d) {
             const float* __restrict__ row = rows + d * NAP;
-            const float ypr = yp * RRv[d];
-            float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+            float ypr[NS], t0[NS], t1[NS], t2[NS];
+#pragma unroll
+            for (int n = 0; n < NS; ++n) {
+                ypr[n] = yp[n] * RRv[n][d];
+                t0[n] = t1[n] = t2[n] = 0.f;
+            }
 #pragma unroll
             for (int a = 0; a < nA; ++a) {
-                const float s = row[a];
-                if (a % 3 == 0) t0 = fmaf(s, UU[a], t0);
-                else if (a % 3 == 1) t1 = fmaf(s, UU[a], t1);
-                else t2 = fmaf(s, UU[a], t2);
-                GU[a] = fmaf(s, ypr, GU[a]);
-            }
-            const float t = (t0 + t1) + t2;
-            GR[d] = fmaf(t, yp, GR[d]);
-            tr = fmaf(t, RRv[d], tr);
-        }
-        scr[bc * sstride] = tr;
-    }
+                const float sv = row[a];
 #pragma unroll
-    for (int b = 0; b < nB; ++b)
-#pragma unroll
-        for (int c = 0; c < nC; ++c) {
-            const float tr = scr[(b * nC + c) * sstride];
-            GY[b] = fmaf(tr, PP[c], GY[b]);
-            GP[c] = fmaf(tr, YY[b], GP[c]);
-        }
-    float du[RI], dy[RY], dp[RP], dr[RR];
-    sym_backprop<RI>(GU, u, du);
-    sym_backprop<RY>(GY, cy, dy);
-    sym_backprop<RP>(GP, cp, dp);
-    sym_backprop<RR>(GR, cr, dr);
-
-    // linear term -q.z : d/du_i = -sum_jkl q[ijkl] cy_j cp_k cr_l ; e[jkl] = sum_i u_i q[ijkl]
-    float ey[RY], ep[RP], er[RR];
-#pragma unroll
-    for (int j = 0; j < RY; ++j) ey[j] = 0.f;
-#pragma unroll
-    for (int k = 0; k < RP; ++k) ep[k] = 0.f;
-#pragma unroll
-    for (int l = 0; l < RR; ++l) er[l] = 0.f;
-    float lin_u[RI];
-#pragma unroll
-    for (int i = 0; i < RI; ++i) lin_u[i] = 0.f;
-#pragma unroll
-    for (int j = 0; j < RY; ++j) {
-#pragma unroll
-        for (int k = 0; k < RP; ++k) {
-            const float yk = cy[j] * cp[k];
-            float e_jk = 0.f;  // sum_l e[jkl] cr_l
-#pragma unroll
-            for (int l = 0; l < RR; ++l) {
-                const float t_jkl = yk * cr[l];
-                float e = 0.f;  // sum_i u_i q[ijkl]
-#pragma unroll
-                for (int i = 0; i < RI; ++i) {
-                    const float qv = q[(((i * RY + j) * RP + k) * RR + l) * qstride];
-                    lin_u[i] = fmaf(qv, t_jkl, lin_u[i]);
-                    e = fmaf(qv, u[i], e);
+                for (int n = 0; n < NS; ++n) {
+                    if (a % 3 == 0) t0[n] = fmaf(sv, UU[n][a], t0[n]);
+                    else if (a % 3 == 1) t1[n] = fmaf(sv, UU[n][a], t1[n]);
+                    else t2[n] = fmaf(sv, UU[n][a], t2[n]);
+                    GU[n][a] = fmaf(sv, ypr[n], GU[n][a]);
                 }
-                er[l] = fmaf(e, yk, er[l]);
-                e_jk = fmaf(e, cr[l], e_jk);
             }
-            ey[j] = fmaf(e_jk, cp[k], ey[j]);
-            ep[k] = fmaf(e_jk, cy[j], ep[k]);
+#pragma unroll
+            for (int n = 0; n < NS; ++n) {
+                const float t = (t0[n] + t1[n]) + t2[n];
+                GR[n][d] = fmaf(t, yp[n], GR[n][d]);
+                tr[n] = fmaf(t, RRv[n][d], tr[n]);
+            }
         }
+#pragma unroll
+        for (int n = 0; n < NS; ++n) scr[n * ssample + bc * sstride] = tr[n];
     }
-    float gy = 0.f, gp = 0.f, gr = 0.f;
+
 #pragma unroll
-    for (int j = 0; j < RY; ++j) gy = fmaf(dy[j] - ey[j], dcy[j], gy);
+    for (int n = 0; n < NS; ++n) {
 #pragma unroll
-    for (int k = 0; k < RP; ++k) gp = fmaf(dp[k] - ep[k], dcp[k], gp);
+        for (int b = 0; b < nB; ++b)
 #pragma unroll
-    for (int l = 0; l < RR; ++l) gr = fmaf(dr[l] - er[l], dcr[l], gr);
-    g[0] = gy;
-    g[1] = gp;
-    g[2] = gr;
+            for (int c = 0; c < nC; ++c) {
+                const float tr = scr[n * ssample + (b * nC + c) * sstride];
+                GY[n][b] = fmaf(tr, PP[n][c], GY[n][b]);
+                GP[n][c] = fmaf(tr, YY[n][b], GP[n][c]);
+            }
+        float du[RI], dy[RY], dp[RP], dr[RR];
+        sym_backprop<RI>(GU[n], u[n], du);
+        sym_backprop<RY>(GY[n], cy[n], dy);
+        sym_backprop<RP>(GP[n], cp[n], dp);
+        sym_backprop<RR>(GR[n], cr[n], dr);
+
+        // linear term -q.z : d/du_i = -sum_jkl q[ijkl] cy_j cp_k cr_l ; e[jkl] = sum_i u_i q[ijkl]
+        float ey[RY], ep[RP], er[RR], lin_u[RI];
 #pragma unroll
-    for (int i = 0; i < RI; ++i) g[3 + i] = du[i] - lin_u[i];
+        for (int j = 0; j < RY; ++j) ey[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < RP; ++k) ep[k] = 0.f;
+#pragma unroll
+        for (int l = 0; l < RR; ++l) er[l] = 0.f;
+#pragma unroll
+        for (int i = 0; i < RI; ++i) lin_u[i] = 0.f;
+        const float* qn = q + n * qsample;
+#pragma unroll
+        for (int j = 0; j < RY; ++j) {
+#pragma unroll
+            for (int k = 0; k < RP; ++k) {
+                const float yk = cy[n][j] * cp[n][k];
+                float e_jk = 0.f;  // sum_l e[jkl] cr_l
+#pragma unroll
+                for (int l = 0; l < RR; ++l) {
+                    const float t_jkl = yk * cr[n][l];
+                    float e = 0.f;  // sum_i u_i q[ijkl]
+#pragma unroll
+                    for (int i = 0; i < RI; ++i) {
+                        const float qv = qn[(((i * RY + j) * RP + k) * RR + l) * qstride];
+                        lin_u[i] = fmaf(qv, t_jkl, lin_u[i]);
+                        e = fmaf(qv, u[n][i], e);
+                    }
+                    er[l] = fmaf(e, yk, er[l]);
+                    e_jk = fmaf(e, cr[n][l], e_jk);
+                }
+                ey[j] = fmaf(e_jk, cp[n][k], ey[j]);
+                ep[k] = fmaf(e_jk, cy[n][j], ep[k]);
+            }
+        }
+        float gy = 0.f, gp = 0.f, gr = 0.f;
+#pragma unroll
+        for (int j = 0; j < RY; ++j) gy = fmaf(dy[j] - ey[j], dcy[n][j], gy);
+#pragma unroll
+        for (int k = 0; k < RP; ++k) gp = fmaf(dp[k] - ep[k], dcp[n][k], gp);
+#pragma unroll
+        for (int l = 0; l < RR; ++l) gr = fmaf(dr[l] - er[l], dcr[n][l], gr);
+        g[n][0] = gy;
+        g[n][1] = gp;
+        g[n][2] = gr;
+#pragma unroll
+        for (int i = 0; i < RI; ++i) g[n][3 + i] = du[i] - lin_u[i];
+    }
 }
 
 // ---- one-time constant preparation (per Tucker core), identical on host and device ----

@@ -33,14 +33,14 @@ extern "C" int hostcheck_tucker_fit_5333(const float* W2, int F, const double* r
             for (int f = 0; f < F; ++f) acc = fmaf(W2[(size_t)r * F + f], X[s * ldx + f], acc);
             q[r] = acc;
         }
-        float p[NP] = {0};
+        float p[1][NP] = {{0}};
         for (int it = 0; it < T; ++it) {
-            float g[NP];
+            float g[1][NP];
             float scr[tri(RY) * tri(RP)];
-            tucker_gradient<RI, RY, RP, RR, NAP>(p, S.data(), q, 1, scr, 1, ry, rp, rr, g);
-            clip_and_step<NP>(p, g, lr, clip);
+            tucker_gradient<RI, RY, RP, RR, NAP, 1>(p, S.data(), q, 1, 0, scr, 1, 0, ry, rp, rr, g);
+            clip_and_step<NP>(p[0], g[0], lr, clip);
         }
-        for (int i = 0; i < NP; ++i) P[s * NP + i] = p[i];
+        for (int i = 0; i < NP; ++i) P[s * NP + i] = p[0][i];
     }
     return 0;
 }
@@ -69,8 +69,15 @@ extern "C" int hostcheck_tucker_grad_5333(const float* W2, int F, const double* 
             for (int f = 0; f < F; ++f) acc = fmaf(W2[(size_t)r * F + f], X[s * ldx + f], acc);
             q[r] = acc;
         }
-        float scr[tri(RY) * tri(RP)];
-        tucker_gradient<RI, RY, RP, RR, NAP>(Pin + s * NP, S.data(), q, 1, scr, 1, ry, rp, rr, G + s * NP);
+        float scr[2][tri(RY) * tri(RP)];
+        // two samples per call (the same sample twice) exercises the NS=2 path the GPU kernel uses
+        float pin[2][NP], gout[2][NP];
+        for (int i = 0; i < NP; ++i) pin[0][i] = pin[1][i] = Pin[s * NP + i];
+        float q2[2][R];
+        for (int r = 0; r < R; ++r) q2[0][r] = q2[1][r] = q[r];
+        tucker_gradient<RI, RY, RP, RR, NAP, 2>(pin, S.data(), &q2[0][0], 1, R, &scr[0][0], 1, tri(RY) * tri(RP), ry, rp, rr, gout);
+        for (int i = 0; i < NP; ++i) G[s * NP + i] = gout[1][i];
+        for (int i = 0; i < NP; ++i) if (gout[0][i] != gout[1][i]) return 1;
     }
     return 0;
 }
