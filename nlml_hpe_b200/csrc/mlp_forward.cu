@@ -200,6 +200,8 @@ struct nlml_mlp_plan {
     CUtensorMap wmap_hi[kNumT], wmap_lo[kNumT];
     float* Wt[kNumT] = {};   // transposed FP32 copies [in][out] for the fused narrow-layer kernels
     int path = 0;  // 0 = tensor-core chain where eligible, 1 = FP32 CUDA-core chain everywhere
+    int tc_group = 1;      // k-blocks accumulated in TMEM per promotion (NLML_TC_GROUP).  Max error vs the reference over
+                           // 32768 samples: 1 -> 5.3e-4 deg, 2 -> 8.3e-4 deg (+3 % speed), 22 (never promote) -> 3.7e-3 deg
     bool two_cta = true;   // 256-wide layers: cta_group::2 kernel (false: 1-CTA MMAs with W multicast; NLML_TC_1CTA=1)
     int input_size = 0, latent = 0, head_in = 0;
     int64_t chunk = 148 * 128;  // samples per pass: 148 M-tiles = whole waves of the persistent GEMMs
@@ -265,7 +267,7 @@ int launch_tc(nlml_mlp_plan* pl, const int* t, int nz, const __half* const* Ahi,
     const int out = pl->out_dims[t[0]], Kp = pl->Kp[t[0]];
     tc::TcMaps maps;
     tc::LinearTcArgs a{};
-    a.N = n; a.out = out; a.Kp = Kp; a.act = act_of(t[0]); a.problems = nz; a.ldy = out;
+    a.N = n; a.out = out; a.Kp = Kp; a.act = act_of(t[0]); a.problems = nz; a.ldy = out; a.group = pl->tc_group;
     for (int z = 0; z < nz; ++z) {
         if (int rc = tc::make_plane_map(&maps.a_hi[z], Ahi[z], n, Kp, Kp, tc::BM)) return rc;
         if (int rc = tc::make_plane_map(&maps.a_lo[z], Alo[z], n, Kp, Kp, tc::BM)) return rc;
@@ -531,6 +533,7 @@ extern "C" int nlml_mlp_plan_create(const float* const* weights, const float* co
             if (int rc = prepare_tc_layer(pl, t, weights[t])) { nlml_mlp_plan_destroy(pl); return rc; }
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg2::SMEM_BYTES));
     if (const char* e = std::getenv("NLML_TC_1CTA")) pl->two_cta = !(e[0] == '1');
+    if (const char* e = std::getenv("NLML_TC_GROUP")) pl->tc_group = std::max(1, std::atoi(e));
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<256>::SMEM_BYTES));
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<128>::SMEM_BYTES));
     NLML_CUDA(cudaFuncSetAttribute(tc::neck_kernel<kNeckIn, kNeckMid, kNeckLat, kHeadIn, kHeadW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNeckSmem));

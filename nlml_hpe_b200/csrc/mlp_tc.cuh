@@ -38,7 +38,7 @@ struct Cfg {
     static constexpr int W_BYTES = BN * BK * 2;           // one plane of the W tile
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;              // two accumulator buffers
-    static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+    static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ + kEpilogueWarps * (BN / 2) * 4 /*bias*/;
 };
 
 constexpr int kMaxProblems = 3;   // the three heads ride one launch
@@ -48,6 +48,7 @@ struct LinearTcArgs {
     int out, Kp;        // output features (multiple of BN), padded reduction length (multiple of BK)
     int act;            // 0 none, 1 relu, 2 tanh
     int problems;       // independent problems of identical shape (1 for the encoder, 3 for the heads)
+    int group;          // k-blocks accumulated in TMEM before a partial tile is promoted to FP32 registers
     float inv_scale[kMaxProblems];    // 1 / (power-of-two scale folded into the W planes)
     const float* bias[kMaxProblems];  // [out]
     __half* Yhi[kMaxProblems];        // [N][ldy] or null
@@ -148,6 +149,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// 256-bit global store (sm_100): one full 32-byte sector per lane
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile, 128-byte swizzle, rows 128 B apart, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
@@ -191,6 +197,7 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
     uint64_t* tfull = bars + 2 * C::STAGES;   // [2]  partial accumulator of one k-block complete
     uint64_t* tempty = tfull + 2;             // [2]  partial accumulator drained into registers
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* bias_all = reinterpret_cast<float*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256);   // [warp][HALF], private per epilogue warp
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = a.Kp / BK;
@@ -254,7 +261,8 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
             int acc = 0; uint32_t acc_phase = 0;
             for (long long t = first; t < num_tiles; t += step) {
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&tempty[acc], acc_phase ^ 1);
+                    const bool g_first = kb % a.group == 0, g_last = (kb % a.group == a.group - 1) || kb == num_kb - 1;
+                    if (g_first) mbar_wait(&tempty[acc], acc_phase ^ 1);
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -264,16 +272,18 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per k-step inside the swizzle row
-                        umma_f16(d_tmem, a_lo + adv, w_hi + adv, idesc, k != 0);          // small terms first
+                        umma_f16(d_tmem, a_lo + adv, w_hi + adv, idesc, !(g_first && k == 0));   // small terms first
                         umma_f16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
                         umma_f16(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
                     }
                     // operand stage free once these MMAs have read it (told to every CTA that writes into it)
                     if (CL == 1) umma_commit(&empty[stage]);
                     else umma_commit_mcast(&empty[stage], kMask);
-                    umma_commit(&tfull[acc]);     // partial tile ready for promotion
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    if (g_last) {
+                        umma_commit(&tfull[acc]);     // partial tile ready for promotion
+                        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    }
                 }
             }
         }
@@ -291,10 +301,14 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
             float* __restrict__ Yf32 = a.Yf32[z];
             __half* __restrict__ Yhi = a.Yhi[z];
             __half* __restrict__ Ylo = a.Ylo[z];
+            float* bias_s = bias_all + (warp - 2) * HALF;   // this warp's slice of the bias, read back as broadcasts
+            __syncwarp();
+            for (int j = lane; j < HALF; j += 32) bias_s[j] = __ldg(bias + n0 + j);
+            __syncwarp();
             float sum[HALF];
 #pragma unroll
             for (int j = 0; j < HALF; ++j) sum[j] = 0.f;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = 0; kb < num_kb; kb += a.group) {
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
@@ -317,11 +331,16 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
                     float y[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        y[j] = act_apply(fmaf(sum[c0 + j], inv_scale, __ldg(bias + n0 + c0 + j)), a.act);
+                        y[j] = act_apply(fmaf(sum[c0 + j], inv_scale, bias_s[c0 + j]), a.act);
                     if (Yf32) {
-                        float4* dst = reinterpret_cast<float4*>(Yf32 + row * a.ldy + n0 + c0);
+                        float* dst = Yf32 + row * a.ldy + n0 + c0;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t w[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) w[e] = __float_as_uint(y[8 * j + e]);
+                            st_global_v8(dst + 8 * j, w);
+                        }
                     }
                     if (Yhi) {
                         uint32_t hi[16], lo[16];
@@ -333,12 +352,15 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
                             hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
                             lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
                         }
-                        uint4* dh = reinterpret_cast<uint4*>(Yhi + row * a.ldy + n0 + c0);
-                        uint4* dl = reinterpret_cast<uint4*>(Ylo + row * a.ldy + n0 + c0);
+                        __half* dh = Yhi + row * a.ldy + n0 + c0;
+                        __half* dl = Ylo + row * a.ldy + n0 + c0;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                            dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        for (int j = 0; j < 2; ++j) {
+                            uint32_t wh[8], wl[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) { wh[e] = hi[8 * j + e]; wl[e] = lo[8 * j + e]; }
+                            st_global_v8(dh + 16 * j, wh);
+                            st_global_v8(dl + 16 * j, wl);
                         }
                     }
                 }
@@ -371,7 +393,7 @@ struct Cfg2 {
     static constexpr int W_BYTES = (BN / 2) * BK * 2;      // one plane of this CTA's half of the W tile (128 rows)
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;   // 64 KB
     static constexpr int TMEM_COLS = 2 * BN;
-    static constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256;
+    static constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256 + kEpilogueWarps * (BN / 2) * 4 /*bias*/;
 };
 
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int c_inner, int c_outer, uint64_t* leader_bar) {
@@ -417,6 +439,7 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
     uint64_t* tfull = bars + 2 * C::STAGES;   // [2]  (own) partial accumulator of one k-block complete
     uint64_t* tempty = tfull + 2;             // [2]  (leader's copy) drained by all 16 epilogue warps of the pair
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* bias_all = reinterpret_cast<float*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256);   // [warp][HALF], private per epilogue warp
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = cluster_ctarank();
@@ -472,7 +495,8 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
             int acc = 0; uint32_t acc_phase = 0;
             for (long long t = first; t < num_tiles; t += step) {
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&tempty[acc], acc_phase ^ 1);
+                    const bool g_first = kb % a.group == 0, g_last = (kb % a.group == a.group - 1) || kb == num_kb - 1;
+                    if (g_first) mbar_wait(&tempty[acc], acc_phase ^ 1);
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -482,14 +506,16 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
-                        umma_f16_2sm(d_tmem, a_lo + adv, w_hi + adv, idesc, k != 0);
+                        umma_f16_2sm(d_tmem, a_lo + adv, w_hi + adv, idesc, !(g_first && k == 0));
                         umma_f16_2sm(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
                         umma_f16_2sm(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
                     }
                     umma_commit_2sm(&empty[stage], 3);   // both CTAs' producers may refill the stage
-                    umma_commit_2sm(&tfull[acc], 3);     // both CTAs' epilogue warps may promote their half
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    if (g_last) {
+                        umma_commit_2sm(&tfull[acc], 3);     // both CTAs' epilogue warps may promote their half
+                        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    }
                 }
             }
         }
@@ -507,10 +533,14 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
             float* __restrict__ Yf32 = a.Yf32[z];
             __half* __restrict__ Yhi = a.Yhi[z];
             __half* __restrict__ Ylo = a.Ylo[z];
+            float* bias_s = bias_all + (warp - 2) * HALF;   // this warp's slice of the bias, read back as broadcasts
+            __syncwarp();
+            for (int j = lane; j < HALF; j += 32) bias_s[j] = __ldg(bias + n0 + j);
+            __syncwarp();
             float sum[HALF];
 #pragma unroll
             for (int j = 0; j < HALF; ++j) sum[j] = 0.f;
-            for (int kb = 0; kb < num_kb; ++kb) {
+            for (int kb = 0; kb < num_kb; kb += a.group) {
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
@@ -533,11 +563,16 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
                     float y[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        y[j] = act_apply(fmaf(sum[c0 + j], inv_scale, __ldg(bias + n0 + c0 + j)), a.act);
+                        y[j] = act_apply(fmaf(sum[c0 + j], inv_scale, bias_s[c0 + j]), a.act);
                     if (Yf32) {
-                        float4* dst = reinterpret_cast<float4*>(Yf32 + row * a.ldy + n0 + c0);
+                        float* dst = Yf32 + row * a.ldy + n0 + c0;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t w[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) w[e] = __float_as_uint(y[8 * j + e]);
+                            st_global_v8(dst + 8 * j, w);
+                        }
                     }
                     if (Yhi) {
                         uint32_t hi[16], lo[16];
@@ -549,12 +584,15 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
                             hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
                             lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
                         }
-                        uint4* dh = reinterpret_cast<uint4*>(Yhi + row * a.ldy + n0 + c0);
-                        uint4* dl = reinterpret_cast<uint4*>(Ylo + row * a.ldy + n0 + c0);
+                        __half* dh = Yhi + row * a.ldy + n0 + c0;
+                        __half* dl = Ylo + row * a.ldy + n0 + c0;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                            dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        for (int j = 0; j < 2; ++j) {
+                            uint32_t wh[8], wl[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) { wh[e] = hi[8 * j + e]; wl[e] = lo[8 * j + e]; }
+                            st_global_v8(dh + 16 * j, wh);
+                            st_global_v8(dl + 16 * j, wl);
                         }
                     }
                 }
