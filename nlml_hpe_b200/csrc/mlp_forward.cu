@@ -181,7 +181,8 @@ struct Workspace {
     float* f32[2] = {nullptr, nullptr};   // FP32 activations, ping-pong by layer parity
     __half* hi[2] = {nullptr, nullptr};   // FP16 hi/lo planes, ping-pong by layer parity
     __half* lo[2] = {nullptr, nullptr};
-    float* lat = nullptr;                 // [chunk][latent]
+    float* lat = nullptr;                 // [rows][latent]
+    int64_t rows = 0;                     // capacity in samples (<= plan chunk); grown on demand
 };
 }  // namespace
 
@@ -204,7 +205,8 @@ struct nlml_mlp_plan {
                            // 32768 samples: 1 -> 5.3e-4 deg, 2 -> 8.3e-4 deg (+3 % speed), 22 (never promote) -> 3.7e-3 deg
     bool two_cta = true;   // 256-wide layers: cta_group::2 kernel (false: 1-CTA MMAs with W multicast; NLML_TC_1CTA=1)
     int input_size = 0, latent = 0, head_in = 0;
-    int64_t chunk = 148 * 128;  // samples per pass: 148 M-tiles = whole waves of the persistent GEMMs
+    int64_t chunk = 4 * 148 * 128;  // samples per pass: 4 x 148 M-tiles = whole waves of the persistent GEMMs; the per-launch
+                                    // fixed costs of the 9 kernels amortise over it (1 wave: 42.1, 4 waves: 47.5 M poses/s)
     size_t f32_width[2] = {0, 0}, plane_width[2] = {0, 0};
     Workspace ws[2];
     int num_sms = 148;
@@ -212,6 +214,7 @@ struct nlml_mlp_plan {
     cudaStream_t streams[2] = {nullptr, nullptr};
     float* x_dev[2] = {nullptr, nullptr};
     float* y_dev[2] = {nullptr, nullptr};
+    int64_t host_rows = 0;   // capacity of x_dev / y_dev
 };
 
 namespace {
@@ -224,23 +227,30 @@ inline int act_of(int t) {
 }
 inline bool use_tc(const nlml_mlp_plan* pl, int t) { return pl->path == 0 && pl->tc[t]; }
 
-int alloc_workspace(nlml_mlp_plan* pl, Workspace& w) {
-    if (w.lat) return 0;
-    for (int i = 0; i < 2; ++i) {
-        NLML_CUDA(cudaMalloc(&w.f32[i], sizeof(float) * pl->chunk * pl->f32_width[i]));
-        if (pl->plane_width[i]) {
-            NLML_CUDA(cudaMalloc(&w.hi[i], sizeof(__half) * pl->chunk * pl->plane_width[i]));
-            NLML_CUDA(cudaMalloc(&w.lo[i], sizeof(__half) * pl->chunk * pl->plane_width[i]));
-            // pad columns of the input planes are written by split_planes_kernel; everything else is fully overwritten
-        }
-    }
-    NLML_CUDA(cudaMalloc(&w.lat, sizeof(float) * pl->chunk * pl->latent));
-    return 0;
-}
 void free_workspace(Workspace& w) {
     for (int i = 0; i < 2; ++i) { cudaFree(w.f32[i]); cudaFree(w.hi[i]); cudaFree(w.lo[i]); }
     cudaFree(w.lat);
     w = Workspace();
+}
+// Activation buffers for up to `rows` samples per pass (whole 128-row tiles).  Small batches (the reference's
+// batch-1 calls) get a small workspace; it grows, never shrinks.  Growing synchronises the device first because
+// earlier launches on any stream may still use the old buffers.
+int ensure_workspace(nlml_mlp_plan* pl, Workspace& w, int64_t rows) {
+    rows = std::min<int64_t>(pl->chunk, ceil_div(rows, 128) * 128);
+    if (w.rows >= rows) return 0;
+    if (w.rows) NLML_CUDA(cudaDeviceSynchronize());
+    free_workspace(w);
+    for (int i = 0; i < 2; ++i) {
+        NLML_CUDA(cudaMalloc(&w.f32[i], sizeof(float) * rows * pl->f32_width[i]));
+        if (pl->plane_width[i]) {
+            NLML_CUDA(cudaMalloc(&w.hi[i], sizeof(__half) * rows * pl->plane_width[i]));
+            NLML_CUDA(cudaMalloc(&w.lo[i], sizeof(__half) * rows * pl->plane_width[i]));
+            // pad columns of the input planes are written by split_planes_kernel; everything else is fully overwritten
+        }
+    }
+    NLML_CUDA(cudaMalloc(&w.lat, sizeof(float) * rows * pl->latent));
+    w.rows = rows;
+    return 0;
 }
 
 int launch_simt(nlml_mlp_plan* pl, LinearArgs& a, int nz, cudaStream_t st) {
@@ -365,7 +375,7 @@ int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, flo
         a.LAT = LAT_out ? LAT_out : w.lat;
         const bool next_tc = use_tc(pl, head_t(0, 1));
         for (int h = 0; h < 3; ++h) {
-            const size_t off = (size_t)h * pl->chunk * kHeadW;
+            const size_t off = (size_t)h * w.rows * kHeadW;
             a.Wh[h] = pl->W[head_t(h, 0)]; a.Bh[h] = pl->B[head_t(h, 0)];
             a.Hhi[h] = (!LAT_out && next_tc) ? w.hi[0] + off : nullptr;
             a.Hlo[h] = (!LAT_out && next_tc) ? w.lo[0] + off : nullptr;
@@ -401,7 +411,7 @@ int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, flo
         const bool next_tc = !last && !(fuse_tail && li == 2) && use_tc(pl, head_t(0, li + 1));
         float* yf[3]; __half* yh[3]; __half* yl[3];
         for (int h = 0; h < 3; ++h) {
-            const size_t off = (size_t)h * pl->chunk * out;
+            const size_t off = (size_t)h * w.rows * out;
             yf[h] = last ? YPR + h : (next_tc ? nullptr : w.f32[par] + off);
             yh[h] = next_tc ? w.hi[par] + off : nullptr;
             yl[h] = next_tc ? w.lo[par] + off : nullptr;
@@ -425,7 +435,7 @@ int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, flo
 }
 
 int forward_device(nlml_mlp_plan* pl, const float* X, int64_t N, int64_t ldx, float* YPR, float* LAT, cudaStream_t st) {
-    if (int rc = alloc_workspace(pl, pl->ws[0])) return rc;
+    if (int rc = ensure_workspace(pl, pl->ws[0], N)) return rc;
     for (int64_t s0 = 0; s0 < N; s0 += pl->chunk) {
         const int64_t n = std::min<int64_t>(pl->chunk, N - s0);
         if (int rc = forward_chunk(pl, X + s0 * ldx, n, ldx, YPR ? YPR + s0 * 3 : nullptr,
@@ -534,6 +544,7 @@ extern "C" int nlml_mlp_plan_create(const float* const* weights, const float* co
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg2::SMEM_BYTES));
     if (const char* e = std::getenv("NLML_TC_1CTA")) pl->two_cta = !(e[0] == '1');
     if (const char* e = std::getenv("NLML_TC_GROUP")) pl->tc_group = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("NLML_MLP_CHUNK_WAVES")) pl->chunk = (int64_t)pl->num_sms * 128 * std::max(1, std::atoi(e));
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<256>::SMEM_BYTES));
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<128>::SMEM_BYTES));
     NLML_CUDA(cudaFuncSetAttribute(tc::neck_kernel<kNeckIn, kNeckMid, kNeckLat, kHeadIn, kHeadW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNeckSmem));
@@ -597,15 +608,20 @@ extern "C" int nlml_mlp_forward_host_f32(nlml_mlp_plan* pl, const float* X_host,
     if (N < 0 || ldx < pl->input_size) return set_error(NLML_E_INVALID, "bad sizes");
     DeviceGuard guard(pl->device);
     const int F = pl->input_size;
-    if (!pl->streams[0]) {
+    if (!pl->streams[0])
+        for (int i = 0; i < 2; ++i) NLML_CUDA(cudaStreamCreateWithFlags(&pl->streams[i], cudaStreamNonBlocking));
+    const int64_t want = std::min<int64_t>(pl->chunk, ceil_div(std::max<int64_t>(N, 1), 128) * 128);
+    if (pl->host_rows < want) {
+        if (pl->host_rows) NLML_CUDA(cudaDeviceSynchronize());
         for (int i = 0; i < 2; ++i) {
-            NLML_CUDA(cudaStreamCreateWithFlags(&pl->streams[i], cudaStreamNonBlocking));
-            NLML_CUDA(cudaMalloc(&pl->x_dev[i], sizeof(float) * pl->chunk * F));
-            NLML_CUDA(cudaMalloc(&pl->y_dev[i], sizeof(float) * pl->chunk * 3));
+            cudaFree(pl->x_dev[i]); cudaFree(pl->y_dev[i]);
+            NLML_CUDA(cudaMalloc(&pl->x_dev[i], sizeof(float) * want * F));
+            NLML_CUDA(cudaMalloc(&pl->y_dev[i], sizeof(float) * want * 3));
         }
+        pl->host_rows = want;
     }
     for (int i = 0; i < 2; ++i)
-        if (int rc = alloc_workspace(pl, pl->ws[i])) return rc;
+        if (int rc = ensure_workspace(pl, pl->ws[i], N)) return rc;
     int slot = 0;
     for (int64_t s0 = 0; s0 < N; s0 += pl->chunk, slot ^= 1) {
         const int64_t n = std::min<int64_t>(pl->chunk, N - s0);
