@@ -55,7 +55,8 @@ void nlml_tucker_plan_destroy(nlml_tucker_plan* plan);
  * iters / lr / clip are num_iterations, learning_rate (TD_Tester.py:127) and the max_norm of :150.
  * Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
  * kernel_hint: 0 = choose by N and ranks, 1 = thread-per-sample kernel (throughput, ranks 5,3,3,3),
- * 2 = CTA-per-sample kernel (run-time ranks), 3 = warp-per-sample kernel (latency, ranks 5,3,3,3). */
+ * 2 = CTA-per-sample kernel (run-time ranks), 3 = warp-per-sample kernel (latency, ranks 5,3,3,3),
+ * 4 = thread-per-sample kernel with q resident in tensor memory (12 warps per SM; measured equal to 1). */
 int nlml_tucker_fit_f32(nlml_tucker_plan* plan, const float* X_dev, int64_t N, int64_t ldx,
                         int iters, float lr, float clip, float* P_out_dev, int64_t ldp,
                         int kernel_hint, void* stream);
@@ -109,6 +110,9 @@ int nlml_mlp_set_path(nlml_mlp_plan* plan, int path);
  * denominator of the Tucker-fit kernel's FP32-pipe roofline.  Runs a register-only FFMA loop.
  * ------------------------------------------------------------------------------------------ */
 int nlml_measure_fp32_tflops(int device, double* tflops_out);
+/* Same loop with three run-time register operands per FFMA (no immediates): the register-file-limited rate
+ * that bounds an FMA stream whose multiplier and addend both change, like the fit kernel's inner loop. */
+int nlml_measure_fp32_tflops_3reg(int device, double* tflops_out);
 
 #ifdef __cplusplus
 }

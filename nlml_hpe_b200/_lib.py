@@ -19,7 +19,7 @@ EXPORTS = [
     "nlml_tucker_fit_host_f32", "nlml_tucker_launch_count",
     "nlml_mlp_plan_create", "nlml_mlp_plan_destroy", "nlml_mlp_forward_f32",
     "nlml_mlp_forward_host_f32", "nlml_mlp_latent_f32", "nlml_mlp_launch_count", "nlml_mlp_set_path",
-    "nlml_measure_fp32_tflops",
+    "nlml_measure_fp32_tflops", "nlml_measure_fp32_tflops_3reg",
 ]
 
 _lib = None
@@ -59,6 +59,7 @@ def load():
     lib.nlml_mlp_launch_count.restype = i64
     lib.nlml_mlp_set_path.argtypes = [vp, i32]
     lib.nlml_measure_fp32_tflops.argtypes = [i32, c_double_p]
+    lib.nlml_measure_fp32_tflops_3reg.argtypes = [i32, c_double_p]
     _lib = lib
     return lib
 

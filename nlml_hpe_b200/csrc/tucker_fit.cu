@@ -67,9 +67,64 @@ __global__ void fold_kernel(const double* __restrict__ M, int ri, int ry, int rp
 }
 
 // ---------------------------------------------------------------------------------------------
+// tensor memory as per-thread storage: a thread of warp w owns TMEM lane 32*(w%4) + laneid and reads / writes
+// 32 consecutive columns of it per instruction (tcgen05.ld/st .32x32b.x32)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc_cols(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free_cols(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_load32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_store32(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+          "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+          "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+          "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+          "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_store_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// q accessor for the TMEM-resident variant (same interface as QStrided in tucker_math.h)
+struct QTmem {
+    uint32_t taddr;   // this thread's lane, first column of its q
+    template <int R0, int CNT>
+    __device__ __forceinline__ void load(int /*n*/, float (&v)[32]) const { tmem_load32(taddr + R0, v); }
+};
+
+// ---------------------------------------------------------------------------------------------
 // thread-per-sample kernel
 // ---------------------------------------------------------------------------------------------
-template <int RI, int RY, int RP, int RR, int THREADS, int NS>
+// QTMEM: keep q in tensor memory instead of shared memory.  q is what limits the SM to 8 resident warps
+// (69 KB per 128 samples); in TMEM (unused by this kernel otherwise) a 384-thread CTA fits and 12 warps hide the
+// FMA / shared-memory latencies of the iteration better.
+template <int RI, int RY, int RP, int RR, int THREADS, int NS, bool QTMEM = false>
 struct TpsCfg {
     static constexpr int R = RI * RY * RP * RR;
     static constexpr int RPAD = (R + 3) / 4 * 4;
@@ -81,11 +136,15 @@ struct TpsCfg {
     static constexpr int XSTR = THREADS + 2;   // == 2 (mod 8): transposed tile stores are conflict-free
     static constexpr int S_FLOATS = nBCD * NAP;
     static constexpr int SAMPLES = THREADS * NS;   // samples per CTA; thread t owns samples t, t+THREADS, ...
-    static constexpr int Q_FLOATS = R * SAMPLES;   // [NS][R][THREADS]
+    static constexpr int Q_FLOATS = QTMEM ? 0 : R * SAMPLES;   // [NS][R][THREADS] (shared-memory variant)
+    static constexpr int QCOLS = (RPAD + 31) / 32 * 32;        // TMEM columns per thread (TMEM variant)
+    static constexpr int TMEM_COLS = 512;
+    static_assert(!QTMEM || (NS == 1 && (THREADS / 128) * QCOLS <= TMEM_COLS && THREADS % 128 == 0), "TMEM budget");
     static constexpr int SCR_FLOATS = tri(RY) * tri(RP) * SAMPLES;  // [NS][nB*nC][THREADS] scratch of tucker_gradient
     static constexpr int TILE_FLOATS = FC * XSTR + FC * RPAD;
 
-    static constexpr size_t SMEM_BYTES = sizeof(float) * (S_FLOATS + Q_FLOATS + SCR_FLOATS);
+    static_assert(!QTMEM || TILE_FLOATS <= SCR_FLOATS, "phase-A tiles alias the scratch buffer in the TMEM variant");
+    static constexpr size_t SMEM_BYTES = sizeof(float) * (S_FLOATS + Q_FLOATS + SCR_FLOATS) + 16;
 };
 
 __device__ __forceinline__ float4 load_row4(const float* __restrict__ row, int f, int F, bool vec_ok) {
@@ -101,9 +160,9 @@ __device__ __forceinline__ float4 load_row4(const float* __restrict__ row, int f
     return v;
 }
 
-template <int RI, int RY, int RP, int RR, int THREADS, int NS, int MINB>
+template <int RI, int RY, int RP, int RR, int THREADS, int NS, int MINB, bool QTMEM>
 __global__ void __launch_bounds__(THREADS, MINB) tucker_fit_tps_kernel(const __grid_constant__ TuckerArgs a) {
-    using C = TpsCfg<RI, RY, RP, RR, THREADS, NS>;
+    using C = TpsCfg<RI, RY, RP, RR, THREADS, NS, QTMEM>;
     extern __shared__ __align__(16) float smem[];
     float* S_s = smem;
     float* q_s = smem + C::S_FLOATS;
@@ -111,12 +170,24 @@ __global__ void __launch_bounds__(THREADS, MINB) tucker_fit_tps_kernel(const __g
     float* xs = q_s;                     // [FC][XSTR]   (phase A only)
     float* ws = q_s + C::FC * C::XSTR;   // [FC][RPAD]   (phase A only)
     static_assert(C::TILE_FLOATS <= C::R * THREADS, "phase-A tiles must fit inside one sample slab of q");
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(scr_s + C::SCR_FLOATS);
+    uint32_t q_taddr = 0;
+    if constexpr (QTMEM) {
+        if (threadIdx.x < 32) tmem_alloc_cols(tmem_slot, C::TMEM_COLS);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int w = threadIdx.x >> 5;
+        q_taddr = *tmem_slot + ((uint32_t)((w & 3) * 32) << 16) + (uint32_t)((w >> 2) * C::QCOLS);
+    }
 
     const int tid = threadIdx.x;
     const long long s0 = (long long)blockIdx.x * C::SAMPLES;
     const bool vec_ok = a.vec_ok != 0;
     const int F = a.F;
 
+    // S is broadcast from shared memory.  (Measured alternative: S in the kernel parameters, read through the
+    // constant path with LDC c[0x0][R+off], ran at 473 k-602 k poses/s against 913 k.)
     for (int i = tid; i < C::S_FLOATS / 4; i += THREADS)
         reinterpret_cast<float4*>(S_s)[i] = __ldg(reinterpret_cast<const float4*>(a.S) + i);
 
@@ -124,7 +195,7 @@ __global__ void __launch_bounds__(THREADS, MINB) tucker_fit_tps_kernel(const __g
     // (the tiles alias the q buffer of the pass in flight only: pass n stages its tiles in q slab n)
 #pragma unroll 1
     for (int n = 0; n < NS; ++n) {
-    float* qn_s = q_s + n * (C::R * THREADS);
+    float* qn_s = QTMEM ? scr_s : q_s + n * (C::R * THREADS);   // TMEM variant: tiles live in the scratch buffer
     xs = qn_s;
     ws = qn_s + C::FC * C::XSTR;
     float acc[C::RPAD];
@@ -166,8 +237,19 @@ __global__ void __launch_bounds__(THREADS, MINB) tucker_fit_tps_kernel(const __g
         }
         __syncthreads();
     }
+    if constexpr (QTMEM) {
 #pragma unroll
-    for (int r = 0; r < C::R; ++r) qn_s[r * THREADS + tid] = acc[r];
+        for (int c = 0; c < C::QCOLS / 32; ++c) {
+            float v[32];
+#pragma unroll
+            for (int x = 0; x < 32; ++x) v[x] = (32 * c + x < C::RPAD) ? acc[(32 * c + x < C::RPAD) ? 32 * c + x : 0] : 0.f;
+            tmem_store32(q_taddr + 32 * c, v);
+        }
+        tmem_store_wait();
+    } else {
+#pragma unroll
+        for (int r = 0; r < C::R; ++r) qn_s[r * THREADS + tid] = acc[r];
+    }
     __syncthreads();  // S_s complete, tiles dead
     }
 
@@ -181,8 +263,12 @@ __global__ void __launch_bounds__(THREADS, MINB) tucker_fit_tps_kernel(const __g
 #pragma unroll 1
     for (int it = 0; it < a.T; ++it) {
         float g[NS][C::NP];
-        tucker_gradient<RI, RY, RP, RR, C::NAP, NS>(p, S_s, q_s + tid, THREADS, C::R * THREADS, scr_s + tid, THREADS,
-                                                    tri(RY) * tri(RP) * THREADS, a.rows_y, a.rows_p, a.rows_r, g);
+        if constexpr (QTMEM)
+            tucker_gradient<RI, RY, RP, RR, C::NAP, NS>(p, S_s, QTmem{q_taddr}, scr_s + tid, THREADS,
+                                                        tri(RY) * tri(RP) * THREADS, a.rows_y, a.rows_p, a.rows_r, g);
+        else
+            tucker_gradient<RI, RY, RP, RR, C::NAP, NS>(p, S_s, QStrided{q_s + tid, THREADS, C::R * THREADS}, scr_s + tid, THREADS,
+                                                        tri(RY) * tri(RP) * THREADS, a.rows_y, a.rows_p, a.rows_r, g);
 #pragma unroll
         for (int n = 0; n < NS; ++n) clip_and_step<C::NP>(p[n], g[n], lr, clip);
     }
@@ -194,6 +280,11 @@ __global__ void __launch_bounds__(THREADS, MINB) tucker_fit_tps_kernel(const __g
 #pragma unroll
             for (int i = 0; i < C::NP; ++i) out[i] = p[n][i];
         }
+    }
+    if constexpr (QTMEM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x < 32) tmem_free_cols(*tmem_slot, C::TMEM_COLS);
     }
 }
 
@@ -625,6 +716,30 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// same loop with three register operands per FFMA (multiplier and addend are run-time values held in registers,
+// as in the fit kernel's inner loop): measures the register-file-limited FFMA rate
+__global__ void __launch_bounds__(256) ffma_3reg_kernel(float* out, const float* in, int iters) {
+    float a[8], b[8], c[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        a[k] = threadIdx.x * 1e-3f + k;
+        b[k] = in[(threadIdx.x + k) & 255];
+        c[k] = in[(threadIdx.x + 8 + k) & 255];
+    }
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = fmaf(a[k], b[(k + j) & 7], c[(k + 3 * j) & 7]);
+        }
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += a[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 }  // namespace nlml
 
 // =============================================================================================
@@ -657,10 +772,14 @@ constexpr int kTpsThreads = 128;   // threads per CTA of the thread-per-sample k
 constexpr int kTpsSamples = 1;     // samples per thread.  2 halves the shared-memory wavefronts per sample but the q
                                    // buffer then limits the SM to 4 warps: measured 740 k poses/s against 919 k at 1.
 constexpr int kTpsMinBlocks = 2;
+constexpr int kTpsBigThreads = 384;  // TMEM-resident-q variant: one 12-warp CTA per SM
+// measured: 913 k poses/s with q in TMEM (12 warps/SM) vs 912 k with q in shared memory (8 warps/SM) -- the kernel
+// is bound by the 3-register-operand FFMA rate, not by latency -- so the variant is opt-in (kernel_hint 4) only
 constexpr int kCtaThreads = 128;
 constexpr int kWpsWarps = 4;
 constexpr int64_t kWpsCrossover = 8192;  // below this the warp-per-sample kernel finishes sooner (profiles/)
 using TpsDefault = TpsCfg<5, 3, 3, 3, kTpsThreads, kTpsSamples>;
+using TpsBig = TpsCfg<5, 3, 3, 3, kTpsBigThreads, 1, true>;
 size_t wps_smem_bytes(int F) { return sizeof(float) * kWpsWarps * ((F + 3) / 4 * 4 + 64); }
 
 int launch_fit(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int iters, float lr, float clip,
@@ -678,18 +797,22 @@ int launch_fit(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int
     a.vec_ok = (pl->F % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
     // crossover: below ~one thread-per-sample wave the 3000-step chain is latency bound and the
     // CTA-per-sample kernel finishes sooner
-    const bool use_tps = pl->fast && (hint == 1 || (hint == 0 && N >= kWpsCrossover));
+    const bool use_tps = pl->fast && (hint == 1 || hint == 4 || (hint == 0 && N >= kWpsCrossover));
     const bool use_wps = pl->fast && (hint == 3 || (hint == 0 && N < kWpsCrossover));
-    if ((hint == 1 || hint == 3) && !pl->fast)
+    if ((hint == 1 || hint == 3 || hint == 4) && !pl->fast)
         return set_error(NLML_E_UNSUPPORTED, "thread/warp-per-sample kernels are built for ranks (5,3,3,3) only");
     if (use_wps) {
         auto kern = tucker_fit_wps_kernel<5, 3, 3, 3, kWpsWarps>;
         const unsigned grid = (unsigned)ceil_div(N, kWpsWarps);
         kern<<<grid, 32 * kWpsWarps, wps_smem_bytes(pl->F), st>>>(a);
     } else if (use_tps) {
-        auto kern = tucker_fit_tps_kernel<5, 3, 3, 3, kTpsThreads, kTpsSamples, kTpsMinBlocks>;
-        const unsigned grid = (unsigned)ceil_div(N, TpsDefault::SAMPLES);
-        kern<<<grid, kTpsThreads, TpsDefault::SMEM_BYTES, st>>>(a);
+        if (hint == 4) {
+            auto kern = tucker_fit_tps_kernel<5, 3, 3, 3, kTpsBigThreads, 1, 1, true>;
+            kern<<<(unsigned)ceil_div(N, TpsBig::SAMPLES), kTpsBigThreads, TpsBig::SMEM_BYTES, st>>>(a);
+        } else {
+            auto kern = tucker_fit_tps_kernel<5, 3, 3, 3, kTpsThreads, kTpsSamples, kTpsMinBlocks, false>;
+            kern<<<(unsigned)ceil_div(N, TpsDefault::SAMPLES), kTpsThreads, TpsDefault::SMEM_BYTES, st>>>(a);
+        }
     } else {
         auto kern = tucker_fit_cta_kernel<kCtaThreads>;
         kern<<<(unsigned)N, kCtaThreads, pl->cta_smem, st>>>(a, pl->st_in_smem ? 1 : 0);
@@ -762,8 +885,10 @@ extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, i
 
     pl->fast = (r_id == 5 && r_y == 3 && r_p == 3 && r_r == 3);
     if (pl->fast) {
-        auto kern = tucker_fit_tps_kernel<5, 3, 3, 3, kTpsThreads, kTpsSamples, kTpsMinBlocks>;
+        auto kern = tucker_fit_tps_kernel<5, 3, 3, 3, kTpsThreads, kTpsSamples, kTpsMinBlocks, false>;
         NLML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpsDefault::SMEM_BYTES));
+        NLML_CUDA(cudaFuncSetAttribute(tucker_fit_tps_kernel<5, 3, 3, 3, kTpsBigThreads, 1, 1, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpsBig::SMEM_BYTES));
         if (wps_smem_bytes(F) > 200 * 1024) pl->fast = false;
         else
             NLML_CUDA(cudaFuncSetAttribute(tucker_fit_wps_kernel<5, 3, 3, 3, kWpsWarps>,
@@ -805,7 +930,7 @@ extern "C" int nlml_tucker_fit_f32(nlml_tucker_plan* pl, const float* X_dev, int
     if (N < 0 || ldx < pl->F || ldp < 3 + pl->ri || iters < 0)
         return set_error(NLML_E_INVALID, "bad sizes: N=%lld ldx=%lld (F=%d) ldp=%lld (need >= %d) iters=%d",
                          (long long)N, (long long)ldx, pl->F, (long long)ldp, 3 + pl->ri, iters);
-    if (kernel_hint < 0 || kernel_hint > 3) return set_error(NLML_E_INVALID, "kernel_hint must be 0..3");
+    if (kernel_hint < 0 || kernel_hint > 4) return set_error(NLML_E_INVALID, "kernel_hint must be 0..4");
     DeviceGuard guard(pl->device);
     return launch_fit(pl, X_dev, N, ldx, iters, lr, clip, P_out_dev, ldp, kernel_hint, (cudaStream_t)stream);
 }
@@ -818,7 +943,7 @@ extern "C" int nlml_tucker_fit_host_f32(nlml_tucker_plan* pl, const float* X_hos
     const int np = 3 + pl->ri;
     if (!pl->streams[0]) {
         // two thread-per-sample waves per chunk keeps every SM busy while the next chunk is in flight
-        pl->chunk = (int64_t)pl->num_sms * kTpsMinBlocks * TpsDefault::SAMPLES * 2;
+        pl->chunk = (int64_t)pl->num_sms * kTpsMinBlocks * TpsDefault::SAMPLES * 4;   // 4 waves per chunk
         for (int i = 0; i < 2; ++i) {
             NLML_CUDA(cudaStreamCreateWithFlags(&pl->streams[i], cudaStreamNonBlocking));
             NLML_CUDA(cudaMalloc(&pl->x_dev[i], sizeof(float) * (size_t)pl->chunk * pl->F));
@@ -843,7 +968,11 @@ extern "C" int nlml_tucker_fit_host_f32(nlml_tucker_plan* pl, const float* X_hos
 
 extern "C" int64_t nlml_tucker_launch_count(const nlml_tucker_plan* pl) { return pl ? pl->launches : 0; }
 
-extern "C" int nlml_measure_fp32_tflops(int device, double* tflops_out) {
+static int measure_ffma(int device, int three_reg, double* tflops_out);
+extern "C" int nlml_measure_fp32_tflops(int device, double* tflops_out) { return measure_ffma(device, 0, tflops_out); }
+extern "C" int nlml_measure_fp32_tflops_3reg(int device, double* tflops_out) { return measure_ffma(device, 1, tflops_out); }
+
+static int measure_ffma(int device, int three_reg, double* tflops_out) {
     if (!tflops_out) return set_error(NLML_E_INVALID, "null pointer argument");
     if (int rc = check_device(device)) return rc;
     DeviceGuard guard(device);
@@ -851,14 +980,22 @@ extern "C" int nlml_measure_fp32_tflops(int device, double* tflops_out) {
     NLML_CUDA(cudaGetDeviceProperties(&prop, device));
     const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
     float* out = nullptr;
+    float* in = nullptr;
     NLML_CUDA(cudaMalloc(&out, sizeof(float) * blocks * threads));
+    NLML_CUDA(cudaMalloc(&in, sizeof(float) * 256));
+    {
+        float h[256];
+        for (int i = 0; i < 256; ++i) h[i] = 0.9990f + 1e-6f * i;
+        NLML_CUDA(cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice));
+    }
     cudaEvent_t e0, e1;
     NLML_CUDA(cudaEventCreate(&e0));
     NLML_CUDA(cudaEventCreate(&e1));
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
         NLML_CUDA(cudaEventRecord(e0));
-        ffma_peak_kernel<<<blocks, threads>>>(out, iters);
+        if (three_reg) ffma_3reg_kernel<<<blocks, threads>>>(out, in, iters);
+        else ffma_peak_kernel<<<blocks, threads>>>(out, iters);
         NLML_CUDA(cudaEventRecord(e1));
         NLML_CUDA(cudaEventSynchronize(e1));
         float ms = 0.f;
@@ -869,6 +1006,7 @@ extern "C" int nlml_measure_fp32_tflops(int device, double* tflops_out) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(out);
+    cudaFree(in);
     *tflops_out = best;
     return 0;
 }

@@ -107,18 +107,50 @@ NLML_HD void clip_and_step(float* p, float* g, float lr, float clip) {
     for (int i = 0; i < NP; ++i) p[i] = sub_rn(p[i], mul_rn(lr, mul_rn(g[i], coef)));
 }
 
+// q accessor for memory-resident q: element r of sample n at q[n*sample + r*stride] (a shared-memory column on
+// the GPU, a plain array on the host).  The thread-per-sample kernel's other accessor reads q from tensor memory.
+struct QStrided {
+    const float* q;
+    int stride, sample;
+    template <int R0, int CNT>
+    NLML_HD void load(int n, float (&v)[32]) const {
+#pragma unroll
+        for (int x = 0; x < CNT; ++x) v[x] = q[n * sample + (R0 + x) * stride];
+    }
+};
+
+// Static walk over q in chunks of 32: chunk C covers r in [32C, min(32C+32, R)), r = i*JKL + jkl.
+template <int RI, int JKL, class QA, int C>
+struct QLoadChunk {
+    static constexpr int R = RI * JKL, R0 = 32 * C, CNT = (R - R0) < 32 ? (R - R0) : 32;
+    NLML_HD static void run(const QA& qa, int n, const float (&tq)[JKL], const float* u, float (&lin_u)[RI], float (&e)[JKL]) {
+        if constexpr (R0 < R) {
+            float v[32];
+            qa.template load<R0, CNT>(n, v);
+#pragma unroll
+            for (int x = 0; x < CNT; ++x) {
+                constexpr int dummy = 0; (void)dummy;
+                const int r = R0 + x, i = r / JKL, jkl = r % JKL;   // compile-time after unrolling
+                lin_u[i] = fmaf(v[x], tq[jkl], lin_u[i]);
+                e[jkl] = fmaf(v[x], u[i], e[jkl]);
+            }
+            QLoadChunk<RI, JKL, QA, C + 1>::run(qa, n, tq, u, lin_u, e);
+        }
+    }
+};
+
 // One full gradient evaluation for NS samples held by one thread (fixed small ranks).
 //   S : folded Gram tensor laid out [nB*nC*nD][NAP] (NAP = nA padded to a multiple of 4), read-only, identical
 //       for all samples (shared-memory broadcast on the GPU).  Every element loaded from S feeds 2*NS FMAs,
 //       which is what keeps the kernel off the shared-memory wavefront limit.
-//   q : q = W2 x of sample n, element r at q[n*qsample + r*qstride].
+//   qa : accessor for q = W2 x; qa.load<R0,CNT>(n, v) fetches q[R0 .. R0+CNT) of sample n, 32 at a time.
 //   scr : nB*nC floats of scratch per sample, element k of sample n at scr[n*ssample + k*sstride]
 //         (a shared-memory column on the GPU).
 //   rows_* : cosine rows of the three angle factors.
 // Reads p[n][3+RI], writes g[n][3+RI].
-template <int RI, int RY, int RP, int RR, int NAP, int NS>
-NLML_HD void tucker_gradient(const float (&p)[NS][3 + RI], const float* __restrict__ S, const float* q, int qstride,
-                             int qsample, float* scr, int sstride, int ssample, const float* rows_y,
+template <int RI, int RY, int RP, int RR, int NAP, int NS, class QA>
+NLML_HD void tucker_gradient(const float (&p)[NS][3 + RI], const float* __restrict__ S, const QA& qa,
+                             float* scr, int sstride, int ssample, const float* rows_y,
                              const float* rows_p, const float* rows_r, float (&g)[NS][3 + RI]) {
     constexpr int nA = tri(RI), nB = tri(RY), nC = tri(RP), nD = tri(RR);
     float cy[NS][RY], dcy[NS][RY], cp[NS][RP], dcp[NS][RP], cr[NS][RR], dcr[NS][RR], u[NS][RI];
@@ -209,8 +241,23 @@ NLML_HD void tucker_gradient(const float (&p)[NS][3 + RI], const float* __restri
         sym_backprop<RP>(GP[n], cp[n], dp);
         sym_backprop<RR>(GR[n], cr[n], dr);
 
-        // linear term -q.z : d/du_i = -sum_jkl q[ijkl] cy_j cp_k cr_l ; e[jkl] = sum_i u_i q[ijkl]
-        float ey[RY], ep[RP], er[RR], lin_u[RI];
+        // linear term -q.z : d/du_i = -sum_jkl q[ijkl] t_jkl with t = cy (x) cp (x) cr ; e[jkl] = sum_i u_i q[ijkl].
+        // q is consumed in its storage order (i slowest), 32 consecutive elements at a time.
+        constexpr int JKL = RY * RP * RR, R = RI * JKL;
+        float tq[JKL], e[JKL], lin_u[RI];
+#pragma unroll
+        for (int j = 0; j < RY; ++j)
+#pragma unroll
+            for (int k = 0; k < RP; ++k)
+#pragma unroll
+                for (int l = 0; l < RR; ++l) {
+                    tq[(j * RP + k) * RR + l] = cy[n][j] * cp[n][k] * cr[n][l];
+                    e[(j * RP + k) * RR + l] = 0.f;
+                }
+#pragma unroll
+        for (int i = 0; i < RI; ++i) lin_u[i] = 0.f;
+        float ey[RY], ep[RP], er[RR];
+        QLoadChunk<RI, JKL, QA, 0>::run(qa, n, tq, u[n], lin_u, e);
 #pragma unroll
         for (int j = 0; j < RY; ++j) ey[j] = 0.f;
 #pragma unroll
@@ -218,31 +265,20 @@ NLML_HD void tucker_gradient(const float (&p)[NS][3 + RI], const float* __restri
 #pragma unroll
         for (int l = 0; l < RR; ++l) er[l] = 0.f;
 #pragma unroll
-        for (int i = 0; i < RI; ++i) lin_u[i] = 0.f;
-        const float* qn = q + n * qsample;
-#pragma unroll
-        for (int j = 0; j < RY; ++j) {
+        for (int j = 0; j < RY; ++j)
 #pragma unroll
             for (int k = 0; k < RP; ++k) {
                 const float yk = cy[n][j] * cp[n][k];
                 float e_jk = 0.f;  // sum_l e[jkl] cr_l
 #pragma unroll
                 for (int l = 0; l < RR; ++l) {
-                    const float t_jkl = yk * cr[n][l];
-                    float e = 0.f;  // sum_i u_i q[ijkl]
-#pragma unroll
-                    for (int i = 0; i < RI; ++i) {
-                        const float qv = qn[(((i * RY + j) * RP + k) * RR + l) * qstride];
-                        lin_u[i] = fmaf(qv, t_jkl, lin_u[i]);
-                        e = fmaf(qv, u[n][i], e);
-                    }
-                    er[l] = fmaf(e, yk, er[l]);
-                    e_jk = fmaf(e, cr[n][l], e_jk);
+                    const float ev = e[(j * RP + k) * RR + l];
+                    er[l] = fmaf(ev, yk, er[l]);
+                    e_jk = fmaf(ev, cr[n][l], e_jk);
                 }
                 ey[j] = fmaf(e_jk, cp[n][k], ey[j]);
                 ep[k] = fmaf(e_jk, cy[n][j], ep[k]);
             }
-        }
         float gy = 0.f, gp = 0.f, gr = 0.f;
 #pragma unroll
         for (int j = 0; j < RY; ++j) gy = fmaf(dy[j] - ey[j], dcy[n][j], gy);

@@ -69,5 +69,5 @@ def hostcheck():
     out = os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so")
     hdr = os.path.join(ROOT, "nlml_hpe_b200", "csrc", "tucker_math.h")
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        subprocess.check_call(["g++", "-O2", "-mfma", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, src])
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-mfma", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, src])
     return ctypes.CDLL(out)

@@ -37,7 +37,7 @@ extern "C" int hostcheck_tucker_fit_5333(const float* W2, int F, const double* r
         for (int it = 0; it < T; ++it) {
             float g[1][NP];
             float scr[tri(RY) * tri(RP)];
-            tucker_gradient<RI, RY, RP, RR, NAP, 1>(p, S.data(), q, 1, 0, scr, 1, 0, ry, rp, rr, g);
+            tucker_gradient<RI, RY, RP, RR, NAP, 1>(p, S.data(), QStrided{q, 1, 0}, scr, 1, 0, ry, rp, rr, g);
             clip_and_step<NP>(p[0], g[0], lr, clip);
         }
         for (int i = 0; i < NP; ++i) P[s * NP + i] = p[0][i];
@@ -75,7 +75,7 @@ extern "C" int hostcheck_tucker_grad_5333(const float* W2, int F, const double* 
         for (int i = 0; i < NP; ++i) pin[0][i] = pin[1][i] = Pin[s * NP + i];
         float q2[2][R];
         for (int r = 0; r < R; ++r) q2[0][r] = q2[1][r] = q[r];
-        tucker_gradient<RI, RY, RP, RR, NAP, 2>(pin, S.data(), &q2[0][0], 1, R, &scr[0][0], 1, tri(RY) * tri(RP), ry, rp, rr, gout);
+        tucker_gradient<RI, RY, RP, RR, NAP, 2>(pin, S.data(), QStrided{&q2[0][0], 1, R}, &scr[0][0], 1, tri(RY) * tri(RP), ry, rp, rr, gout);
         for (int i = 0; i < NP; ++i) G[s * NP + i] = gout[1][i];
         for (int i = 0; i < NP; ++i) if (gout[0][i] != gout[1][i]) return 1;
     }

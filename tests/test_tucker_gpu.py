@@ -23,7 +23,7 @@ def _gpu(x):
     return torch.from_numpy(np.ascontiguousarray(x)).cuda()
 
 
-@pytest.mark.parametrize("kernel", ["thread_per_sample", "cta_per_sample", "warp_per_sample"])
+@pytest.mark.parametrize("kernel", ["thread_per_sample", "thread_per_sample_tmem", "cta_per_sample", "warp_per_sample"])
 def test_golden_sgd3000_shipped(fitter, X1k, tucker_golden, kernel):
     P = fitter.fit(_gpu(X1k), 3000, kernel=kernel).cpu().numpy()
     ref = tucker_golden["sgd3000_shipped_P"]
@@ -32,7 +32,7 @@ def test_golden_sgd3000_shipped(fitter, X1k, tucker_golden, kernel):
     assert np.abs(P[idx, 3:] - ref[:, 3:]).max() < 1e-4
 
 
-@pytest.mark.parametrize("kernel", ["thread_per_sample", "cta_per_sample", "warp_per_sample"])
+@pytest.mark.parametrize("kernel", ["thread_per_sample", "thread_per_sample_tmem", "cta_per_sample", "warp_per_sample"])
 def test_golden_sgd3000_synthetic_core(rows, tucker_golden, kernel, cuda_lib):
     """BASELINE.json config 2: synthetic core of the configured rank."""
     from nlml_hpe_b200 import synthetic
@@ -51,7 +51,7 @@ def test_golden_sgd200_and_edges(fitter, X1k, tucker_golden):
     d = np.abs(P[:, :3] - tucker_golden["sgd200_shipped_P"][:, :3]).max(1) * DEG
     # transiently ill-conditioned samples around T~200: the reference does not reproduce itself there
     assert np.quantile(d, 0.9) < 1e-3 and d.max() < 5e-2
-    for kernel in ("thread_per_sample", "cta_per_sample", "warp_per_sample"):
+    for kernel in ("thread_per_sample", "thread_per_sample_tmem", "cta_per_sample", "warp_per_sample"):
         Pe = fitter.fit(_gpu(tucker_golden["sgd500_edge_X"]), 500, kernel=kernel).cpu().numpy()
         ref = tucker_golden["sgd500_edge_P"]
         assert np.abs(Pe[:, :3] - ref[:, :3]).max() * DEG < TOL_DEG
@@ -73,6 +73,8 @@ def test_kernels_agree_and_are_deterministic(fitter, X1k):
     b = fitter.fit(x, 3000, kernel="thread_per_sample")
     c = fitter.fit(x, 3000, kernel="cta_per_sample")
     d = fitter.fit(x, 3000, kernel="warp_per_sample")
+    e = fitter.fit(x, 3000, kernel="thread_per_sample_tmem")
+    assert torch.equal(a, e)          # same statements, q merely lives in tensor memory instead of shared memory
     assert torch.equal(a, b)
     assert torch.equal(d, fitter.fit(x, 3000, kernel="warp_per_sample"))
     assert (a[:, :3] - c[:, :3]).abs().max().item() * DEG < TOL_DEG
@@ -83,10 +85,10 @@ def test_kernels_agree_and_are_deterministic(fitter, X1k):
 def test_ragged_batch_sizes(fitter, X1k, n):
     full = fitter.fit(_gpu(X1k[:300]), 100, kernel="thread_per_sample")
     wfull = fitter.fit(_gpu(X1k[:300]), 100, kernel="warp_per_sample")
-    for kernel in ("thread_per_sample", "cta_per_sample", "warp_per_sample"):
+    for kernel in ("thread_per_sample", "thread_per_sample_tmem", "cta_per_sample", "warp_per_sample"):
         part = fitter.fit(_gpu(X1k[:n]), 100, kernel=kernel)
         assert part.shape == (n, 8)
-        if n and kernel == "thread_per_sample":
+        if n and kernel.startswith("thread_per_sample"):
             assert torch.equal(part, full[:n])     # a sample's result does not depend on its batch
         if n and kernel == "warp_per_sample":
             assert torch.equal(part, wfull[:n])
