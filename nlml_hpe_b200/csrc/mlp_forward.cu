@@ -626,8 +626,11 @@ extern "C" int nlml_mlp_forward_host_f32(nlml_mlp_plan* pl, const float* X_host,
     for (int64_t s0 = 0; s0 < N; s0 += pl->chunk, slot ^= 1) {
         const int64_t n = std::min<int64_t>(pl->chunk, N - s0);
         cudaStream_t st = pl->streams[slot];
-        NLML_CUDA(cudaMemcpy2DAsync(pl->x_dev[slot], sizeof(float) * F, X_host + s0 * ldx, sizeof(float) * ldx,
-                                    sizeof(float) * F, (size_t)n, cudaMemcpyHostToDevice, st));
+        if (ldx == F)   // contiguous rows: one linear DMA instead of a pitched copy
+            NLML_CUDA(cudaMemcpyAsync(pl->x_dev[slot], X_host + s0 * ldx, sizeof(float) * F * n, cudaMemcpyHostToDevice, st));
+        else
+            NLML_CUDA(cudaMemcpy2DAsync(pl->x_dev[slot], sizeof(float) * F, X_host + s0 * ldx, sizeof(float) * ldx,
+                                        sizeof(float) * F, (size_t)n, cudaMemcpyHostToDevice, st));
         if (int rc = forward_chunk(pl, pl->x_dev[slot], n, F, pl->y_dev[slot], nullptr, pl->ws[slot], st)) return rc;
         NLML_CUDA(cudaMemcpyAsync(YPR_out_host + s0 * 3, pl->y_dev[slot], sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
     }

@@ -955,11 +955,17 @@ extern "C" int nlml_tucker_fit_host_f32(nlml_tucker_plan* pl, const float* X_hos
         const int64_t n = std::min<int64_t>(pl->chunk, N - s0);
         cudaStream_t st = pl->streams[slot];
         // stream order makes the reuse of this slot's buffers safe (previous chunk on the same stream is done)
-        NLML_CUDA(cudaMemcpy2DAsync(pl->x_dev[slot], sizeof(float) * pl->F, X_host + s0 * ldx, sizeof(float) * ldx,
-                                    sizeof(float) * pl->F, (size_t)n, cudaMemcpyHostToDevice, st));
+        if (ldx == pl->F)   // contiguous rows: one linear DMA instead of a pitched copy
+            NLML_CUDA(cudaMemcpyAsync(pl->x_dev[slot], X_host + s0 * ldx, sizeof(float) * pl->F * n, cudaMemcpyHostToDevice, st));
+        else
+            NLML_CUDA(cudaMemcpy2DAsync(pl->x_dev[slot], sizeof(float) * pl->F, X_host + s0 * ldx, sizeof(float) * ldx,
+                                        sizeof(float) * pl->F, (size_t)n, cudaMemcpyHostToDevice, st));
         if (int rc = launch_fit(pl, pl->x_dev[slot], n, pl->F, iters, lr, clip, pl->p_dev[slot], np, 0, st)) return rc;
-        NLML_CUDA(cudaMemcpy2DAsync(P_out_host + s0 * ldp, sizeof(float) * ldp, pl->p_dev[slot], sizeof(float) * np,
-                                    sizeof(float) * np, (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (ldp == np)
+            NLML_CUDA(cudaMemcpyAsync(P_out_host + s0 * ldp, pl->p_dev[slot], sizeof(float) * np * n, cudaMemcpyDeviceToHost, st));
+        else
+            NLML_CUDA(cudaMemcpy2DAsync(P_out_host + s0 * ldp, sizeof(float) * ldp, pl->p_dev[slot], sizeof(float) * np,
+                                        sizeof(float) * np, (size_t)n, cudaMemcpyDeviceToHost, st));
     }
     NLML_CUDA(cudaStreamSynchronize(pl->streams[0]));
     NLML_CUDA(cudaStreamSynchronize(pl->streams[1]));
