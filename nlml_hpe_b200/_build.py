@@ -9,7 +9,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libnlml_hpe_b200.so")
 SOURCES = ["tucker_fit.cu", "mlp_forward.cu"]
-HEADERS = ["common.cuh", "tucker_math.h", "mlp_tc.cuh", os.path.join("..", "..", "include", "nlml_hpe_b200.h")]
+HEADERS = ["common.cuh", "tucker_math.h", "mlp_tc.cuh", "tucker_tc.cuh", os.path.join("..", "..", "include", "nlml_hpe_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

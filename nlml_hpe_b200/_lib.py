@@ -19,7 +19,7 @@ EXPORTS = [
     "nlml_tucker_fit_host_f32", "nlml_tucker_launch_count",
     "nlml_mlp_plan_create", "nlml_mlp_plan_destroy", "nlml_mlp_forward_f32",
     "nlml_mlp_forward_host_f32", "nlml_mlp_latent_f32", "nlml_mlp_launch_count", "nlml_mlp_set_path",
-    "nlml_measure_fp32_tflops", "nlml_measure_fp32_tflops_3reg",
+    "nlml_measure_fp32_tflops", "nlml_measure_fp32_tflops_3reg", "nlml_debug_tf32_gemm",
 ]
 
 _lib = None
@@ -60,6 +60,7 @@ def load():
     lib.nlml_mlp_set_path.argtypes = [vp, i32]
     lib.nlml_measure_fp32_tflops.argtypes = [i32, c_double_p]
     lib.nlml_measure_fp32_tflops_3reg.argtypes = [i32, c_double_p]
+    lib.nlml_debug_tf32_gemm.argtypes = [vp, vp, i32, i32, vp]
     _lib = lib
     return lib
 

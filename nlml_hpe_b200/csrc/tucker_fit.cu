@@ -118,6 +118,10 @@ struct QTmem {
     __device__ __forceinline__ void load(int /*n*/, float (&v)[32]) const { tmem_load32(taddr + R0, v); }
 };
 
+}  // namespace nlml
+#include "tucker_tc.cuh"
+namespace nlml {
+
 // ---------------------------------------------------------------------------------------------
 // thread-per-sample kernel
 // ---------------------------------------------------------------------------------------------
@@ -973,6 +977,19 @@ extern "C" int nlml_tucker_fit_host_f32(nlml_tucker_plan* pl, const float* X_hos
 }
 
 extern "C" int64_t nlml_tucker_launch_count(const nlml_tucker_plan* pl) { return pl ? pl->launches : 0; }
+
+// test hook: D[128][N] = A[128][K] * B[N][K]^T through the 3xTF32 tcgen05 building block of tucker_tc.cuh
+extern "C" int nlml_debug_tf32_gemm(const float* A_dev, const float* B_dev, int K, int N, float* D_dev) {
+    if (!A_dev || !B_dev || !D_dev) return set_error(NLML_E_INVALID, "null pointer argument");
+    if (K < 8 || K % 8 || K > 64 || N < 16 || N % 16 || N > 256) return set_error(NLML_E_INVALID, "K must be 8..64 (multiple of 8), N 16..256 (multiple of 16)");
+    ttc::TcCheckArgs a{A_dev, B_dev, D_dev, K, N};
+    const size_t smem = 2 * ttc::op_bytes(128, K) + 2 * ttc::op_bytes(N, K) + 64;
+    NLML_CUDA(cudaFuncSetAttribute(ttc::tc_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ttc::tc_check_kernel<<<1, 128, smem>>>(a);
+    NLML_CUDA(cudaGetLastError());
+    NLML_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
 
 static int measure_ffma(int device, int three_reg, double* tflops_out);
 extern "C" int nlml_measure_fp32_tflops(int device, double* tflops_out) { return measure_ffma(device, 0, tflops_out); }

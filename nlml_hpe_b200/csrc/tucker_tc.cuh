@@ -1,0 +1,159 @@
+// Tensor-core building blocks for the Tucker-fit iteration: small FP32-grade GEMMs
+//   D[128 x N] = A[128 x K] * B[N x K]^T      (K = 8 or 16, N <= 256)
+// on tcgen05 with kind::tf32 and the 3xTF32 operand split (hi = tf32(v), lo = v - hi; lo*hi + hi*lo + hi*hi), the
+// A operand written into shared memory by the threads themselves (one thread = one sample = one row = one TMEM lane).
+//
+// Operand layout: the canonical K-major NO-SWIZZLE form of the UMMA shared-memory descriptor
+// (cute::UMMA::make_umma_desc, LayoutType::INTERLEAVE: ((8,n),2):((1,SBO),LBO) in 16-byte units):
+//   element (row, k)  ->  (row / 8) * SBO + (k / 4) * LBO + (row % 8) * 16 + (k % 4) * 4   bytes
+// i.e. 8-row x 16-byte "core matrices" of 128 contiguous bytes; LBO = distance between the K chunks of one MMA,
+// SBO = distance between 8-row groups.  We store [row group][k chunk][8 rows][16 B]: LBO = 128, SBO = (K/4) * 128.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace nlml {
+namespace ttc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// byte offset of element (row, k) of an operand tile with K columns (K % 4 == 0)
+__host__ __device__ constexpr int op_offset(int row, int k, int K) {
+    return (row / 8) * ((K / 4) * 128) + (k / 4) * 128 + (row % 8) * 16 + (k % 4) * 4;
+}
+__host__ __device__ constexpr int op_bytes(int rows, int K) { return rows * K * 4; }
+
+// descriptor for the K-slice [k0, k0+8) of such a tile
+__device__ __forceinline__ uint64_t make_desc_noswz(uint32_t tile_addr, int K, int k0) {
+    const uint32_t addr = tile_addr + (uint32_t)((k0 / 4) * 128);
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);              // start address
+    d |= (uint64_t)(128 >> 4) << 16;                      // LBO: next K chunk (4 tf32) of the same rows
+    d |= (uint64_t)(((K / 4) * 128) >> 4) << 32;          // SBO: next 8-row group
+    d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
+    // layout type 0 = no swizzle
+    return d;
+}
+// kind::tf32 instruction descriptor: D = F32, A = B = TF32, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_to(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// generic-proxy shared-memory writes -> visible to the tensor core's async proxy
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// hi = value rounded to TF32 (10 mantissa bits, round to nearest even on the dropped 13 bits), lo = v - hi (exact in FP32)
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+    uint32_t u = __float_as_uint(v);
+    u += 0x00000fffu + ((u >> 13) & 1u);
+    u &= 0xffffe000u;
+    hi = __uint_as_float(u);
+    lo = v - hi;
+}
+
+// D += A * B^T over K (multiple of 8) with the 3-pass split; a/b tiles in the no-swizzle layout above.
+// Issued by ONE thread.  `first` = overwrite the accumulator with the first MMA.
+__device__ __forceinline__ void issue_gemm_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                                  int K, int N, bool first) {
+    const uint32_t idesc = make_idesc_tf32(128, N);
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        const uint64_t dah = make_desc_noswz(a_hi, K, k0), dal = make_desc_noswz(a_lo, K, k0);
+        const uint64_t dbh = make_desc_noswz(b_hi, K, k0), dbl = make_desc_noswz(b_lo, K, k0);
+        umma_tf32(tmem_d, dal, dbh, idesc, !(first && k0 == 0));   // small terms first
+        umma_tf32(tmem_d, dah, dbl, idesc, 1);
+        umma_tf32(tmem_d, dah, dbh, idesc, 1);
+    }
+}
+
+// ---- stand-alone check kernel: one CTA, D[128][N] = A[128][K] * B[N][K]^T --------------------------------
+struct TcCheckArgs {
+    const float* A;   // [128][K]
+    const float* B;   // [N][K]
+    float* D;         // [128][N]
+    int K, N;
+};
+
+__global__ void __launch_bounds__(128) tc_check_kernel(const __grid_constant__ TcCheckArgs a) {
+    extern __shared__ __align__(1024) uint8_t csm[];
+    const int K = a.K, N = a.N;
+    uint8_t* a_hi = csm;
+    uint8_t* a_lo = a_hi + op_bytes(128, K);
+    uint8_t* b_hi = a_lo + op_bytes(128, K);
+    uint8_t* b_lo = b_hi + op_bytes(N, K);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(b_lo + op_bytes(N, K));
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // operands: thread = row of A; B rows spread over the threads
+    for (int k = 0; k < K; ++k) {
+        float hi, lo;
+        split_tf32(a.A[tid * K + k], hi, lo);
+        *reinterpret_cast<float*>(a_hi + op_offset(tid, k, K)) = hi;
+        *reinterpret_cast<float*>(a_lo + op_offset(tid, k, K)) = lo;
+    }
+    for (int idx = tid; idx < N * K; idx += 128) {
+        const int n = idx / K, k = idx % K;
+        float hi, lo;
+        split_tf32(a.B[idx], hi, lo);
+        *reinterpret_cast<float*>(b_hi + op_offset(n, k, K)) = hi;
+        *reinterpret_cast<float*>(b_lo + op_offset(n, k, K)) = lo;
+    }
+    fence_async_smem();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *slot;
+    if (tid == 0) {
+        issue_gemm_3xtf32(tmem, smem_u32(a_hi), smem_u32(a_lo), smem_u32(b_hi), smem_u32(b_lo), K, N, true);
+        umma_commit_to(bar);
+    }
+    mbar_wait(bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32];
+        tmem_load32(taddr + c0, v);
+        for (int j = 0; j < 32 && c0 + j < N; ++j) a.D[tid * N + c0 + j] = v[j];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+}
+
+}  // namespace ttc
+}  // namespace nlml
