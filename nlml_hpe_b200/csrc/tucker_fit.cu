@@ -13,6 +13,7 @@
 //                          and the small-N / single-image case of TD_Inference.py, where latency of
 //                          the 3000-step chain matters more than throughput.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -37,6 +38,7 @@ struct TuckerArgs {
     int ri, ry, rp, rr;
     int nBCDp;
     int vec_ok;  // X rows and W2 rows are 16-byte aligned and F % 4 == 0
+    int dbg;     // measurement only (NLML_TUCKER_DBG): tensor-core kernel 1 = no MMAs / waits, 2 = no TMEM consumption
     float rows_y[4 * kMaxModeRank], rows_p[4 * kMaxModeRank], rows_r[4 * kMaxModeRank];
 };
 
@@ -94,6 +96,20 @@ __device__ __forceinline__ void tmem_load32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// same load without the wait: the caller overlaps it with arithmetic and calls tmem_load_wait() before touching r[]
+__device__ __forceinline__ void tmem_load32_async(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_load_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_store32(uint32_t taddr, const float* v) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -704,6 +720,337 @@ __global__ void __launch_bounds__(32 * WARPS) tucker_fit_wps_kernel(const __grid
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// tensor-core iteration kernel (ranks 5,3,3,3): SURVEY.md section 8f row 2.
+// One CTA = 128 samples = 128 TMEM lanes; a thread owns one sample.  The two contractions with the folded Gram
+// tensor leave the FP32 pipe:
+//   T[s, bcd]   = sum_A UU[s,A] * S[A,bcd]                          tcgen05 GEMM  128 x 224 x 16
+//   V[s, A,b,c] = sum_D RR[s,D] * S[A,b,c,D]                        tcgen05 GEMM  128 x 3*192 x 8   (3 chunks of 5 A's)
+//   GU[s,A]     = sum_b YY_b sum_c PP_c V[s,A,b,c]                  630 FMAs per sample, from TMEM
+// (3xTF32: FP32-grade products; at most 6 accumulation steps per TMEM accumulator, so the tensor core's truncating
+// accumulate does not matter here).  Per iteration a thread computes its cosine features and monomials, writes its
+// row of the two A operands (UU, RR) into shared memory in the UMMA no-swizzle layout, thread 0 issues the MMAs,
+// the linear term runs while they execute, and the results come back with tcgen05.ld.
+// FP32-pipe work per sample-iteration drops from ~7.7 k FMAs to ~1.9 k.
+// ---------------------------------------------------------------------------------------------
+struct TcFitCfg {
+    static constexpr int RI = 5, RY = 3, RP = 3, RR = 3, R = 135, RPAD = 136, NP = 8;
+    static constexpr int nA = 15, nB = 6, nC = 6, nD = 6, nBCD = 216;
+    static constexpr int THREADS = 128;
+    static constexpr int K1 = 16, N1 = 224;          // T GEMM: K = A (15 -> 16), N = bcd (216 -> 224)
+    static constexpr int KV = 8, NV = 192, VCH = 3;  // V GEMM: K = D (6 -> 8), N = 5 A's x 36 (b,c) = 180 -> 192, 3 chunks
+    static constexpr int A_PER_CH = 5;
+    static constexpr int B1_BYTES = ttc::op_bytes(N1, K1);    // 14336 per plane
+    static constexpr int BV_BYTES = ttc::op_bytes(NV, KV);    // 6144 per plane and chunk
+    static constexpr int A1_BYTES = ttc::op_bytes(128, K1);   // 8192 per plane
+    static constexpr int AV_BYTES = ttc::op_bytes(128, KV);   // 4096 per plane
+    static constexpr int OFF_B1 = 0;                                   // hi, lo
+    static constexpr int OFF_BV = OFF_B1 + 2 * B1_BYTES;               // [chunk][hi, lo]
+    static constexpr int OFF_A1 = OFF_BV + 2 * VCH * BV_BYTES;         // hi, lo
+    static constexpr int OFF_AV = OFF_A1 + 2 * A1_BYTES;               // hi, lo
+    static constexpr int OFF_Q = OFF_AV + 2 * AV_BYTES;                // q [R][128] floats; phase-A tiles alias it
+    static constexpr int OFF_BAR = OFF_Q + R * THREADS * 4;
+    static constexpr int OFF_GX = OFF_BAR + 64;                        // gradient exchange [8][128] floats
+    static constexpr size_t SMEM_BYTES = OFF_GX + 8 * THREADS * 4;
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int COL_T = 0, COL_V = 224;      // round 1: T | V chunk 0 ; round 2: V chunk 1 (at COL_T) | V chunk 2
+    static constexpr int FC = 16, XSTR = THREADS + 2; // phase-A tiles, as in the thread-per-sample kernel
+};
+
+// V chunk (5 A's x 36 (b,c), padded to 192 columns) -> GU of those A's; double-buffered TMEM loads
+template <int A0>
+__device__ __forceinline__ void tc_reduce_v(uint32_t taddr, const float (&PP)[6], const float (&YY)[6], float (&GU)[15]) {
+    using C = TcFitCfg;
+    float v2[C::A_PER_CH * 6];   // sum_c V[a,b,c] * PP_c
+#pragma unroll
+    for (int i = 0; i < C::A_PER_CH * 6; ++i) v2[i] = 0.f;
+    uint32_t buf[2][32];
+    tmem_load32_async(taddr, buf[0]);
+#pragma unroll
+    for (int ci = 0; ci < C::NV / 32; ++ci) {
+        tmem_load_wait();
+        if (ci + 1 < C::NV / 32) tmem_load32_async(taddr + 32 * (ci + 1), buf[(ci + 1) & 1]);
+#pragma unroll
+        for (int x = 0; x < 32; ++x) {
+            const int n = 32 * ci + x;
+            if (n < C::A_PER_CH * 36) v2[n / 6] = fmaf(__uint_as_float(buf[ci & 1][x]), PP[n % 6], v2[n / 6]);
+        }
+    }
+#pragma unroll
+    for (int al = 0; al < C::A_PER_CH; ++al) {
+        float acc = 0.f;
+#pragma unroll
+        for (int b = 0; b < 6; ++b) acc = fmaf(v2[al * 6 + b], YY[b], acc);
+        GU[A0 + al] = acc;
+    }
+}
+
+// Two threads per sample (256 threads = 8 warps per CTA; warps w and w+4 own the same TMEM lanes):
+//   role 0 ("angle thread", warps 0-3): writes the UU operand, consumes T -> d/d(yaw,pitch,roll)
+//   role 1 ("identity thread", warps 4-7): writes the RR operand, consumes V -> d/du
+// Both keep a bitwise-identical copy of p; the two gradient parts are exchanged through shared memory once per step.
+__global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_constant__ TuckerArgs a) {
+    using C = TcFitCfg;
+    extern __shared__ __align__(1024) uint8_t tsm[];
+    uint8_t* b1_hi = tsm + C::OFF_B1;
+    uint8_t* b1_lo = b1_hi + C::B1_BYTES;
+    uint8_t* bv = tsm + C::OFF_BV;
+    uint8_t* a1_hi = tsm + C::OFF_A1;
+    uint8_t* a1_lo = a1_hi + C::A1_BYTES;
+    uint8_t* av_hi = tsm + C::OFF_AV;
+    uint8_t* av_lo = av_hi + C::AV_BYTES;
+    float* q_s = reinterpret_cast<float*>(tsm + C::OFF_Q);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tsm + C::OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    float* gx = reinterpret_cast<float*>(tsm + C::OFF_GX);   // [8][128] gradient exchange between the two roles
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & 127, role = tid >> 7;
+    const long long s0 = (long long)blockIdx.x * C::THREADS;
+    const bool vec_ok = a.vec_ok != 0;
+    const int F = a.F;
+
+    if (tid == 0) {
+        ttc::mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc_cols(tmem_slot, C::TMEM_COLS);
+
+    // ---- constant B operands: the folded Gram tensor in both GEMM views, split hi/lo ----
+    for (int idx = tid; idx < C::N1 * C::K1; idx += 256) {
+        const int n = idx / C::K1, k = idx % C::K1;
+        const float v = (n < C::nBCD && k < C::nA) ? __ldg(a.S + n * 16 + k) : 0.f;
+        float hi, lo;
+        ttc::split_tf32(v, hi, lo);
+        *reinterpret_cast<float*>(b1_hi + ttc::op_offset(n, k, C::K1)) = hi;
+        *reinterpret_cast<float*>(b1_lo + ttc::op_offset(n, k, C::K1)) = lo;
+    }
+    for (int idx = tid; idx < C::VCH * C::NV * C::KV; idx += 256) {
+        const int ch = idx / (C::NV * C::KV), rem = idx % (C::NV * C::KV), n = rem / C::KV, d = rem % C::KV;
+        float v = 0.f;
+        if (n < C::A_PER_CH * C::nB * C::nC && d < C::nD) {
+            const int aa = ch * C::A_PER_CH + n / (C::nB * C::nC), b = (n / C::nC) % C::nB, c = n % C::nC;
+            v = __ldg(a.S + ((b * C::nC + c) * C::nD + d) * 16 + aa);
+        }
+        float hi, lo;
+        ttc::split_tf32(v, hi, lo);
+        *reinterpret_cast<float*>(bv + (2 * ch) * C::BV_BYTES + ttc::op_offset(n, d, C::KV)) = hi;
+        *reinterpret_cast<float*>(bv + (2 * ch + 1) * C::BV_BYTES + ttc::op_offset(n, d, C::KV)) = lo;
+    }
+
+    // ---- phase A: q[r] = sum_f W2[r][f] * x[f]; the two threads of a sample take half of the rows r each ----
+    {
+        constexpr int RH = C::RPAD / 2;   // 68 rows per role
+        float* xs = q_s;
+        float* ws = q_s + C::FC * C::XSTR;
+        float acc[RH];
+#pragma unroll
+        for (int r = 0; r < RH; ++r) acc[r] = 0.f;
+        for (int f0 = 0; f0 < F; f0 += C::FC) {
+            for (int idx = tid; idx < C::THREADS * (C::FC / 4); idx += 256) {
+                const int s = idx / (C::FC / 4), c4 = idx % (C::FC / 4);
+                const long long grow = s0 + s;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (grow < a.N) v = load_row4(a.X + grow * a.ldx, f0 + 4 * c4, F, vec_ok);
+                xs[(4 * c4 + 0) * C::XSTR + s] = v.x;
+                xs[(4 * c4 + 1) * C::XSTR + s] = v.y;
+                xs[(4 * c4 + 2) * C::XSTR + s] = v.z;
+                xs[(4 * c4 + 3) * C::XSTR + s] = v.w;
+            }
+            for (int idx = tid; idx < C::RPAD * (C::FC / 4); idx += 256) {
+                const int r = idx / (C::FC / 4), c4 = idx % (C::FC / 4);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < C::R) v = load_row4(a.W2 + (long long)r * F, f0 + 4 * c4, F, vec_ok);
+                ws[(4 * c4 + 0) * C::RPAD + r] = v.x;
+                ws[(4 * c4 + 1) * C::RPAD + r] = v.y;
+                ws[(4 * c4 + 2) * C::RPAD + r] = v.z;
+                ws[(4 * c4 + 3) * C::RPAD + r] = v.w;
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (int f = 0; f < C::FC; ++f) {
+                const float xv = xs[f * C::XSTR + row];
+#pragma unroll
+                for (int r4 = 0; r4 < RH / 4; ++r4) {
+                    const float4 w = *reinterpret_cast<const float4*>(&ws[f * C::RPAD + role * RH + 4 * r4]);
+                    acc[4 * r4 + 0] = fmaf(xv, w.x, acc[4 * r4 + 0]);
+                    acc[4 * r4 + 1] = fmaf(xv, w.y, acc[4 * r4 + 1]);
+                    acc[4 * r4 + 2] = fmaf(xv, w.z, acc[4 * r4 + 2]);
+                    acc[4 * r4 + 3] = fmaf(xv, w.w, acc[4 * r4 + 3]);
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int r = 0; r < RH; ++r)
+            if (role * RH + r < C::R) q_s[(role * RH + r) * C::THREADS + row] = acc[r];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const QStrided qa{q_s + row, C::THREADS, 0};
+
+    // ---- phase B ----
+    float p[C::NP];
+#pragma unroll
+    for (int i = 0; i < C::NP; ++i) p[i] = 0.f;  // zero init, TD_Tester.py:130
+    const float lr = a.lr, clip = a.clip;
+    uint32_t phase = 0;
+#pragma unroll 1
+    for (int it = 0; it < a.T; ++it) {
+        float cy[3], dcy[3], cp[3], dcp[3], cr[3], dcr[3], u[5];
+        cos_features<3>(p[0], a.rows_y, cy, dcy);
+        cos_features<3>(p[1], a.rows_p, cp, dcp);
+        cos_features<3>(p[2], a.rows_r, cr, dcr);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) u[i] = p[3 + i];
+        float YY[6], PP[6], RRv[8];
+        sym_products<3>(cy, YY);
+        sym_products<3>(cp, PP);
+        sym_products<3>(cr, RRv);
+        RRv[6] = RRv[7] = 0.f;
+
+        // this sample's rows of the two A operands: UU by the angle thread, RR by the identity thread
+        if (role == 0) {
+            float UU[16];
+            sym_products<5>(u, UU);
+            UU[15] = 0.f;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+                float h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ttc::split_tf32(UU[4 * k4 + e], h[e], l[e]);
+                *reinterpret_cast<float4*>(a1_hi + ttc::op_offset(row, 4 * k4, C::K1)) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(a1_lo + ttc::op_offset(row, 4 * k4, C::K1)) = make_float4(l[0], l[1], l[2], l[3]);
+            }
+        } else {
+#pragma unroll
+            for (int k4 = 0; k4 < 2; ++k4) {
+                float h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ttc::split_tf32(RRv[4 * k4 + e], h[e], l[e]);
+                *reinterpret_cast<float4*>(av_hi + ttc::op_offset(row, 4 * k4, C::KV)) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(av_lo + ttc::op_offset(row, 4 * k4, C::KV)) = make_float4(l[0], l[1], l[2], l[3]);
+            }
+        }
+        ttc::fence_async_smem();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0 && a.dbg != 1) {   // round 1: T and V chunk 0
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            ttc::issue_gemm_3xtf32(tmem + C::COL_T, ttc::smem_u32(a1_hi), ttc::smem_u32(a1_lo), ttc::smem_u32(b1_hi),
+                                   ttc::smem_u32(b1_lo), C::K1, C::N1, true);
+            ttc::issue_gemm_3xtf32(tmem + C::COL_V, ttc::smem_u32(av_hi), ttc::smem_u32(av_lo), ttc::smem_u32(bv),
+                                   ttc::smem_u32(bv + C::BV_BYTES), C::KV, C::NV, true);
+            ttc::umma_commit_to(bar);
+        }
+        // the linear term does not depend on the MMAs: it runs while they execute.  (Both roles evaluate it: the
+        // angle thread needs ey/ep/er, the identity thread lin_u; splitting it would save ~200 FMAs per thread.)
+        float lin_u[5], ey[3], ep[3], er[3];
+        linear_term<5, 3, 3, 3>(qa, 0, cy, cp, cr, u, lin_u, ey, ep, er);
+
+        if (a.dbg != 1) ttc::mbar_wait(bar, phase);
+        phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+        float GU[15];
+#pragma unroll
+        for (int i = 0; i < 15; ++i) GU[i] = 0.f;
+        if (a.dbg == 2) {
+            if (role == 0) { gx[row] = cy[0]; gx[128 + row] = cp[0]; gx[256 + row] = cr[0]; }
+        } else if (role == 0) {
+            // T[bcd] -> GR, GY, GP -> d/d(yaw, pitch, roll)
+            float GY[6], GP[6], GR[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) GY[i] = GP[i] = GR[i] = 0.f;
+            float tr[36];   // sum_d T[b,c,d] * RR_d
+#pragma unroll
+            for (int i = 0; i < 36; ++i) tr[i] = 0.f;
+            uint32_t buf[2][32];
+            tmem_load32_async(lane_addr + C::COL_T, buf[0]);
+#pragma unroll
+            for (int ci = 0; ci < C::N1 / 32; ++ci) {
+                tmem_load_wait();
+                if (ci + 1 < C::N1 / 32) tmem_load32_async(lane_addr + C::COL_T + 32 * (ci + 1), buf[(ci + 1) & 1]);
+#pragma unroll
+                for (int x = 0; x < 32; ++x) {
+                    const int bcd = 32 * ci + x;
+                    if (bcd < C::nBCD) {
+                        const int b = bcd / 36, c = (bcd / 6) % 6, d = bcd % 6;
+                        const float t = __uint_as_float(buf[ci & 1][x]);
+                        GR[d] = fmaf(t, YY[b] * PP[c], GR[d]);
+                        tr[b * 6 + c] = fmaf(t, RRv[d], tr[b * 6 + c]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < 6; ++b)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    GY[b] = fmaf(tr[b * 6 + c], PP[c], GY[b]);
+                    GP[c] = fmaf(tr[b * 6 + c], YY[b], GP[c]);
+                }
+            float dy[3], dp[3], dr[3];
+            sym_backprop<3>(GY, cy, dy);
+            sym_backprop<3>(GP, cp, dp);
+            sym_backprop<3>(GR, cr, dr);
+            float gy = 0.f, gp = 0.f, gr = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                gy = fmaf(dy[j] - ey[j], dcy[j], gy);
+                gp = fmaf(dp[j] - ep[j], dcp[j], gp);
+                gr = fmaf(dr[j] - er[j], dcr[j], gr);
+            }
+            gx[0 * 128 + row] = gy;
+            gx[1 * 128 + row] = gp;
+            gx[2 * 128 + row] = gr;
+        } else {
+            tc_reduce_v<0>(lane_addr + C::COL_V, PP, YY, GU);
+        }
+
+
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();   // T and V chunk 0 drained
+        if (tid == 128 && a.dbg != 1) {  // round 2: V chunks 1 and 2 (consumed by the identity threads only)
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            ttc::issue_gemm_3xtf32(tmem + C::COL_T, ttc::smem_u32(av_hi), ttc::smem_u32(av_lo), ttc::smem_u32(bv + 2 * C::BV_BYTES),
+                                   ttc::smem_u32(bv + 3 * C::BV_BYTES), C::KV, C::NV, true);
+            ttc::issue_gemm_3xtf32(tmem + C::COL_V, ttc::smem_u32(av_hi), ttc::smem_u32(av_lo), ttc::smem_u32(bv + 4 * C::BV_BYTES),
+                                   ttc::smem_u32(bv + 5 * C::BV_BYTES), C::KV, C::NV, true);
+            ttc::umma_commit_to(bar);
+        }
+        if (role == 1) {
+            if (a.dbg != 1) ttc::mbar_wait(bar, phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (a.dbg != 2) {
+                tc_reduce_v<5>(lane_addr + C::COL_T, PP, YY, GU);
+                tc_reduce_v<10>(lane_addr + C::COL_V, PP, YY, GU);
+            }
+            float du[5];
+            sym_backprop<5>(GU, u, du);
+#pragma unroll
+            for (int i = 0; i < 5; ++i) gx[(3 + i) * 128 + row] = du[i] - lin_u[i];
+        }
+        phase ^= 1;   // both roles track the barrier phase; the angle threads simply never wait on round 2
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();   // gradient halves exchanged; round-2 results drained
+        float g[C::NP];
+#pragma unroll
+        for (int i = 0; i < C::NP; ++i) g[i] = gx[i * 128 + row];
+        clip_and_step<C::NP>(p, g, lr, clip);
+    }
+    if (role == 0 && s0 + row < a.N) {
+        float* out = a.P + (s0 + row) * a.ldp;
+#pragma unroll
+        for (int i = 0; i < C::NP; ++i) out[i] = p[i];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_free_cols(tmem, C::TMEM_COLS);
+}
+
 // register-only FFMA loop: measures the sustained FP32 FMA rate used as a roofline denominator
 __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
@@ -799,13 +1146,17 @@ int launch_fit(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int
     a.lr = lr;
     a.clip = clip;
     a.vec_ok = (pl->F % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+    if (const char* e = std::getenv("NLML_TUCKER_DBG")) a.dbg = std::atoi(e);
     // crossover: below ~one thread-per-sample wave the 3000-step chain is latency bound and the
     // CTA-per-sample kernel finishes sooner
+    const bool use_tc = pl->fast && hint == 5;
     const bool use_tps = pl->fast && (hint == 1 || hint == 4 || (hint == 0 && N >= kWpsCrossover));
     const bool use_wps = pl->fast && (hint == 3 || (hint == 0 && N < kWpsCrossover));
-    if ((hint == 1 || hint == 3 || hint == 4) && !pl->fast)
+    if ((hint == 1 || hint == 3 || hint == 4 || hint == 5) && !pl->fast)
         return set_error(NLML_E_UNSUPPORTED, "thread/warp-per-sample kernels are built for ranks (5,3,3,3) only");
-    if (use_wps) {
+    if (use_tc) {
+        tucker_fit_tc_kernel<<<(unsigned)ceil_div(N, TcFitCfg::THREADS), 2 * TcFitCfg::THREADS, TcFitCfg::SMEM_BYTES, st>>>(a);
+    } else if (use_wps) {
         auto kern = tucker_fit_wps_kernel<5, 3, 3, 3, kWpsWarps>;
         const unsigned grid = (unsigned)ceil_div(N, kWpsWarps);
         kern<<<grid, 32 * kWpsWarps, wps_smem_bytes(pl->F), st>>>(a);
@@ -893,6 +1244,7 @@ extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, i
         NLML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpsDefault::SMEM_BYTES));
         NLML_CUDA(cudaFuncSetAttribute(tucker_fit_tps_kernel<5, 3, 3, 3, kTpsBigThreads, 1, 1, true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpsBig::SMEM_BYTES));
+        NLML_CUDA(cudaFuncSetAttribute(tucker_fit_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcFitCfg::SMEM_BYTES));
         if (wps_smem_bytes(F) > 200 * 1024) pl->fast = false;
         else
             NLML_CUDA(cudaFuncSetAttribute(tucker_fit_wps_kernel<5, 3, 3, 3, kWpsWarps>,
@@ -934,7 +1286,7 @@ extern "C" int nlml_tucker_fit_f32(nlml_tucker_plan* pl, const float* X_dev, int
     if (N < 0 || ldx < pl->F || ldp < 3 + pl->ri || iters < 0)
         return set_error(NLML_E_INVALID, "bad sizes: N=%lld ldx=%lld (F=%d) ldp=%lld (need >= %d) iters=%d",
                          (long long)N, (long long)ldx, pl->F, (long long)ldp, 3 + pl->ri, iters);
-    if (kernel_hint < 0 || kernel_hint > 4) return set_error(NLML_E_INVALID, "kernel_hint must be 0..4");
+    if (kernel_hint < 0 || kernel_hint > 5) return set_error(NLML_E_INVALID, "kernel_hint must be 0..5");
     DeviceGuard guard(pl->device);
     return launch_fit(pl, X_dev, N, ldx, iters, lr, clip, P_out_dev, ldp, kernel_hint, (cudaStream_t)stream);
 }

@@ -139,6 +139,74 @@ struct QLoadChunk {
     }
 };
 
+// Linear term -q.z : lin_u[i] = sum_jkl q[ijkl] t_jkl with t = cy (x) cp (x) cr, and the contractions of
+// e[jkl] = sum_i u_i q[ijkl] with the other two angle factors (ey, ep, er).  q is consumed in its storage order
+// (i slowest), 32 consecutive elements at a time.
+template <int RI, int RY, int RP, int RR, class QA>
+NLML_HD void linear_term(const QA& qa, int n, const float* cy, const float* cp, const float* cr, const float* u,
+                         float (&lin_u)[RI], float (&ey)[RY], float (&ep)[RP], float (&er)[RR]) {
+    constexpr int JKL = RY * RP * RR;
+    float tq[JKL], e[JKL];
+#pragma unroll
+    for (int j = 0; j < RY; ++j)
+#pragma unroll
+        for (int k = 0; k < RP; ++k)
+#pragma unroll
+            for (int l = 0; l < RR; ++l) {
+                tq[(j * RP + k) * RR + l] = cy[j] * cp[k] * cr[l];
+                e[(j * RP + k) * RR + l] = 0.f;
+            }
+#pragma unroll
+    for (int i = 0; i < RI; ++i) lin_u[i] = 0.f;
+    QLoadChunk<RI, JKL, QA, 0>::run(qa, n, tq, u, lin_u, e);
+#pragma unroll
+    for (int j = 0; j < RY; ++j) ey[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < RP; ++k) ep[k] = 0.f;
+#pragma unroll
+    for (int l = 0; l < RR; ++l) er[l] = 0.f;
+#pragma unroll
+    for (int j = 0; j < RY; ++j)
+#pragma unroll
+        for (int k = 0; k < RP; ++k) {
+            const float yk = cy[j] * cp[k];
+            float e_jk = 0.f;  // sum_l e[jkl] cr_l
+#pragma unroll
+            for (int l = 0; l < RR; ++l) {
+                const float ev = e[(j * RP + k) * RR + l];
+                er[l] = fmaf(ev, yk, er[l]);
+                e_jk = fmaf(ev, cr[l], e_jk);
+            }
+            ey[j] = fmaf(e_jk, cp[k], ey[j]);
+            ep[k] = fmaf(e_jk, cy[j], ep[k]);
+        }
+}
+
+// Chain rule from the derivatives w.r.t. the monomials (GU, GY, GP, GR) and the linear term to d/dp.
+template <int RI, int RY, int RP, int RR>
+NLML_HD void assemble_gradient(const float* GU, const float* GY, const float* GP, const float* GR, const float* u,
+                               const float* cy, const float* cp, const float* cr, const float* dcy, const float* dcp,
+                               const float* dcr, const float* lin_u, const float* ey, const float* ep, const float* er,
+                               float* g) {
+    float du[RI], dy[RY], dp[RP], dr[RR];
+    sym_backprop<RI>(GU, u, du);
+    sym_backprop<RY>(GY, cy, dy);
+    sym_backprop<RP>(GP, cp, dp);
+    sym_backprop<RR>(GR, cr, dr);
+    float gy = 0.f, gp = 0.f, gr = 0.f;
+#pragma unroll
+    for (int j = 0; j < RY; ++j) gy = fmaf(dy[j] - ey[j], dcy[j], gy);
+#pragma unroll
+    for (int k = 0; k < RP; ++k) gp = fmaf(dp[k] - ep[k], dcp[k], gp);
+#pragma unroll
+    for (int l = 0; l < RR; ++l) gr = fmaf(dr[l] - er[l], dcr[l], gr);
+    g[0] = gy;
+    g[1] = gp;
+    g[2] = gr;
+#pragma unroll
+    for (int i = 0; i < RI; ++i) g[3 + i] = du[i] - lin_u[i];
+}
+
 // One full gradient evaluation for NS samples held by one thread (fixed small ranks).
 //   S : folded Gram tensor laid out [nB*nC*nD][NAP] (NAP = nA padded to a multiple of 4), read-only, identical
 //       for all samples (shared-memory broadcast on the GPU).  Every element loaded from S feeds 2*NS FMAs,
@@ -235,62 +303,10 @@ NLML_HD void tucker_gradient(const float (&p)[NS][3 + RI], const float* __restri
                 GY[n][b] = fmaf(tr, PP[n][c], GY[n][b]);
                 GP[n][c] = fmaf(tr, YY[n][b], GP[n][c]);
             }
-        float du[RI], dy[RY], dp[RP], dr[RR];
-        sym_backprop<RI>(GU[n], u[n], du);
-        sym_backprop<RY>(GY[n], cy[n], dy);
-        sym_backprop<RP>(GP[n], cp[n], dp);
-        sym_backprop<RR>(GR[n], cr[n], dr);
-
-        // linear term -q.z : d/du_i = -sum_jkl q[ijkl] t_jkl with t = cy (x) cp (x) cr ; e[jkl] = sum_i u_i q[ijkl].
-        // q is consumed in its storage order (i slowest), 32 consecutive elements at a time.
-        constexpr int JKL = RY * RP * RR, R = RI * JKL;
-        float tq[JKL], e[JKL], lin_u[RI];
-#pragma unroll
-        for (int j = 0; j < RY; ++j)
-#pragma unroll
-            for (int k = 0; k < RP; ++k)
-#pragma unroll
-                for (int l = 0; l < RR; ++l) {
-                    tq[(j * RP + k) * RR + l] = cy[n][j] * cp[n][k] * cr[n][l];
-                    e[(j * RP + k) * RR + l] = 0.f;
-                }
-#pragma unroll
-        for (int i = 0; i < RI; ++i) lin_u[i] = 0.f;
-        float ey[RY], ep[RP], er[RR];
-        QLoadChunk<RI, JKL, QA, 0>::run(qa, n, tq, u[n], lin_u, e);
-#pragma unroll
-        for (int j = 0; j < RY; ++j) ey[j] = 0.f;
-#pragma unroll
-        for (int k = 0; k < RP; ++k) ep[k] = 0.f;
-#pragma unroll
-        for (int l = 0; l < RR; ++l) er[l] = 0.f;
-#pragma unroll
-        for (int j = 0; j < RY; ++j)
-#pragma unroll
-            for (int k = 0; k < RP; ++k) {
-                const float yk = cy[n][j] * cp[n][k];
-                float e_jk = 0.f;  // sum_l e[jkl] cr_l
-#pragma unroll
-                for (int l = 0; l < RR; ++l) {
-                    const float ev = e[(j * RP + k) * RR + l];
-                    er[l] = fmaf(ev, yk, er[l]);
-                    e_jk = fmaf(ev, cr[n][l], e_jk);
-                }
-                ey[j] = fmaf(e_jk, cp[n][k], ey[j]);
-                ep[k] = fmaf(e_jk, cy[n][j], ep[k]);
-            }
-        float gy = 0.f, gp = 0.f, gr = 0.f;
-#pragma unroll
-        for (int j = 0; j < RY; ++j) gy = fmaf(dy[j] - ey[j], dcy[n][j], gy);
-#pragma unroll
-        for (int k = 0; k < RP; ++k) gp = fmaf(dp[k] - ep[k], dcp[n][k], gp);
-#pragma unroll
-        for (int l = 0; l < RR; ++l) gr = fmaf(dr[l] - er[l], dcr[n][l], gr);
-        g[n][0] = gy;
-        g[n][1] = gp;
-        g[n][2] = gr;
-#pragma unroll
-        for (int i = 0; i < RI; ++i) g[n][3 + i] = du[i] - lin_u[i];
+        float lin_u[RI], ey[RY], ep[RP], er[RR];
+        linear_term<RI, RY, RP, RR>(qa, n, cy[n], cp[n], cr[n], u[n], lin_u, ey, ep, er);
+        assemble_gradient<RI, RY, RP, RR>(GU[n], GY[n], GP[n], GR[n], u[n], cy[n], cp[n], cr[n], dcy[n], dcp[n], dcr[n],
+                                          lin_u, ey, ep, er, g[n]);
     }
 }
 
