@@ -300,7 +300,7 @@ def run_b200(args):
         "gpu_launches": int(t_launches),
         "roofline": {"bound": "fp32_fma", "achieved": per_gpu_t * TUCKER_FLOP_PER_POSE / 1e12, "peak": fp32_peak,
                      "unit": "TFLOP/s", "frac": per_gpu_t * TUCKER_FLOP_PER_POSE / 1e12 / fp32_peak, "traffic": None,
-                     "kernel": "tucker_fit_tps_kernel<5,3,3,3,128,1,2,false>",
+                     "kernel": "tucker_fit_tc_kernel (3xTF32 tcgen05 for the two folded-Gram contractions + FP32 SIMT for the rest)",
                      "peak_3reg": fp32_peak_3reg, "frac_3reg": per_gpu_t * TUCKER_FLOP_PER_POSE / 1e12 / fp32_peak_3reg,
                      "note": "3000 on-chip iterations per 5.6 KB streamed: neither HBM nor tensor pipe binds; peak = FFMA rate "
                              "measured live by nlml_measure_fp32_tflops (immediate-operand FFMA); peak_3reg = the same loop "

@@ -56,7 +56,8 @@ void nlml_tucker_plan_destroy(nlml_tucker_plan* plan);
  * Asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
  * kernel_hint: 0 = choose by N and ranks, 1 = thread-per-sample kernel (throughput, ranks 5,3,3,3),
  * 2 = CTA-per-sample kernel (run-time ranks), 3 = warp-per-sample kernel (latency, ranks 5,3,3,3),
- * 4 = thread-per-sample kernel with q resident in tensor memory (12 warps per SM; measured equal to 1). */
+ * 4 = thread-per-sample kernel with q resident in tensor memory (12 warps per SM; measured equal to 1),
+ * 5 = tensor-core iteration kernel (3xTF32 tcgen05 GEMMs for the folded-Gram contractions; the large-batch default). */
 int nlml_tucker_fit_f32(nlml_tucker_plan* plan, const float* X_dev, int64_t N, int64_t ldx,
                         int iters, float lr, float clip, float* P_out_dev, int64_t ldp,
                         int kernel_hint, void* stream);

@@ -725,10 +725,11 @@ __global__ void __launch_bounds__(32 * WARPS) tucker_fit_wps_kernel(const __grid
 // One CTA = 128 samples = 128 TMEM lanes; a thread owns one sample.  The two contractions with the folded Gram
 // tensor leave the FP32 pipe:
 //   T[s, bcd]   = sum_A UU[s,A] * S[A,bcd]                          tcgen05 GEMM  128 x 224 x 16
-//   V[s, A,b,c] = sum_D RR[s,D] * S[A,b,c,D]                        tcgen05 GEMM  128 x 3*192 x 8   (3 chunks of 5 A's)
-//   GU[s,A]     = sum_b YY_b sum_c PP_c V[s,A,b,c]                  630 FMAs per sample, from TMEM
-// (3xTF32: FP32-grade products; at most 6 accumulation steps per TMEM accumulator, so the tensor core's truncating
-// accumulate does not matter here).  Per iteration a thread computes its cosine features and monomials, writes its
+//   V[s, A,b]   = sum_{c,D} (PP_c RR_D)[s] * S[A,b,c,D]             tcgen05 GEMM  128 x 96 x 40
+//   GU[s,A]     = sum_b YY_b V[s,A,b]                               90 FMAs per sample, from TMEM
+// (3xTF32: FP32-grade products; 6 resp. 15 accumulation steps per TMEM accumulator, so the tensor core's truncating
+// accumulate stays below the split's own error).  Reading results back from TMEM is what this kernel is bound by
+// (a first version that produced V[s,A,b,c] = 540 columns per sample spent 42 % of its time in tcgen05.ld).  Per iteration a thread computes its cosine features and monomials, writes its
 // row of the two A operands (UU, RR) into shared memory in the UMMA no-swizzle layout, thread 0 issues the MMAs,
 // the linear term runs while they execute, and the results come back with tcgen05.ld.
 // FP32-pipe work per sample-iteration drops from ~7.7 k FMAs to ~1.9 k.
@@ -736,65 +737,79 @@ __global__ void __launch_bounds__(32 * WARPS) tucker_fit_wps_kernel(const __grid
 struct TcFitCfg {
     static constexpr int RI = 5, RY = 3, RP = 3, RR = 3, R = 135, RPAD = 136, NP = 8;
     static constexpr int nA = 15, nB = 6, nC = 6, nD = 6, nBCD = 216;
-    static constexpr int THREADS = 128;
-    static constexpr int K1 = 16, N1 = 224;          // T GEMM: K = A (15 -> 16), N = bcd (216 -> 224)
-    static constexpr int KV = 8, NV = 192, VCH = 3;  // V GEMM: K = D (6 -> 8), N = 5 A's x 36 (b,c) = 180 -> 192, 3 chunks
-    static constexpr int A_PER_CH = 5;
+    static constexpr int THREADS = 128;               // samples per CTA (= TMEM lanes); the CTA has 2 threads per sample
+    static constexpr int K1 = 16, N1 = 224;           // T GEMM: K = A (15 -> 16), N = bcd (216 -> 224)
+    static constexpr int KV = 40, NV = 96;            // V GEMM: K = (c,D) (36 -> 40), N = (A,b) (90 -> 96)
     static constexpr int B1_BYTES = ttc::op_bytes(N1, K1);    // 14336 per plane
-    static constexpr int BV_BYTES = ttc::op_bytes(NV, KV);    // 6144 per plane and chunk
+    static constexpr int BV_BYTES = ttc::op_bytes(NV, KV);    // 15360 per plane
     static constexpr int A1_BYTES = ttc::op_bytes(128, K1);   // 8192 per plane
-    static constexpr int AV_BYTES = ttc::op_bytes(128, KV);   // 4096 per plane
+    static constexpr int AV_BYTES = ttc::op_bytes(128, KV);   // 20480 per plane
     static constexpr int OFF_B1 = 0;                                   // hi, lo
-    static constexpr int OFF_BV = OFF_B1 + 2 * B1_BYTES;               // [chunk][hi, lo]
-    static constexpr int OFF_A1 = OFF_BV + 2 * VCH * BV_BYTES;         // hi, lo
+    static constexpr int OFF_BV = OFF_B1 + 2 * B1_BYTES;               // hi, lo
+    static constexpr int OFF_A1 = OFF_BV + 2 * BV_BYTES;               // hi, lo
     static constexpr int OFF_AV = OFF_A1 + 2 * A1_BYTES;               // hi, lo
     static constexpr int OFF_Q = OFF_AV + 2 * AV_BYTES;                // q [R][128] floats; phase-A tiles alias it
     static constexpr int OFF_BAR = OFF_Q + R * THREADS * 4;
-    static constexpr int OFF_GX = OFF_BAR + 64;                        // gradient exchange [8][128] floats
-    static constexpr size_t SMEM_BYTES = OFF_GX + 8 * THREADS * 4;
+    static constexpr int OFF_GX = OFF_BAR + 64;                        // exchange between the two roles [NGX][128] floats
+    static constexpr int NGX = 8 + 15;                                 // 8 gradient parts + role 1's partial GR, GP, GY
+    static constexpr size_t SMEM_BYTES = OFF_GX + NGX * THREADS * 4;
     static constexpr int TMEM_COLS = 512;
-    static constexpr int COL_T = 0, COL_V = 224;      // round 1: T | V chunk 0 ; round 2: V chunk 1 (at COL_T) | V chunk 2
+    static constexpr int COL_T = 0, COL_V = 224;
     static constexpr int FC = 16, XSTR = THREADS + 2; // phase-A tiles, as in the thread-per-sample kernel
 };
 
-// V chunk (5 A's x 36 (b,c), padded to 192 columns) -> GU of those A's; double-buffered TMEM loads
-template <int A0>
-__device__ __forceinline__ void tc_reduce_v(uint32_t taddr, const float (&PP)[6], const float (&YY)[6], float (&GU)[15]) {
-    using C = TcFitCfg;
-    float v2[C::A_PER_CH * 6];   // sum_c V[a,b,c] * PP_c
+// Half of T (3 of the 6 b's = 108 columns) -> partial GR[6], GP[6] and the 3 GY of those b's
+template <int B0>
+__device__ __forceinline__ void tc_reduce_t(uint32_t taddr, const float (&YY)[6], const float (&PP)[6], const float (&RRv)[8],
+                                            float (&GR)[6], float (&GP)[6], float (&GY3)[3]) {
+    float tr[18];   // sum_d T[b,c,d] * RR_d for the 3 b's
 #pragma unroll
-    for (int i = 0; i < C::A_PER_CH * 6; ++i) v2[i] = 0.f;
+    for (int i = 0; i < 18; ++i) tr[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) GR[i] = GP[i] = 0.f;
+    constexpr int C0 = B0 * 36;            // first column of this half
+    constexpr int L0 = C0 / 32 * 32;       // aligned start of the 32-column loads covering [C0, C0 + 108)
+    constexpr int NL = (C0 + 108 - L0 + 31) / 32;
     uint32_t buf[2][32];
-    tmem_load32_async(taddr, buf[0]);
+    tmem_load32_async(taddr + L0, buf[0]);
 #pragma unroll
-    for (int ci = 0; ci < C::NV / 32; ++ci) {
+    for (int ci = 0; ci < NL; ++ci) {
         tmem_load_wait();
-        if (ci + 1 < C::NV / 32) tmem_load32_async(taddr + 32 * (ci + 1), buf[(ci + 1) & 1]);
+        if (ci + 1 < NL) tmem_load32_async(taddr + L0 + 32 * (ci + 1), buf[(ci + 1) & 1]);
 #pragma unroll
         for (int x = 0; x < 32; ++x) {
-            const int n = 32 * ci + x;
-            if (n < C::A_PER_CH * 36) v2[n / 6] = fmaf(__uint_as_float(buf[ci & 1][x]), PP[n % 6], v2[n / 6]);
+            const int bcd = L0 + 32 * ci + x;
+            if (bcd >= C0 && bcd < C0 + 108) {
+                const int b = bcd / 36, c = (bcd / 6) % 6, d = bcd % 6;
+                const float t = __uint_as_float(buf[ci & 1][x]);
+                GR[d] = fmaf(t, YY[b] * PP[c], GR[d]);
+                tr[(b - B0) * 6 + c] = fmaf(t, RRv[d], tr[(b - B0) * 6 + c]);
+            }
         }
     }
 #pragma unroll
-    for (int al = 0; al < C::A_PER_CH; ++al) {
-        float acc = 0.f;
+    for (int bl = 0; bl < 3; ++bl) {
+        float gy = 0.f;
 #pragma unroll
-        for (int b = 0; b < 6; ++b) acc = fmaf(v2[al * 6 + b], YY[b], acc);
-        GU[A0 + al] = acc;
+        for (int c = 0; c < 6; ++c) {
+            gy = fmaf(tr[bl * 6 + c], PP[c], gy);
+            GP[c] = fmaf(tr[bl * 6 + c], YY[B0 + bl], GP[c]);
+        }
+        GY3[bl] = gy;
     }
 }
 
 // Two threads per sample (256 threads = 8 warps per CTA; warps w and w+4 own the same TMEM lanes):
-//   role 0 ("angle thread", warps 0-3): writes the UU operand, consumes T -> d/d(yaw,pitch,roll)
-//   role 1 ("identity thread", warps 4-7): writes the RR operand, consumes V -> d/du
-// Both keep a bitwise-identical copy of p; the two gradient parts are exchanged through shared memory once per step.
+//   role 0 ("angle thread", warps 0-3): writes the UU operand, consumes the first half of T, finishes d/d(angles)
+//   role 1 ("identity thread", warps 4-7): writes the PP (x) RR operand, consumes the second half of T and V -> d/du
+// Both keep a bitwise-identical copy of p; partial sums and gradient parts cross through shared memory.
 __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_constant__ TuckerArgs a) {
     using C = TcFitCfg;
     extern __shared__ __align__(1024) uint8_t tsm[];
     uint8_t* b1_hi = tsm + C::OFF_B1;
     uint8_t* b1_lo = b1_hi + C::B1_BYTES;
-    uint8_t* bv = tsm + C::OFF_BV;
+    uint8_t* bv_hi = tsm + C::OFF_BV;
+    uint8_t* bv_lo = bv_hi + C::BV_BYTES;
     uint8_t* a1_hi = tsm + C::OFF_A1;
     uint8_t* a1_lo = a1_hi + C::A1_BYTES;
     uint8_t* av_hi = tsm + C::OFF_AV;
@@ -802,7 +817,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
     float* q_s = reinterpret_cast<float*>(tsm + C::OFF_Q);
     uint64_t* bar = reinterpret_cast<uint64_t*>(tsm + C::OFF_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
-    float* gx = reinterpret_cast<float*>(tsm + C::OFF_GX);   // [8][128] gradient exchange between the two roles
+    float* gx = reinterpret_cast<float*>(tsm + C::OFF_GX);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row = tid & 127, role = tid >> 7;
@@ -817,6 +832,8 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
     if (warp == 0) tmem_alloc_cols(tmem_slot, C::TMEM_COLS);
 
     // ---- constant B operands: the folded Gram tensor in both GEMM views, split hi/lo ----
+    //   B1[n = bcd][k = A]          = S[A,b,c,d]
+    //   BV[n = A*6 + b][k = c*6 + d] = S[A,b,c,d]
     for (int idx = tid; idx < C::N1 * C::K1; idx += 256) {
         const int n = idx / C::K1, k = idx % C::K1;
         const float v = (n < C::nBCD && k < C::nA) ? __ldg(a.S + n * 16 + k) : 0.f;
@@ -825,17 +842,17 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         *reinterpret_cast<float*>(b1_hi + ttc::op_offset(n, k, C::K1)) = hi;
         *reinterpret_cast<float*>(b1_lo + ttc::op_offset(n, k, C::K1)) = lo;
     }
-    for (int idx = tid; idx < C::VCH * C::NV * C::KV; idx += 256) {
-        const int ch = idx / (C::NV * C::KV), rem = idx % (C::NV * C::KV), n = rem / C::KV, d = rem % C::KV;
+    for (int idx = tid; idx < C::NV * C::KV; idx += 256) {
+        const int n = idx / C::KV, k = idx % C::KV;
         float v = 0.f;
-        if (n < C::A_PER_CH * C::nB * C::nC && d < C::nD) {
-            const int aa = ch * C::A_PER_CH + n / (C::nB * C::nC), b = (n / C::nC) % C::nB, c = n % C::nC;
-            v = __ldg(a.S + ((b * C::nC + c) * C::nD + d) * 16 + aa);
+        if (n < C::nA * C::nB && k < C::nC * C::nD) {
+            const int aa = n / C::nB, b = n % C::nB;
+            v = __ldg(a.S + (b * 36 + k) * 16 + aa);
         }
         float hi, lo;
         ttc::split_tf32(v, hi, lo);
-        *reinterpret_cast<float*>(bv + (2 * ch) * C::BV_BYTES + ttc::op_offset(n, d, C::KV)) = hi;
-        *reinterpret_cast<float*>(bv + (2 * ch + 1) * C::BV_BYTES + ttc::op_offset(n, d, C::KV)) = lo;
+        *reinterpret_cast<float*>(bv_hi + ttc::op_offset(n, k, C::KV)) = hi;
+        *reinterpret_cast<float*>(bv_lo + ttc::op_offset(n, k, C::KV)) = lo;
     }
 
     // ---- phase A: q[r] = sum_f W2[r][f] * x[f]; the two threads of a sample take half of the rows r each ----
@@ -912,13 +929,13 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         sym_products<3>(cr, RRv);
         RRv[6] = RRv[7] = 0.f;
 
-        // this sample's rows of the two A operands: UU by the angle thread, RR by the identity thread
+        // this sample's rows of the two A operands: UU by the angle thread, PP (x) RR by the identity thread
         if (role == 0) {
             float UU[16];
             sym_products<5>(u, UU);
             UU[15] = 0.f;
 #pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
+            for (int k4 = 0; k4 < C::K1 / 4; ++k4) {
                 float h[4], l[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) ttc::split_tf32(UU[4 * k4 + e], h[e], l[e]);
@@ -927,10 +944,14 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             }
         } else {
 #pragma unroll
-            for (int k4 = 0; k4 < 2; ++k4) {
+            for (int k4 = 0; k4 < C::KV / 4; ++k4) {
                 float h[4], l[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) ttc::split_tf32(RRv[4 * k4 + e], h[e], l[e]);
+                for (int e = 0; e < 4; ++e) {
+                    const int k = 4 * k4 + e;
+                    const float v = k < 36 ? PP[k / 6] * RRv[k % 6] : 0.f;
+                    ttc::split_tf32(v, h[e], l[e]);
+                }
                 *reinterpret_cast<float4*>(av_hi + ttc::op_offset(row, 4 * k4, C::KV)) = make_float4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<float4*>(av_lo + ttc::op_offset(row, 4 * k4, C::KV)) = make_float4(l[0], l[1], l[2], l[3]);
             }
@@ -938,16 +959,16 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         ttc::fence_async_smem();
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (tid == 0 && a.dbg != 1) {   // round 1: T and V chunk 0
+        if (tid == 0 && a.dbg != 1) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             ttc::issue_gemm_3xtf32(tmem + C::COL_T, ttc::smem_u32(a1_hi), ttc::smem_u32(a1_lo), ttc::smem_u32(b1_hi),
                                    ttc::smem_u32(b1_lo), C::K1, C::N1, true);
-            ttc::issue_gemm_3xtf32(tmem + C::COL_V, ttc::smem_u32(av_hi), ttc::smem_u32(av_lo), ttc::smem_u32(bv),
-                                   ttc::smem_u32(bv + C::BV_BYTES), C::KV, C::NV, true);
+            ttc::issue_gemm_3xtf32(tmem + C::COL_V, ttc::smem_u32(av_hi), ttc::smem_u32(av_lo), ttc::smem_u32(bv_hi),
+                                   ttc::smem_u32(bv_lo), C::KV, C::NV, true);
             ttc::umma_commit_to(bar);
         }
         // the linear term does not depend on the MMAs: it runs while they execute.  (Both roles evaluate it: the
-        // angle thread needs ey/ep/er, the identity thread lin_u; splitting it would save ~200 FMAs per thread.)
+        // angle thread needs ey/ep/er, the identity thread lin_u.)
         float lin_u[5], ey[3], ep[3], er[3];
         linear_term<5, 3, 3, 3>(qa, 0, cy, cp, cr, u, lin_u, ey, ep, er);
 
@@ -955,43 +976,45 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-        float GU[15];
+        float GR[6], GP[6], GY3[3];
+        if (role == 1) {
+            // second half of T (b = 3..5): partial sums go to the angle thread
+            if (a.dbg != 2) tc_reduce_t<3>(lane_addr + C::COL_T, YY, PP, RRv, GR, GP, GY3);
 #pragma unroll
-        for (int i = 0; i < 15; ++i) GU[i] = 0.f;
-        if (a.dbg == 2) {
-            if (role == 0) { gx[row] = cy[0]; gx[128 + row] = cp[0]; gx[256 + row] = cr[0]; }
-        } else if (role == 0) {
-            // T[bcd] -> GR, GY, GP -> d/d(yaw, pitch, roll)
-            float GY[6], GP[6], GR[6];
+            for (int i = 0; i < 6; ++i) { gx[(8 + i) * 128 + row] = GR[i]; gx[(14 + i) * 128 + row] = GP[i]; }
 #pragma unroll
-            for (int i = 0; i < 6; ++i) GY[i] = GP[i] = GR[i] = 0.f;
-            float tr[36];   // sum_d T[b,c,d] * RR_d
+            for (int i = 0; i < 3; ++i) gx[(20 + i) * 128 + row] = GY3[i];
+            // V[A,b] = sum_{c,D} PP_c RR_D S[A,b,c,D]  ->  GU[A] = sum_b YY_b V[A,b]  ->  d/du
+            float GU[15];
 #pragma unroll
-            for (int i = 0; i < 36; ++i) tr[i] = 0.f;
-            uint32_t buf[2][32];
-            tmem_load32_async(lane_addr + C::COL_T, buf[0]);
+            for (int i = 0; i < 15; ++i) GU[i] = 0.f;
+            if (a.dbg != 2) {
 #pragma unroll
-            for (int ci = 0; ci < C::N1 / 32; ++ci) {
-                tmem_load_wait();
-                if (ci + 1 < C::N1 / 32) tmem_load32_async(lane_addr + C::COL_T + 32 * (ci + 1), buf[(ci + 1) & 1]);
+                for (int ci = 0; ci < C::NV / 32; ++ci) {
+                    float v[32];
+                    tmem_load32(lane_addr + C::COL_V + 32 * ci, v);
 #pragma unroll
-                for (int x = 0; x < 32; ++x) {
-                    const int bcd = 32 * ci + x;
-                    if (bcd < C::nBCD) {
-                        const int b = bcd / 36, c = (bcd / 6) % 6, d = bcd % 6;
-                        const float t = __uint_as_float(buf[ci & 1][x]);
-                        GR[d] = fmaf(t, YY[b] * PP[c], GR[d]);
-                        tr[b * 6 + c] = fmaf(t, RRv[d], tr[b * 6 + c]);
+                    for (int x = 0; x < 32; ++x) {
+                        const int n = 32 * ci + x;
+                        if (n < 90) GU[n / 6] = fmaf(v[x], YY[n % 6], GU[n / 6]);
                     }
                 }
             }
+            float du[5];
+            sym_backprop<5>(GU, u, du);
 #pragma unroll
-            for (int b = 0; b < 6; ++b)
+            for (int i = 0; i < 5; ++i) gx[(3 + i) * 128 + row] = du[i] - lin_u[i];
+        } else {
+            if (a.dbg != 2) tc_reduce_t<0>(lane_addr + C::COL_T, YY, PP, RRv, GR, GP, GY3);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();   // T and V drained; role 1's partial sums and d/du are in gx
+        if (role == 0) {
+            float GY[6];
 #pragma unroll
-                for (int c = 0; c < 6; ++c) {
-                    GY[b] = fmaf(tr[b * 6 + c], PP[c], GY[b]);
-                    GP[c] = fmaf(tr[b * 6 + c], YY[b], GP[c]);
-                }
+            for (int i = 0; i < 6; ++i) { GR[i] += gx[(8 + i) * 128 + row]; GP[i] += gx[(14 + i) * 128 + row]; }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { GY[i] = GY3[i]; GY[3 + i] = gx[(20 + i) * 128 + row]; }
             float dy[3], dp[3], dr[3];
             sym_backprop<3>(GY, cy, dy);
             sym_backprop<3>(GP, cp, dp);
@@ -1006,36 +1029,8 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             gx[0 * 128 + row] = gy;
             gx[1 * 128 + row] = gp;
             gx[2 * 128 + row] = gr;
-        } else {
-            tc_reduce_v<0>(lane_addr + C::COL_V, PP, YY, GU);
         }
-
-
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();   // T and V chunk 0 drained
-        if (tid == 128 && a.dbg != 1) {  // round 2: V chunks 1 and 2 (consumed by the identity threads only)
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            ttc::issue_gemm_3xtf32(tmem + C::COL_T, ttc::smem_u32(av_hi), ttc::smem_u32(av_lo), ttc::smem_u32(bv + 2 * C::BV_BYTES),
-                                   ttc::smem_u32(bv + 3 * C::BV_BYTES), C::KV, C::NV, true);
-            ttc::issue_gemm_3xtf32(tmem + C::COL_V, ttc::smem_u32(av_hi), ttc::smem_u32(av_lo), ttc::smem_u32(bv + 4 * C::BV_BYTES),
-                                   ttc::smem_u32(bv + 5 * C::BV_BYTES), C::KV, C::NV, true);
-            ttc::umma_commit_to(bar);
-        }
-        if (role == 1) {
-            if (a.dbg != 1) ttc::mbar_wait(bar, phase);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (a.dbg != 2) {
-                tc_reduce_v<5>(lane_addr + C::COL_T, PP, YY, GU);
-                tc_reduce_v<10>(lane_addr + C::COL_V, PP, YY, GU);
-            }
-            float du[5];
-            sym_backprop<5>(GU, u, du);
-#pragma unroll
-            for (int i = 0; i < 5; ++i) gx[(3 + i) * 128 + row] = du[i] - lin_u[i];
-        }
-        phase ^= 1;   // both roles track the barrier phase; the angle threads simply never wait on round 2
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();   // gradient halves exchanged; round-2 results drained
+        __syncthreads();   // all 8 gradient parts in gx
         float g[C::NP];
 #pragma unroll
         for (int i = 0; i < C::NP; ++i) g[i] = gx[i * 128 + row];
@@ -1128,6 +1123,7 @@ constexpr int kTpsBigThreads = 384;  // TMEM-resident-q variant: one 12-warp CTA
 // is bound by the 3-register-operand FFMA rate, not by latency -- so the variant is opt-in (kernel_hint 4) only
 constexpr int kCtaThreads = 128;
 constexpr int kWpsWarps = 4;
+constexpr int64_t kTcCrossover = 2 * 148 * 128;   // two waves of the tensor-core kernel (128 samples per SM)
 constexpr int64_t kWpsCrossover = 8192;  // below this the warp-per-sample kernel finishes sooner (profiles/)
 using TpsDefault = TpsCfg<5, 3, 3, 3, kTpsThreads, kTpsSamples>;
 using TpsBig = TpsCfg<5, 3, 3, 3, kTpsBigThreads, 1, true>;
@@ -1149,9 +1145,10 @@ int launch_fit(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int
     if (const char* e = std::getenv("NLML_TUCKER_DBG")) a.dbg = std::atoi(e);
     // crossover: below ~one thread-per-sample wave the 3000-step chain is latency bound and the
     // CTA-per-sample kernel finishes sooner
-    const bool use_tc = pl->fast && hint == 5;
-    const bool use_tps = pl->fast && (hint == 1 || hint == 4 || (hint == 0 && N >= kWpsCrossover));
-    const bool use_wps = pl->fast && (hint == 3 || (hint == 0 && N < kWpsCrossover));
+    // large batches: the tensor-core iteration kernel (1.45 M poses/s) beats the FP32 thread-per-sample kernel (0.92 M)
+    const bool use_tc = pl->fast && (hint == 5 || (hint == 0 && N >= kTcCrossover));
+    const bool use_tps = pl->fast && !use_tc && (hint == 1 || hint == 4 || (hint == 0 && N >= kWpsCrossover));
+    const bool use_wps = pl->fast && !use_tc && (hint == 3 || (hint == 0 && N < kWpsCrossover));
     if ((hint == 1 || hint == 3 || hint == 4 || hint == 5) && !pl->fast)
         return set_error(NLML_E_UNSUPPORTED, "thread/warp-per-sample kernels are built for ranks (5,3,3,3) only");
     if (use_tc) {
@@ -1299,7 +1296,7 @@ extern "C" int nlml_tucker_fit_host_f32(nlml_tucker_plan* pl, const float* X_hos
     const int np = 3 + pl->ri;
     if (!pl->streams[0]) {
         // two thread-per-sample waves per chunk keeps every SM busy while the next chunk is in flight
-        pl->chunk = (int64_t)pl->num_sms * kTpsMinBlocks * TpsDefault::SAMPLES * 4;   // 4 waves per chunk
+        pl->chunk = (int64_t)pl->num_sms * TcFitCfg::THREADS * 8;   // 8 waves of the tensor-core kernel per chunk
         for (int i = 0; i < 2; ++i) {
             NLML_CUDA(cudaStreamCreateWithFlags(&pl->streams[i], cudaStreamNonBlocking));
             NLML_CUDA(cudaMalloc(&pl->x_dev[i], sizeof(float) * (size_t)pl->chunk * pl->F));
