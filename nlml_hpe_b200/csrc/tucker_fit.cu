@@ -918,9 +918,9 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
 #pragma unroll 1
     for (int it = 0; it < a.T; ++it) {
         float cy[3], dcy[3], cp[3], dcp[3], cr[3], dcr[3], u[5];
-        cos_features<3>(p[0], a.rows_y, cy, dcy);
-        cos_features<3>(p[1], a.rows_p, cp, dcp);
-        cos_features<3>(p[2], a.rows_r, cr, dcr);
+        cos_features_fast<3>(p[0], a.rows_y, cy, dcy);
+        cos_features_fast<3>(p[1], a.rows_p, cp, dcp);
+        cos_features_fast<3>(p[2], a.rows_r, cr, dcr);
 #pragma unroll
         for (int i = 0; i < 5; ++i) u[i] = p[3 + i];
         float YY[6], PP[6], RRv[8];
@@ -967,10 +967,16 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
                                    ttc::smem_u32(bv_lo), C::KV, C::NV, true);
             ttc::umma_commit_to(bar);
         }
-        // the linear term does not depend on the MMAs: it runs while they execute.  (Both roles evaluate it: the
-        // angle thread needs ey/ep/er, the identity thread lin_u.)
+        // the linear term does not depend on the MMAs: it runs while they execute.  Each role keeps only the outputs it
+        // needs (the angle thread ey/ep/er, the identity thread lin_u); the other half is dead code in its branch.
         float lin_u[5], ey[3], ep[3], er[3];
-        linear_term<5, 3, 3, 3>(qa, 0, cy, cp, cr, u, lin_u, ey, ep, er);
+        if (role == 0) {
+            float unused[5];
+            linear_term<5, 3, 3, 3>(qa, 0, cy, cp, cr, u, unused, ey, ep, er);
+        } else {
+            float u0[3], u1[3], u2[3];
+            linear_term<5, 3, 3, 3>(qa, 0, cy, cp, cr, u, lin_u, u0, u1, u2);
+        }
 
         if (a.dbg != 1) ttc::mbar_wait(bar, phase);
         phase ^= 1;

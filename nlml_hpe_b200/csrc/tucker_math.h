@@ -69,6 +69,40 @@ NLML_HD void cos_features(float w, const float* rows, float* c, float* dc) {
     }
 }
 
+// sin and cos of a moderate argument (|x| < ~1e4) without the large-argument slow path of sincosf: three-term
+// Cody-Waite reduction by pi/2 and the classic single-precision minimax kernels on [-pi/4, pi/4] (~1 ulp).
+// Used by the tensor-core kernel, where nine inlined sincosf slow paths would push the iteration body out of
+// the instruction cache.  The factor arguments b*w + c stay within a few radians.
+NLML_HD void sincos_small(float x, float* sn, float* cs) {
+    const float kf = rintf(x * 0.636619772367581343f);   // x * 2/pi
+    float r = fmaf(-kf, 1.5703125f, x);
+    r = fmaf(-kf, 4.837512969970703125e-4f, r);
+    r = fmaf(-kf, 7.54978995489188216e-8f, r);
+    const float r2 = r * r;
+    float ps = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = fmaf(ps, r2, -1.6666654611e-1f);
+    const float s = fmaf(ps * r2, r, r);
+    float pc = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = fmaf(pc, r2, 4.166664568298827e-2f);
+    const float c = fmaf(pc * r2, r2, fmaf(-0.5f, r2, 1.0f));
+    const int q = (int)kf;
+    const float a = (q & 1) ? c : s, b = (q & 1) ? s : c;
+    *sn = (q & 2) ? -a : a;
+    *cs = ((q + 1) & 2) ? -b : b;
+}
+
+template <int R>
+NLML_HD void cos_features_fast(float w, const float* rows, float* c, float* dc) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const float a = rows[4 * j + 0], b = rows[4 * j + 1], ph = rows[4 * j + 2], d = rows[4 * j + 3];
+        float s, co;
+        sincos_small(b * w + ph, &s, &co);
+        c[j] = a * co + d;
+        dc[j] = -(a * b) * s;
+    }
+}
+
 // symmetric second-order monomials v_i v_j (i<=j), packed with pair_index
 template <int R>
 NLML_HD void sym_products(const float* v, float* vv) {
