@@ -749,7 +749,7 @@ struct TcFitCfg {
     static constexpr int OFF_A1 = OFF_BV + 2 * BV_BYTES;               // hi, lo
     static constexpr int OFF_AV = OFF_A1 + 2 * A1_BYTES;               // hi, lo
     static constexpr int OFF_Q = OFF_AV + 2 * AV_BYTES;                // q [R][128] floats; phase-A tiles alias it
-    static constexpr int OFF_BAR = OFF_Q + R * THREADS * 4;
+    static constexpr int OFF_BAR = OFF_Q + RPAD * THREADS * 4;         // q stored as [RPAD/4][128] float4
     static constexpr int OFF_GX = OFF_BAR + 64;                        // exchange between the two roles [NGX][128] floats
     static constexpr int NGX = 8 + 15;                                 // 8 gradient parts + role 1's partial GR, GP, GY
     static constexpr size_t SMEM_BYTES = OFF_GX + NGX * THREADS * 4;
@@ -898,16 +898,18 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             }
             __syncthreads();
         }
+        __syncthreads();   // tiles dead before q (vectorised layout [R/4][128] float4) overwrites the region
 #pragma unroll
-        for (int r = 0; r < RH; ++r)
-            if (role * RH + r < C::R) q_s[(role * RH + r) * C::THREADS + row] = acc[r];
+        for (int r4 = 0; r4 < RH / 4; ++r4)
+            reinterpret_cast<float4*>(q_s)[(role * (RH / 4) + r4) * C::THREADS + row] =
+                make_float4(acc[4 * r4], acc[4 * r4 + 1], acc[4 * r4 + 2], acc[4 * r4 + 3]);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const QStrided qa{q_s + row, C::THREADS, 0};
+    const QVec4 qa{reinterpret_cast<const float4*>(q_s) + row, C::THREADS};
 
     // ---- phase B ----
     float p[C::NP];

@@ -153,6 +153,22 @@ struct QStrided {
     }
 };
 
+// q accessor for the vectorised layout [R/4][pitch] of float4 (element r of the thread's sample = component r%4 of
+// q4[(r/4)*pitch]): eight 128-bit loads per 32 elements instead of 32 scalar ones.
+struct QVec4 {
+    const float4* q4;
+    int pitch;
+    template <int R0, int CNT>
+    NLML_HD void load(int /*n*/, float (&v)[32]) const {
+        static_assert(R0 % 4 == 0, "chunks start on a float4 boundary");
+#pragma unroll
+        for (int x4 = 0; x4 < (CNT + 3) / 4; ++x4) {
+            const float4 t = q4[(R0 / 4 + x4) * pitch];
+            v[4 * x4 + 0] = t.x; v[4 * x4 + 1] = t.y; v[4 * x4 + 2] = t.z; v[4 * x4 + 3] = t.w;
+        }
+    }
+};
+
 // Static walk over q in chunks of 32: chunk C covers r in [32C, min(32C+32, R)), r = i*JKL + jkl.
 template <int RI, int JKL, class QA, int C>
 struct QLoadChunk {
