@@ -826,7 +826,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
     const int F = a.F;
 
     if (tid == 0) {
-        ttc::mbar_init(bar, 1);
+        ttc::mbar_init(bar, 2);   // one commit per GEMM (issued by different threads)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc_cols(tmem_slot, C::TMEM_COLS);
@@ -920,18 +920,11 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
 #pragma unroll 1
     for (int it = 0; it < a.T; ++it) {
         float cy[3], dcy[3], cp[3], dcp[3], cr[3], dcr[3], u[5];
-        cos_features_fast<3>(p[0], a.rows_y, cy, dcy);
-        cos_features_fast<3>(p[1], a.rows_p, cp, dcp);
-        cos_features_fast<3>(p[2], a.rows_r, cr, dcr);
 #pragma unroll
         for (int i = 0; i < 5; ++i) u[i] = p[3 + i];
-        float YY[6], PP[6], RRv[8];
-        sym_products<3>(cy, YY);
-        sym_products<3>(cp, PP);
-        sym_products<3>(cr, RRv);
-        RRv[6] = RRv[7] = 0.f;
-
-        // this sample's rows of the two A operands: UU by the angle thread, PP (x) RR by the identity thread
+        // The T GEMM needs only u: the angle threads publish the UU operand first and thread 0 launches that GEMM
+        // before anybody evaluates a cosine; it runs underneath the feature computation.  (Named barrier 1: the 128
+        // angle threads only.)
         if (role == 0) {
             float UU[16];
             sym_products<5>(u, UU);
@@ -944,30 +937,47 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
                 *reinterpret_cast<float4*>(a1_hi + ttc::op_offset(row, 4 * k4, C::K1)) = make_float4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<float4*>(a1_lo + ttc::op_offset(row, 4 * k4, C::K1)) = make_float4(l[0], l[1], l[2], l[3]);
             }
-        } else {
+            ttc::fence_async_smem();
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tid == 0 && a.dbg != 1) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                ttc::issue_gemm_3xtf32(tmem + C::COL_T, ttc::smem_u32(a1_hi), ttc::smem_u32(a1_lo), ttc::smem_u32(b1_hi),
+                                       ttc::smem_u32(b1_lo), C::K1, C::N1, true);
+                ttc::umma_commit_to(bar);
+            }
+        }
+        cos_features_fast<3>(p[0], a.rows_y, cy, dcy);
+        cos_features_fast<3>(p[1], a.rows_p, cp, dcp);
+        cos_features_fast<3>(p[2], a.rows_r, cr, dcr);
+        float YY[6], PP[6], RRv[8];
+        sym_products<3>(cy, YY);
+        sym_products<3>(cp, PP);
+        sym_products<3>(cr, RRv);
+        RRv[6] = RRv[7] = 0.f;
+        // the identity threads publish the PP (x) RR operand; thread 128 launches the V GEMM (named barrier 2)
+        if (role == 1) {
 #pragma unroll
             for (int k4 = 0; k4 < C::KV / 4; ++k4) {
                 float h[4], l[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const int k = 4 * k4 + e;
-                    const float v = k < 36 ? PP[k / 6] * RRv[k % 6] : 0.f;
+                    const int kk = 4 * k4 + e;
+                    const float v = kk < 36 ? PP[kk / 6] * RRv[kk % 6] : 0.f;
                     ttc::split_tf32(v, h[e], l[e]);
                 }
                 *reinterpret_cast<float4*>(av_hi + ttc::op_offset(row, 4 * k4, C::KV)) = make_float4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<float4*>(av_lo + ttc::op_offset(row, 4 * k4, C::KV)) = make_float4(l[0], l[1], l[2], l[3]);
             }
-        }
-        ttc::fence_async_smem();
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (tid == 0 && a.dbg != 1) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            ttc::issue_gemm_3xtf32(tmem + C::COL_T, ttc::smem_u32(a1_hi), ttc::smem_u32(a1_lo), ttc::smem_u32(b1_hi),
-                                   ttc::smem_u32(b1_lo), C::K1, C::N1, true);
-            ttc::issue_gemm_3xtf32(tmem + C::COL_V, ttc::smem_u32(av_hi), ttc::smem_u32(av_lo), ttc::smem_u32(bv_hi),
-                                   ttc::smem_u32(bv_lo), C::KV, C::NV, true);
-            ttc::umma_commit_to(bar);
+            ttc::fence_async_smem();
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (tid == 128 && a.dbg != 1) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                ttc::issue_gemm_3xtf32(tmem + C::COL_V, ttc::smem_u32(av_hi), ttc::smem_u32(av_lo), ttc::smem_u32(bv_hi),
+                                       ttc::smem_u32(bv_lo), C::KV, C::NV, true);
+                ttc::umma_commit_to(bar);
+            }
         }
         // the linear term does not depend on the MMAs: it runs while they execute.  Each role keeps only the outputs it
         // needs (the angle thread ey/ep/er, the identity thread lin_u); the other half is dead code in its branch.
