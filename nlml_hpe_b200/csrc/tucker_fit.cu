@@ -816,7 +816,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
     uint8_t* av_lo = av_hi + C::AV_BYTES;
     float* q_s = reinterpret_cast<float*>(tsm + C::OFF_Q);
     uint64_t* bar = reinterpret_cast<uint64_t*>(tsm + C::OFF_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
     float* gx = reinterpret_cast<float*>(tsm + C::OFF_GX);
 
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -826,7 +826,8 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
     const int F = a.F;
 
     if (tid == 0) {
-        ttc::mbar_init(bar, 2);   // one commit per GEMM (issued by different threads)
+        ttc::mbar_init(bar, 1);       // T GEMM done
+        ttc::mbar_init(bar + 1, 1);   // V GEMM done
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc_cols(tmem_slot, C::TMEM_COLS);
@@ -947,11 +948,10 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
                 ttc::umma_commit_to(bar);
             }
         }
-        cos_features_fast<3>(p[0], a.rows_y, cy, dcy);
+        // pitch and roll features first: they are all the V GEMM's operand needs; yaw follows once it is launched
         cos_features_fast<3>(p[1], a.rows_p, cp, dcp);
         cos_features_fast<3>(p[2], a.rows_r, cr, dcr);
         float YY[6], PP[6], RRv[8];
-        sym_products<3>(cy, YY);
         sym_products<3>(cp, PP);
         sym_products<3>(cr, RRv);
         RRv[6] = RRv[7] = 0.f;
@@ -976,9 +976,11 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 ttc::issue_gemm_3xtf32(tmem + C::COL_V, ttc::smem_u32(av_hi), ttc::smem_u32(av_lo), ttc::smem_u32(bv_hi),
                                        ttc::smem_u32(bv_lo), C::KV, C::NV, true);
-                ttc::umma_commit_to(bar);
+                ttc::umma_commit_to(bar + 1);
             }
         }
+        cos_features_fast<3>(p[0], a.rows_y, cy, dcy);
+        sym_products<3>(cy, YY);
         // the linear term does not depend on the MMAs: it runs while they execute.  Each role keeps only the outputs it
         // needs (the angle thread ey/ep/er, the identity thread lin_u); the other half is dead code in its branch.
         float lin_u[5], ey[3], ep[3], er[3];
@@ -990,8 +992,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             linear_term<5, 3, 3, 3>(qa, 0, cy, cp, cr, u, lin_u, u0, u1, u2);
         }
 
-        if (a.dbg != 1) ttc::mbar_wait(bar, phase);
-        phase ^= 1;
+        if (a.dbg != 1) ttc::mbar_wait(bar, phase);       // T GEMM (launched first, long done)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
         float GR[6], GP[6], GY3[3];
@@ -1006,6 +1007,8 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             float GU[15];
 #pragma unroll
             for (int i = 0; i < 15; ++i) GU[i] = 0.f;
+            if (a.dbg != 1) ttc::mbar_wait(bar + 1, phase);   // V GEMM
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (a.dbg != 2) {
 #pragma unroll
                 for (int ci = 0; ci < C::NV / 32; ++ci) {
@@ -1025,6 +1028,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         } else {
             if (a.dbg != 2) tc_reduce_t<0>(lane_addr + C::COL_T, YY, PP, RRv, GR, GP, GY3);
         }
+        phase ^= 1;
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();   // T and V drained; role 1's partial sums and d/du are in gx
         if (role == 0) {
