@@ -992,17 +992,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             linear_term<5, 3, 3, 3>(qa, 0, cy, cp, cr, u, lin_u, u0, u1, u2);
         }
 
-        if (a.dbg != 1) ttc::mbar_wait(bar, phase);       // T GEMM (launched first, long done)
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-        float GR[6], GP[6], GY3[3];
         if (role == 1) {
-            // second half of T (b = 3..5): partial sums go to the angle thread
-            if (a.dbg != 2) tc_reduce_t<3>(lane_addr + C::COL_T, YY, PP, RRv, GR, GP, GY3);
-#pragma unroll
-            for (int i = 0; i < 6; ++i) { gx[(8 + i) * 128 + row] = GR[i]; gx[(14 + i) * 128 + row] = GP[i]; }
-#pragma unroll
-            for (int i = 0; i < 3; ++i) gx[(20 + i) * 128 + row] = GY3[i];
             // V[A,b] = sum_{c,D} PP_c RR_D S[A,b,c,D]  ->  GU[A] = sum_b YY_b V[A,b]  ->  d/du
             float GU[15];
 #pragma unroll
@@ -1026,17 +1016,20 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
 #pragma unroll
             for (int i = 0; i < 5; ++i) gx[(3 + i) * 128 + row] = du[i] - lin_u[i];
         } else {
-            if (a.dbg != 2) tc_reduce_t<0>(lane_addr + C::COL_T, YY, PP, RRv, GR, GP, GY3);
-        }
-        phase ^= 1;
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();   // T and V drained; role 1's partial sums and d/du are in gx
-        if (role == 0) {
-            float GY[6];
+            // all of T -> GR, GP, GY -> d/d(yaw, pitch, roll)
+            float GR[6], GP[6], GY[6], GR2[6], GP2[6], GY3[3];
+            if (a.dbg != 1) ttc::mbar_wait(bar, phase);       // T GEMM (launched first, long done)
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (a.dbg != 2) {
+                tc_reduce_t<0>(lane_addr + C::COL_T, YY, PP, RRv, GR, GP, GY3);
 #pragma unroll
-            for (int i = 0; i < 6; ++i) { GR[i] += gx[(8 + i) * 128 + row]; GP[i] += gx[(14 + i) * 128 + row]; }
+                for (int i = 0; i < 3; ++i) GY[i] = GY3[i];
+                tc_reduce_t<3>(lane_addr + C::COL_T, YY, PP, RRv, GR2, GP2, GY3);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) { GY[i] = GY3[i]; GY[3 + i] = gx[(20 + i) * 128 + row]; }
+                for (int i = 0; i < 3; ++i) GY[3 + i] = GY3[i];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { GR[i] += GR2[i]; GP[i] += GP2[i]; }
+            }
             float dy[3], dp[3], dr[3];
             sym_backprop<3>(GY, cy, dy);
             sym_backprop<3>(GP, cp, dp);
@@ -1052,6 +1045,8 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             gx[1 * 128 + row] = gp;
             gx[2 * 128 + row] = gr;
         }
+        phase ^= 1;
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();   // all 8 gradient parts in gx
         float g[C::NP];
 #pragma unroll
