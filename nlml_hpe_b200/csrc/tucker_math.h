@@ -24,6 +24,7 @@
 #else
 #define NLML_HD inline
 #include <cmath>
+struct alignas(16) float4 { float x, y, z, w; };   // host check build only
 #endif
 
 namespace nlml {

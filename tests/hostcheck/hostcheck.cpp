@@ -81,3 +81,8 @@ extern "C" int hostcheck_tucker_grad_5333(const float* W2, int F, const double* 
     }
     return 0;
 }
+
+// sin/cos of the tensor-core kernel (tucker_math.h sincos_small), exposed so its accuracy can be pinned against libm.
+extern "C" void hostcheck_sincos_small(const float* x, int64_t n, float* sn, float* cs) {
+    for (int64_t i = 0; i < n; ++i) nlml::sincos_small(x[i], sn + i, cs + i);
+}

@@ -62,3 +62,19 @@ def test_fit_edge_inputs(hostcheck, art, rows, tucker_golden):
     ref = tucker_golden["sgd500_edge_P"]
     assert np.abs(P[:, :3] - ref[:, :3]).max() * DEG < 1e-2
     assert np.abs(P[1]).max() == 0.0 and np.abs(ref[1]).max() == 0.0   # zero input never moves
+
+
+def test_sincos_small_accuracy(hostcheck):
+    """The tensor-core kernel's slow-path-free sincos: <= 2 ulp-ish absolute error on the argument range of the
+    cosine factors (b*w + c stays within a few radians; checked out to +-100)."""
+    import ctypes
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-8, 8, 200000), rng.uniform(-100, 100, 50000),
+                        np.array([0.0, -0.0, np.pi / 4, -np.pi / 4, np.pi / 2, np.pi, 1e-8, -1e-8])]).astype(np.float32)
+    sn, cs = np.empty_like(x), np.empty_like(x)
+    hostcheck.hostcheck_sincos_small.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    hostcheck.hostcheck_sincos_small.restype = None
+    hostcheck.hostcheck_sincos_small(x.ctypes.data, x.size, sn.ctypes.data, cs.ctypes.data)
+    xd = x.astype(np.float64)
+    assert np.abs(sn - np.sin(xd)).max() < 2.5e-7
+    assert np.abs(cs - np.cos(xd)).max() < 2.5e-7
