@@ -34,6 +34,9 @@ TUCKER_FLOP_PER_POSE = 2 * (135 * F + T_ITERS * TUCKER_FMA_PER_ITER)
 TUCKER_FLOP_PER_POSE_GRAM = 2 * 135 * F + T_ITERS * (2 * 135 * 135 + 2000)
 TUCKER_FLOP_PER_POSE_REFERENCE = T_ITERS * 2 * 2 * 135 * F
 # tensor-core kernel: issued TF32 flops per pose (two GEMMs per iteration, 3 MMAs per MAC)
+# one Newton evaluation: per S row (216) 15 FMA for T + 4x15 FMA for GU/HY/HP/HR + 20 for the scalar sums,
+# linear term 5*3*(6*9) FMA + assembly
+SOLVE_FLOP_PER_EVAL = 2 * (216 * (15 + 60 + 20) + 5 * 3 * 54 + 400)
 TUCKER_TC_FLOP_PER_POSE = T_ITERS * 2 * 3 * (224 * 16 + 96 * 40)
 TUCKER_BYTES_PER_POSE = F * 4 + 8 * 4
 MLP_FLOP_PER_POSE = 4_714_240
@@ -265,6 +268,15 @@ def run_b200(args):
         e2e_steps = max(1, min(steps, args.e2e_steps))
         ms_e2e = time_host_steps(lambda: fitter.fit_host(X_host, T_ITERS, LR, CLIP, out=P_host), e2e_steps, 1, torch, dist, world)
         tucker_e2e_ms = ms_e2e / e2e_steps
+        # converged fit: what TD_Tester.Test computes with scipy Powell
+        l0 = fitter.launches
+        ms_s, _ = time_steps(lambda: fitter.solve(X, out=P), steps, warmup, torch, dist, world)
+        s_launches = (fitter.launches - l0) * steps // (steps + warmup)
+        solve_ms = ms_s / steps
+        ms_se = time_host_steps(lambda: fitter.solve_host(X_host.numpy(), out=P_host), e2e_steps, 1, torch, dist, world)
+        solve_e2e_ms = ms_se / e2e_steps
+        _, ev = fitter.solve(X[:65536], return_evals=True)
+        solve_evals = float(ev.float().mean().item())
     clk = clocks.summary()
 
     with ClockSampler(local) as clocks2:
@@ -322,6 +334,20 @@ def run_b200(args):
                          "unit": "GB/s", "frac": per_gpu_t * TUCKER_BYTES_PER_POSE / 1e9 / peaks["hbm_gbs"], "traffic": None,
                          "peak_source": peaks["source"]},
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
+        "converged": {
+            "metric": "poses/sec (Tucker-fit to convergence: damped Newton from p=0, the optimum TD_Tester.Test searches with scipy Powell)",
+            "value": total / (solve_ms * 1e-3), "unit": "poses/s", "ms_per_step": solve_ms, "dtype": "f32",
+            "e2e": {"value": total / (solve_e2e_ms * 1e-3), "unit": "poses/s", "h2d_bytes_per_step": n * F * 4,
+                    "d2h_bytes_per_step": n * 8 * 4, "steps": e2e_steps, "api": "nlml_tucker_solve_host_f32"},
+            "gpu_launches": int(s_launches), "mean_evaluations_per_pose": solve_evals,
+            "roofline_fp32": {"bound": "fp32_fma", "unit": "TFLOP/s", "peak_3reg": fp32_peak_3reg,
+                              "achieved": n / (solve_ms * 1e-3) * (2 * 135 * F + solve_evals * SOLVE_FLOP_PER_EVAL) / 1e12,
+                              "frac_3reg": n / (solve_ms * 1e-3) * (2 * 135 * F + solve_evals * SOLVE_FLOP_PER_EVAL) / 1e12 / fp32_peak_3reg,
+                              "note": f"2*R*F projection + mean evaluations x {SOLVE_FLOP_PER_EVAL} flop (value+gradient+Hessian from one "
+                                      "pass over the folded Gram tensor); warps run until their slowest sample converges"},
+            "roofline_hbm": {"bound": "hbm", "achieved": n / (solve_ms * 1e-3) * TUCKER_BYTES_PER_POSE / 1e9, "peak": peaks["hbm_gbs"],
+                             "unit": "GB/s", "frac": n / (solve_ms * 1e-3) * TUCKER_BYTES_PER_POSE / 1e9 / peaks["hbm_gbs"]},
+        },
         "mlp": {
             "metric": "poses/sec (Encoder + yaw/pitch/roll MLP heads forward)", "value": mlp_pps, "unit": "poses/s",
             "ms_per_step": mlp_ms, "dtype": "f32",

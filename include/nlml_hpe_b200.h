@@ -67,6 +67,18 @@ int nlml_tucker_fit_f32(nlml_tucker_plan* plan, const float* X_dev, int64_t N, i
 int nlml_tucker_fit_host_f32(nlml_tucker_plan* plan, const float* X_host, int64_t N, int64_t ldx,
                              int iters, float lr, float clip, float* P_out_host, int64_t ldp);
 
+/* Converged fit: what TD_Tester.Test ships by default is a scipy Powell search over the same objective from
+ * p = 0 (/root/reference/TD_Tester.py:164, :191-199).  This entry point reaches the local minimum of that basin
+ * with a damped Newton iteration on the exact Hessian (csrc/tucker_math.h tucker_lm_solve), one thread per
+ * sample, data-dependent number of evaluations (max_evals; 0 = default 64).  Ranks (5,3,3,3) only
+ * (NLML_E_UNSUPPORTED otherwise).  P_out as nlml_tucker_fit_f32 (radians + identity coefficients);
+ * evals_out_dev: optional DEVICE int32 [N], evaluations used per sample.  Asynchronous on `stream`. */
+int nlml_tucker_solve_f32(nlml_tucker_plan* plan, const float* X_dev, int64_t N, int64_t ldx, int max_evals,
+                          float* P_out_dev, int64_t ldp, int32_t* evals_out_dev, void* stream);
+/* Same with HOST buffers (pipelined like nlml_tucker_fit_host_f32). */
+int nlml_tucker_solve_host_f32(nlml_tucker_plan* plan, const float* X_host, int64_t N, int64_t ldx,
+                               int max_evals, float* P_out_host, int64_t ldp);
+
 /* Number of kernel launches issued by this plan so far (for bench.py's gpu_launches). */
 int64_t nlml_tucker_launch_count(const nlml_tucker_plan* plan);
 

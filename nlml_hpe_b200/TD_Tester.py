@@ -8,10 +8,11 @@ Same names, argument meaning and return conventions as /root/reference/TD_Tester
 plus the batched form the reference lacks (`optimize_with_sgd_batch`).
 
 Behavioural notes:
-* `Test` here runs the FIXED-ITERATION fit (the block the reference keeps commented out at
-  :168-184 and the only one with a parity contract) and converts radians to degrees as :182-184
-  does.  The shipped default, scipy Powell (:191-199), is a data-dependent f64 search and is a
-  "next" row of SURVEY.md section 8f.
+* `Test` runs, like the reference's default, a CONVERGED fit from p = 0: where the reference calls scipy Powell
+  (:191-199; unpinned third-party search, stops at xtol = ftol = 1e-4) this module runs the damped-Newton solve
+  of the same objective on the GPU (`solve_batch`), which ends in the same basin at a lower or equal loss
+  (tests/test_tucker_gpu.py).  `TEST_SOLVER = "sgd"` selects the fixed-iteration block the reference keeps
+  commented out at :168-184 instead (the one with the bit-level parity contract).
 * Like the reference, `Test` returns the u_id it was GIVEN (normally None), not the optimum (:291).
 * No module-global trace lists (:18-22) are kept: the call is re-entrant.
 * No progress printing (:131, :142-143).
@@ -24,6 +25,8 @@ import numpy as np
 import torch
 
 from .tucker import TuckerFitter
+
+TEST_SOLVER = "converged"   # or "sgd": what Test() runs (see the module docstring)
 
 _PLAN_CACHE = {}
 _PLAN_CACHE_MAX = 4
@@ -66,6 +69,19 @@ def optimize_with_sgd_batch(W, X, u_id_shape, params_y, params_p, params_r, lear
     return torch.from_numpy(out) if was_tensor else out
 
 
+def solve_batch(W, X, u_id_shape, params_y, params_p, params_r, max_evals=0, device=None):
+    """Batched converged fit (the optimum Test() looks for, TD_Tester.py:191-199): X [N,F] -> [N, 3+u_id_shape]
+    radians + identity coefficients, of the same kind as X."""
+    fit = _fitter(W, params_y, params_p, params_r, device)
+    if fit.ranks[0] != int(u_id_shape):
+        raise ValueError(f"u_id_shape={u_id_shape} does not match W.shape[0]={fit.ranks[0]}")
+    if isinstance(X, torch.Tensor) and X.is_cuda:
+        return fit.solve(X, max_evals)
+    was_tensor = isinstance(X, torch.Tensor)
+    out = fit.solve_host(_as_numpy(X, np.float32), max_evals)
+    return torch.from_numpy(out) if was_tensor else out
+
+
 def optimize_with_sgd(W, x, u_id, u_id_shape, params_y, params_p, params_r, learning_rate=0.001,
                       num_iterations=3000):
     """Single-sample form with the reference signature (TD_Tester.py:127).  `u_id` is unused there too."""
@@ -76,6 +92,12 @@ def optimize_with_sgd(W, x, u_id, u_id_shape, params_y, params_p, params_r, lear
 
 def Test(W, x, u_id_shape, optimized_params_y, optimized_params_p, optimized_params_r, u_id, f_y, f_p, f_r):
     """Reference entry point (TD_Tester.py:162-163) -> (yaw, pitch, roll) in degrees and the given u_id."""
-    p = optimize_with_sgd(W, x, u_id, u_id_shape, optimized_params_y, optimized_params_p, optimized_params_r)
-    deg = np.degrees(p.numpy().astype(np.float64))
+    if TEST_SOLVER == "sgd":
+        p = optimize_with_sgd(W, x, u_id, u_id_shape, optimized_params_y, optimized_params_p, optimized_params_r).numpy()
+    elif TEST_SOLVER == "converged":
+        p = np.asarray(solve_batch(W, _as_numpy(x, np.float32).reshape(1, -1), u_id_shape, optimized_params_y,
+                                   optimized_params_p, optimized_params_r))[0]
+    else:
+        raise ValueError(f"TEST_SOLVER must be 'converged' or 'sgd', got {TEST_SOLVER!r}")
+    deg = np.degrees(p.astype(np.float64))
     return deg[0], deg[1], deg[2], u_id

@@ -16,7 +16,7 @@ c_double_p = ctypes.POINTER(ctypes.c_double)
 EXPORTS = [
     "nlml_abi_version", "nlml_last_error",
     "nlml_tucker_plan_create", "nlml_tucker_plan_destroy", "nlml_tucker_fit_f32",
-    "nlml_tucker_fit_host_f32", "nlml_tucker_launch_count",
+    "nlml_tucker_fit_host_f32", "nlml_tucker_solve_f32", "nlml_tucker_solve_host_f32", "nlml_tucker_launch_count",
     "nlml_mlp_plan_create", "nlml_mlp_plan_destroy", "nlml_mlp_forward_f32",
     "nlml_mlp_forward_host_f32", "nlml_mlp_latent_f32", "nlml_mlp_launch_count", "nlml_mlp_set_path",
     "nlml_measure_fp32_tflops", "nlml_measure_fp32_tflops_3reg", "nlml_debug_tf32_gemm",
@@ -47,6 +47,8 @@ def load():
     lib.nlml_tucker_plan_destroy.restype = None
     lib.nlml_tucker_fit_f32.argtypes = [vp, vp, i64, i64, i32, f32, f32, vp, i64, i32, vp]
     lib.nlml_tucker_fit_host_f32.argtypes = [vp, vp, i64, i64, i32, f32, f32, vp, i64]
+    lib.nlml_tucker_solve_f32.argtypes = [vp, vp, i64, i64, i32, vp, i64, vp, vp]
+    lib.nlml_tucker_solve_host_f32.argtypes = [vp, vp, i64, i64, i32, vp, i64]
     lib.nlml_tucker_launch_count.argtypes = [vp]
     lib.nlml_tucker_launch_count.restype = i64
     lib.nlml_mlp_plan_create.argtypes = [vp, vp, vp, vp, i32, ctypes.POINTER(vp)]

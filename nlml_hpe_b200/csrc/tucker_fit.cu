@@ -39,6 +39,8 @@ struct TuckerArgs {
     int nBCDp;
     int vec_ok;  // X rows and W2 rows are 16-byte aligned and F % 4 == 0
     int dbg;     // measurement only (NLML_TUCKER_DBG): tensor-core kernel 1 = no MMAs / waits, 2 = no TMEM consumption
+    LmOptions lm;   // converged solve only
+    int* evals;     // converged solve only: optional [N] evaluations used per sample
     float rows_y[4 * kMaxModeRank], rows_p[4 * kMaxModeRank], rows_r[4 * kMaxModeRank];
 };
 
@@ -180,7 +182,8 @@ __device__ __forceinline__ float4 load_row4(const float* __restrict__ row, int f
     return v;
 }
 
-template <int RI, int RY, int RP, int RR, int THREADS, int NS, int MINB, bool QTMEM>
+// SOLVE: phase B is the converged damped-Newton solve (tucker_lm_solve) instead of the T fixed iterations.
+template <int RI, int RY, int RP, int RR, int THREADS, int NS, int MINB, bool QTMEM, bool SOLVE = false>
 __global__ void __launch_bounds__(THREADS, MINB) tucker_fit_tps_kernel(const __grid_constant__ TuckerArgs a) {
     using C = TpsCfg<RI, RY, RP, RR, THREADS, NS, QTMEM>;
     extern __shared__ __align__(16) float smem[];
@@ -271,6 +274,23 @@ __global__ void __launch_bounds__(THREADS, MINB) tucker_fit_tps_kernel(const __g
         for (int r = 0; r < C::R; ++r) qn_s[r * THREADS + tid] = acc[r];
     }
     __syncthreads();  // S_s complete, tiles dead
+    }
+
+    if constexpr (SOLVE) {
+        // ---- phase B': converged fit, data-dependent number of Newton evaluations per sample ----
+        static_assert(!SOLVE || (NS == 1 && !QTMEM), "the solve variant keeps one sample per thread with q in shared memory");
+        static_assert(!SOLVE || 3 * (tri(RY) + tri(RP)) <= tri(RY) * tri(RP), "scratch column too small for the solve");
+        float ps[C::NP], Lf;
+        const int evals = tucker_lm_solve<RI, RY, RP, RR, C::NAP>(S_s, q_s + tid, THREADS, scr_s + tid, THREADS, a.rows_y,
+                                                                  a.rows_p, a.rows_r, a.lm, ps, Lf);
+        const long long row = s0 + tid;
+        if (row < a.N) {
+            float* out = a.P + row * a.ldp;
+#pragma unroll
+            for (int i = 0; i < C::NP; ++i) out[i] = ps[i];
+            if (a.evals) a.evals[row] = evals;
+        }
+        return;
     }
 
     // ---- phase B: T iterations entirely on chip ----
@@ -1135,6 +1155,7 @@ constexpr int kTpsThreads = 128;   // threads per CTA of the thread-per-sample k
 constexpr int kTpsSamples = 1;     // samples per thread.  2 halves the shared-memory wavefronts per sample but the q
                                    // buffer then limits the SM to 4 warps: measured 740 k poses/s against 919 k at 1.
 constexpr int kTpsMinBlocks = 2;
+constexpr int kSolveMinBlocks = 2;   // converged-solve variant of the same kernel
 constexpr int kTpsBigThreads = 384;  // TMEM-resident-q variant: one 12-warp CTA per SM
 // measured: 913 k poses/s with q in TMEM (12 warps/SM) vs 912 k with q in shared memory (8 warps/SM) -- the kernel
 // is bound by the 3-register-operand FFMA rate, not by latency -- so the variant is opt-in (kernel_hint 4) only
@@ -1188,6 +1209,63 @@ int launch_fit(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int
     }
     NLML_CUDA(cudaGetLastError());
     pl->launches += 1;
+    return 0;
+}
+
+// converged fit: thread-per-sample kernel, phase B' = tucker_lm_solve
+int launch_solve(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int max_evals, float* P, int64_t ldp,
+                 int* evals, cudaStream_t st) {
+    if (N == 0) return 0;
+    if (!pl->fast) return set_error(NLML_E_UNSUPPORTED, "the converged solve is built for ranks (5,3,3,3) only");
+    TuckerArgs a = pl->base;
+    a.X = X;
+    a.N = N;
+    a.ldx = ldx;
+    a.P = P;
+    a.ldp = ldp;
+    a.vec_ok = (pl->F % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+    a.lm = lm_default_options();
+    if (max_evals > 0) a.lm.max_evals = max_evals;
+    a.evals = evals;
+    auto kern = tucker_fit_tps_kernel<5, 3, 3, 3, kTpsThreads, 1, kSolveMinBlocks, false, true>;
+    kern<<<(unsigned)ceil_div(N, TpsDefault::SAMPLES), kTpsThreads, TpsDefault::SMEM_BYTES, st>>>(a);
+    NLML_CUDA(cudaGetLastError());
+    pl->launches += 1;
+    return 0;
+}
+
+// HOST buffers: chunk the batch and overlap H2D copy / kernel / D2H copy on two internal streams.
+template <class Launch>
+int host_pipeline(nlml_tucker_plan* pl, const float* X_host, int64_t N, int64_t ldx, float* P_out_host, int64_t ldp,
+                  Launch&& launch) {
+    const int np = 3 + pl->ri;
+    if (!pl->streams[0]) {
+        pl->chunk = (int64_t)pl->num_sms * TcFitCfg::THREADS * 8;   // 8 waves of the tensor-core kernel per chunk
+        for (int i = 0; i < 2; ++i) {
+            NLML_CUDA(cudaStreamCreateWithFlags(&pl->streams[i], cudaStreamNonBlocking));
+            NLML_CUDA(cudaMalloc(&pl->x_dev[i], sizeof(float) * (size_t)pl->chunk * pl->F));
+            NLML_CUDA(cudaMalloc(&pl->p_dev[i], sizeof(float) * (size_t)pl->chunk * np));
+        }
+    }
+    int slot = 0;
+    for (int64_t s0 = 0; s0 < N; s0 += pl->chunk, slot ^= 1) {
+        const int64_t n = std::min<int64_t>(pl->chunk, N - s0);
+        cudaStream_t st = pl->streams[slot];
+        // stream order makes the reuse of this slot's buffers safe (previous chunk on the same stream is done)
+        if (ldx == pl->F)   // contiguous rows: one linear DMA instead of a pitched copy
+            NLML_CUDA(cudaMemcpyAsync(pl->x_dev[slot], X_host + s0 * ldx, sizeof(float) * pl->F * n, cudaMemcpyHostToDevice, st));
+        else
+            NLML_CUDA(cudaMemcpy2DAsync(pl->x_dev[slot], sizeof(float) * pl->F, X_host + s0 * ldx, sizeof(float) * ldx,
+                                        sizeof(float) * pl->F, (size_t)n, cudaMemcpyHostToDevice, st));
+        if (int rc = launch(pl->x_dev[slot], n, pl->p_dev[slot], st)) return rc;
+        if (ldp == np)
+            NLML_CUDA(cudaMemcpyAsync(P_out_host + s0 * ldp, pl->p_dev[slot], sizeof(float) * np * n, cudaMemcpyDeviceToHost, st));
+        else
+            NLML_CUDA(cudaMemcpy2DAsync(P_out_host + s0 * ldp, sizeof(float) * ldp, pl->p_dev[slot], sizeof(float) * np,
+                                        sizeof(float) * np, (size_t)n, cudaMemcpyDeviceToHost, st));
+    }
+    NLML_CUDA(cudaStreamSynchronize(pl->streams[0]));
+    NLML_CUDA(cudaStreamSynchronize(pl->streams[1]));
     return 0;
 }
 }  // namespace
@@ -1256,6 +1334,8 @@ extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, i
     if (pl->fast) {
         auto kern = tucker_fit_tps_kernel<5, 3, 3, 3, kTpsThreads, kTpsSamples, kTpsMinBlocks, false>;
         NLML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpsDefault::SMEM_BYTES));
+        NLML_CUDA(cudaFuncSetAttribute(tucker_fit_tps_kernel<5, 3, 3, 3, kTpsThreads, 1, kSolveMinBlocks, false, true>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpsDefault::SMEM_BYTES));
         NLML_CUDA(cudaFuncSetAttribute(tucker_fit_tps_kernel<5, 3, 3, 3, kTpsBigThreads, 1, 1, true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpsBig::SMEM_BYTES));
         NLML_CUDA(cudaFuncSetAttribute(tucker_fit_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcFitCfg::SMEM_BYTES));
@@ -1311,35 +1391,31 @@ extern "C" int nlml_tucker_fit_host_f32(nlml_tucker_plan* pl, const float* X_hos
     if (N < 0 || ldx < pl->F || ldp < 3 + pl->ri || iters < 0) return set_error(NLML_E_INVALID, "bad sizes");
     DeviceGuard guard(pl->device);
     const int np = 3 + pl->ri;
-    if (!pl->streams[0]) {
-        // two thread-per-sample waves per chunk keeps every SM busy while the next chunk is in flight
-        pl->chunk = (int64_t)pl->num_sms * TcFitCfg::THREADS * 8;   // 8 waves of the tensor-core kernel per chunk
-        for (int i = 0; i < 2; ++i) {
-            NLML_CUDA(cudaStreamCreateWithFlags(&pl->streams[i], cudaStreamNonBlocking));
-            NLML_CUDA(cudaMalloc(&pl->x_dev[i], sizeof(float) * (size_t)pl->chunk * pl->F));
-            NLML_CUDA(cudaMalloc(&pl->p_dev[i], sizeof(float) * (size_t)pl->chunk * np));
-        }
-    }
-    int slot = 0;
-    for (int64_t s0 = 0; s0 < N; s0 += pl->chunk, slot ^= 1) {
-        const int64_t n = std::min<int64_t>(pl->chunk, N - s0);
-        cudaStream_t st = pl->streams[slot];
-        // stream order makes the reuse of this slot's buffers safe (previous chunk on the same stream is done)
-        if (ldx == pl->F)   // contiguous rows: one linear DMA instead of a pitched copy
-            NLML_CUDA(cudaMemcpyAsync(pl->x_dev[slot], X_host + s0 * ldx, sizeof(float) * pl->F * n, cudaMemcpyHostToDevice, st));
-        else
-            NLML_CUDA(cudaMemcpy2DAsync(pl->x_dev[slot], sizeof(float) * pl->F, X_host + s0 * ldx, sizeof(float) * ldx,
-                                        sizeof(float) * pl->F, (size_t)n, cudaMemcpyHostToDevice, st));
-        if (int rc = launch_fit(pl, pl->x_dev[slot], n, pl->F, iters, lr, clip, pl->p_dev[slot], np, 0, st)) return rc;
-        if (ldp == np)
-            NLML_CUDA(cudaMemcpyAsync(P_out_host + s0 * ldp, pl->p_dev[slot], sizeof(float) * np * n, cudaMemcpyDeviceToHost, st));
-        else
-            NLML_CUDA(cudaMemcpy2DAsync(P_out_host + s0 * ldp, sizeof(float) * ldp, pl->p_dev[slot], sizeof(float) * np,
-                                        sizeof(float) * np, (size_t)n, cudaMemcpyDeviceToHost, st));
-    }
-    NLML_CUDA(cudaStreamSynchronize(pl->streams[0]));
-    NLML_CUDA(cudaStreamSynchronize(pl->streams[1]));
-    return 0;
+    return host_pipeline(pl, X_host, N, ldx, P_out_host, ldp, [&](const float* x, int64_t n, float* p, cudaStream_t st) {
+        return launch_fit(pl, x, n, pl->F, iters, lr, clip, p, np, 0, st);
+    });
+}
+
+extern "C" int nlml_tucker_solve_f32(nlml_tucker_plan* pl, const float* X_dev, int64_t N, int64_t ldx, int max_evals,
+                                     float* P_out_dev, int64_t ldp, int32_t* evals_out_dev, void* stream) {
+    if (!pl || (N > 0 && (!X_dev || !P_out_dev))) return set_error(NLML_E_INVALID, "null pointer argument");
+    if (N < 0 || ldx < pl->F || ldp < 3 + pl->ri || max_evals < 0 || max_evals == 1)
+        return set_error(NLML_E_INVALID, "bad sizes: N=%lld ldx=%lld (F=%d) ldp=%lld (need >= %d) max_evals=%d (0 = default, else >= 2)",
+                         (long long)N, (long long)ldx, pl->F, (long long)ldp, 3 + pl->ri, max_evals);
+    DeviceGuard guard(pl->device);
+    return launch_solve(pl, X_dev, N, ldx, max_evals, P_out_dev, ldp, evals_out_dev, (cudaStream_t)stream);
+}
+
+extern "C" int nlml_tucker_solve_host_f32(nlml_tucker_plan* pl, const float* X_host, int64_t N, int64_t ldx,
+                                          int max_evals, float* P_out_host, int64_t ldp) {
+    if (!pl || (N > 0 && (!X_host || !P_out_host))) return set_error(NLML_E_INVALID, "null pointer argument");
+    if (N < 0 || ldx < pl->F || ldp < 3 + pl->ri || max_evals < 0 || max_evals == 1) return set_error(NLML_E_INVALID, "bad sizes");
+    if (!pl->fast) return set_error(NLML_E_UNSUPPORTED, "the converged solve is built for ranks (5,3,3,3) only");
+    DeviceGuard guard(pl->device);
+    const int np = 3 + pl->ri;
+    return host_pipeline(pl, X_host, N, ldx, P_out_host, ldp, [&](const float* x, int64_t n, float* p, cudaStream_t st) {
+        return launch_solve(pl, x, n, pl->F, max_evals, p, np, nullptr, st);
+    });
 }
 
 extern "C" int64_t nlml_tucker_launch_count(const nlml_tucker_plan* pl) { return pl ? pl->launches : 0; }

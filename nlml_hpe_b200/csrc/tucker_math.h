@@ -361,6 +361,320 @@ NLML_HD void tucker_gradient(const float (&p)[NS][3 + RI], const float* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Converged fit: damped Newton / Levenberg-Marquardt on the same folded form.
+// What the reference ships by default is a scipy Powell search over this objective from p = 0
+// (TD_Tester.py:164, :191-194); the solver below reaches the local minimum of the same basin with the exact
+// Hessian.  Because L - 0.5 x.x = F1 + F2 is a polynomial in (u, c_y, c_p, c_r), every derivative along an angle
+// is the same contraction with the monomials replaced by their derivatives along that angle:
+//   YY -> Y1 = d(YY)/dw_y, Y2 = d2(YY)/dw_y^2, ...   (sym_products_d)
+// so one pass over S yields value, gradient and Hessian.
+// ---------------------------------------------------------------------------------------------
+template <int R>
+NLML_HD void cos_features2(float w, const float* rows, float* c, float* dc, float* d2c) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const float a = rows[4 * j + 0], b = rows[4 * j + 1], ph = rows[4 * j + 2], d = rows[4 * j + 3];
+        float s, co;
+        sincos_small(b * w + ph, &s, &co);
+        c[j] = a * co + d;
+        dc[j] = -(a * b) * s;
+        d2c[j] = -(a * b * b) * co;
+    }
+}
+
+// monomials v_i v_j (i<=j) of a vector that depends on one scalar, with their first and second derivatives
+template <int R>
+NLML_HD void sym_products_d(const float* v, const float* dv, const float* d2v, float* vv, float* vv1, float* vv2) {
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = i; j < R; ++j) {
+            const int k = pair_index(i, j, R);
+            vv[k] = v[i] * v[j];
+            vv1[k] = fmaf(dv[i], v[j], v[i] * dv[j]);
+            vv2[k] = fmaf(d2v[i], v[j], fmaf(2.0f * dv[i], dv[j], v[i] * d2v[j]));
+        }
+}
+
+// packed lower triangle of a symmetric NP x NP matrix
+NLML_HD constexpr int tri_index(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
+
+// Value (without the constant 0.5 x.x), gradient and Hessian of the objective at p = (w_y, w_p, w_r, u).
+//   scr : 3*(nB+nC) floats of per-sample scratch (element k at scr[k*sstride]).
+//   q   : q = W2 x of this sample, element r at q[r*qstride].
+template <int RI, int RY, int RP, int RR, int NAP>
+NLML_HD void tucker_newton_eval(const float (&p)[3 + RI], const float* __restrict__ S, const float* __restrict__ q,
+                                int qstride, float* scr, int sstride, const float* rows_y, const float* rows_p,
+                                const float* rows_r, float& Lval, float (&g)[3 + RI],
+                                float (&H)[(3 + RI) * (4 + RI) / 2]) {
+    constexpr int nA = tri(RI), nB = tri(RY), nC = tri(RP), nD = tri(RR);
+    float u[RI], UU[nA];
+    float cy[RY], dcy[RY], d2cy[RY], cp[RP], dcp[RP], d2cp[RP], cr[RR], dcr[RR], d2cr[RR];
+    float R0[nD], R1[nD], R2[nD];
+    cos_features2<RY>(p[0], rows_y, cy, dcy, d2cy);
+    cos_features2<RP>(p[1], rows_p, cp, dcp, d2cp);
+    cos_features2<RR>(p[2], rows_r, cr, dcr, d2cr);
+#pragma unroll
+    for (int i = 0; i < RI; ++i) u[i] = p[3 + i];
+    sym_products<RI>(u, UU);
+    sym_products_d<RR>(cr, dcr, d2cr, R0, R1, R2);
+    {   // values indexed by the (b,c) loop counters go through the scratch column
+        float Y0[nB], Y1[nB], Y2[nB], P0[nC], P1[nC], P2[nC];
+        sym_products_d<RY>(cy, dcy, d2cy, Y0, Y1, Y2);
+        sym_products_d<RP>(cp, dcp, d2cp, P0, P1, P2);
+#pragma unroll
+        for (int b = 0; b < nB; ++b) {
+            scr[(3 * b + 0) * sstride] = Y0[b];
+            scr[(3 * b + 1) * sstride] = Y1[b];
+            scr[(3 * b + 2) * sstride] = Y2[b];
+        }
+#pragma unroll
+        for (int c = 0; c < nC; ++c) {
+            scr[(3 * nB + 3 * c + 0) * sstride] = P0[c];
+            scr[(3 * nB + 3 * c + 1) * sstride] = P1[c];
+            scr[(3 * nB + 3 * c + 2) * sstride] = P2[c];
+        }
+    }
+
+    // ---- quadratic term F2 = sum S UU YY PP RR and its derivatives ----
+    float GU[nA], HY[nA], HP[nA], HR[nA];
+#pragma unroll
+    for (int a = 0; a < nA; ++a) GU[a] = HY[a] = HP[a] = HR[a] = 0.f;
+    float F2 = 0.f, gy = 0.f, gp = 0.f, gr = 0.f, hyy = 0.f, hpp = 0.f, hrr = 0.f, hyp = 0.f, hyr = 0.f, hpr = 0.f;
+#pragma unroll 1
+    for (int b = 0; b < nB; ++b) {
+        const float y0 = scr[(3 * b + 0) * sstride], y1 = scr[(3 * b + 1) * sstride], y2 = scr[(3 * b + 2) * sstride];
+#pragma unroll 1
+        for (int c = 0; c < nC; ++c) {
+            const float p0 = scr[(3 * nB + 3 * c + 0) * sstride], p1 = scr[(3 * nB + 3 * c + 1) * sstride],
+                        p2 = scr[(3 * nB + 3 * c + 2) * sstride];
+            const float m00 = y0 * p0, m10 = y1 * p0, m01 = y0 * p1, m20 = y2 * p0, m02 = y0 * p2, m11 = y1 * p1;
+            const float* __restrict__ rows = S + (b * nC + c) * (nD * NAP);
+#pragma unroll
+            for (int d = 0; d < nD; ++d) {
+                const float* __restrict__ row = rows + d * NAP;
+                const float w00 = m00 * R0[d], wy = m10 * R0[d], wp = m01 * R0[d], wr = m00 * R1[d];
+                float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                for (int a = 0; a < nA; ++a) {
+                    const float sv = row[a];
+                    if (a % 3 == 0) t0 = fmaf(sv, UU[a], t0);
+                    else if (a % 3 == 1) t1 = fmaf(sv, UU[a], t1);
+                    else t2 = fmaf(sv, UU[a], t2);
+                    GU[a] = fmaf(sv, w00, GU[a]);
+                    HY[a] = fmaf(sv, wy, HY[a]);
+                    HP[a] = fmaf(sv, wp, HP[a]);
+                    HR[a] = fmaf(sv, wr, HR[a]);
+                }
+                const float t = (t0 + t1) + t2;
+                F2 = fmaf(t, w00, F2);
+                gy = fmaf(t, wy, gy);
+                gp = fmaf(t, wp, gp);
+                gr = fmaf(t, wr, gr);
+                hyy = fmaf(t, m20 * R0[d], hyy);
+                hpp = fmaf(t, m02 * R0[d], hpp);
+                hrr = fmaf(t, m00 * R2[d], hrr);
+                hyp = fmaf(t, m11 * R0[d], hyp);
+                hyr = fmaf(t, m10 * R1[d], hyr);
+                hpr = fmaf(t, m01 * R1[d], hpr);
+            }
+        }
+    }
+
+    // ---- linear term F1 = -sum q[ijkl] u_i cy_j cp_k cr_l and its derivatives ----
+    float kl0[RP * RR], klp[RP * RR], klr[RP * RR], klpp[RP * RR], klrr[RP * RR], klpr[RP * RR];
+#pragma unroll
+    for (int k = 0; k < RP; ++k)
+#pragma unroll
+        for (int l = 0; l < RR; ++l) {
+            kl0[k * RR + l] = cp[k] * cr[l];
+            klp[k * RR + l] = dcp[k] * cr[l];
+            klr[k * RR + l] = cp[k] * dcr[l];
+            klpp[k * RR + l] = d2cp[k] * cr[l];
+            klrr[k * RR + l] = cp[k] * d2cr[l];
+            klpr[k * RR + l] = dcp[k] * dcr[l];
+        }
+    float F1 = 0.f, A0[RI], Ay[RI], Ap[RI], Ar[RI];
+#pragma unroll
+    for (int i = 0; i < RI; ++i) {
+        float a0 = 0.f, ay = 0.f, ap = 0.f, ar = 0.f, byy = 0.f, bpp = 0.f, brr = 0.f, byp = 0.f, byr = 0.f, bpr = 0.f;
+#pragma unroll
+        for (int j = 0; j < RY; ++j) {
+            float s0 = 0.f, sp = 0.f, sr = 0.f, spp = 0.f, srr = 0.f, spr = 0.f;
+#pragma unroll
+            for (int kl = 0; kl < RP * RR; ++kl) {
+                const float qv = q[((i * RY + j) * RP * RR + kl) * qstride];
+                s0 = fmaf(qv, kl0[kl], s0);
+                sp = fmaf(qv, klp[kl], sp);
+                sr = fmaf(qv, klr[kl], sr);
+                spp = fmaf(qv, klpp[kl], spp);
+                srr = fmaf(qv, klrr[kl], srr);
+                spr = fmaf(qv, klpr[kl], spr);
+            }
+            a0 = fmaf(cy[j], s0, a0);
+            ay = fmaf(dcy[j], s0, ay);
+            ap = fmaf(cy[j], sp, ap);
+            ar = fmaf(cy[j], sr, ar);
+            byy = fmaf(d2cy[j], s0, byy);
+            bpp = fmaf(cy[j], spp, bpp);
+            brr = fmaf(cy[j], srr, brr);
+            byp = fmaf(dcy[j], sp, byp);
+            byr = fmaf(dcy[j], sr, byr);
+            bpr = fmaf(cy[j], spr, bpr);
+        }
+        A0[i] = a0; Ay[i] = ay; Ap[i] = ap; Ar[i] = ar;
+        F1 = fmaf(-u[i], a0, F1);
+        gy = fmaf(-u[i], ay, gy);
+        gp = fmaf(-u[i], ap, gp);
+        gr = fmaf(-u[i], ar, gr);
+        hyy = fmaf(-u[i], byy, hyy);
+        hpp = fmaf(-u[i], bpp, hpp);
+        hrr = fmaf(-u[i], brr, hrr);
+        hyp = fmaf(-u[i], byp, hyp);
+        hyr = fmaf(-u[i], byr, hyr);
+        hpr = fmaf(-u[i], bpr, hpr);
+    }
+
+    // ---- assemble ----
+    Lval = F1 + F2;
+    g[0] = gy; g[1] = gp; g[2] = gr;
+    H[tri_index(0, 0)] = hyy; H[tri_index(1, 1)] = hpp; H[tri_index(2, 2)] = hrr;
+    H[tri_index(1, 0)] = hyp; H[tri_index(2, 0)] = hyr; H[tri_index(2, 1)] = hpr;
+    float du[RI], duy[RI], dup[RI], dur[RI];
+    sym_backprop<RI>(GU, u, du);
+    sym_backprop<RI>(HY, u, duy);
+    sym_backprop<RI>(HP, u, dup);
+    sym_backprop<RI>(HR, u, dur);
+#pragma unroll
+    for (int m = 0; m < RI; ++m) {
+        g[3 + m] = du[m] - A0[m];
+        H[tri_index(3 + m, 0)] = duy[m] - Ay[m];
+        H[tri_index(3 + m, 1)] = dup[m] - Ap[m];
+        H[tri_index(3 + m, 2)] = dur[m] - Ar[m];
+#pragma unroll
+        for (int n = 0; n <= m; ++n)
+            H[tri_index(3 + m, 3 + n)] = (m == n) ? 2.0f * GU[pair_index(m, m, RI)] : GU[pair_index(n, m, RI)];
+    }
+}
+
+// Solve A d = g for a packed symmetric positive-definite A by Cholesky; false when a pivot is not positive.
+template <int NP>
+NLML_HD bool chol_solve(const float (&A)[NP * (NP + 1) / 2], const float (&g)[NP], float (&d)[NP]) {
+    float Lm[NP * (NP + 1) / 2];
+    bool ok = true;
+#pragma unroll
+    for (int r = 0; r < NP; ++r) {
+#pragma unroll
+        for (int c = 0; c <= r; ++c) {
+            float acc = A[tri_index(r, c)];
+#pragma unroll
+            for (int k = 0; k < c; ++k) acc = fmaf(-Lm[tri_index(r, k)], Lm[tri_index(c, k)], acc);
+            if (c == r) {
+                ok = ok && (acc > 0.f);
+                Lm[tri_index(r, r)] = sqrtf(acc > 0.f ? acc : 1.0f);
+            } else {
+                Lm[tri_index(r, c)] = acc / Lm[tri_index(c, c)];
+            }
+        }
+    }
+    float y[NP];
+#pragma unroll
+    for (int r = 0; r < NP; ++r) {
+        float acc = g[r];
+#pragma unroll
+        for (int k = 0; k < r; ++k) acc = fmaf(-Lm[tri_index(r, k)], y[k], acc);
+        y[r] = acc / Lm[tri_index(r, r)];
+    }
+#pragma unroll
+    for (int r = NP - 1; r >= 0; --r) {
+        float acc = y[r];
+#pragma unroll
+        for (int k = r + 1; k < NP; ++k) acc = fmaf(-Lm[tri_index(k, r)], d[k], acc);
+        d[r] = acc / Lm[tri_index(r, r)];
+    }
+    return ok;
+}
+
+struct LmOptions {
+    int max_evals;      // objective/gradient/Hessian evaluations per sample (the unit of work)
+    float lambda0;      // initial damping (Marquardt scaling: A = H + lambda * diag(|H_ii|))
+    float lambda_down;  // damping divisor after an accepted, uncapped step
+    float lambda_up;    // damping multiplier after a rejected step or a failed factorisation
+    float angle_cap;    // largest angle change per step (rad): keeps the search in the basin reached from p = 0
+    float step_tol;     // stop when max |delta p| falls below this
+    float diag_floor;   // added to |H_ii| in the damping term (at p = 0 the angle block of H is exactly zero)
+    float noise_step;   // FP32 floor: on ill-conditioned samples the Newton step itself becomes rounding noise
+                        // (up to ~1e-4 rad); stop after two accepted steps below this that no longer contract
+};
+NLML_HD LmOptions lm_default_options() { return LmOptions{64, 1e-3f, 10.f, 4.f, 0.15f, 2e-6f, 1.0f, 3e-4f}; }
+
+// From p = 0 (TD_Tester.py:164) to the local minimum.  Returns the number of evaluations used.
+template <int RI, int RY, int RP, int RR, int NAP>
+NLML_HD int tucker_lm_solve(const float* __restrict__ S, const float* __restrict__ q, int qstride, float* scr, int sstride,
+                            const float* rows_y, const float* rows_p, const float* rows_r, const LmOptions& o,
+                            float (&p)[3 + RI], float& Lfinal) {
+    constexpr int NP = 3 + RI, NH = NP * (NP + 1) / 2;
+    float L, g[NP], H[NH];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) p[i] = 0.f;
+    tucker_newton_eval<RI, RY, RP, RR, NAP>(p, S, q, qstride, scr, sstride, rows_y, rows_p, rows_r, L, g, H);
+    int evals = 1;
+    float lam = o.lambda0;
+    int guard = 4 * o.max_evals;   // failed factorisations do not consume evaluations
+    int flat = 0;                  // consecutive small accepted steps that did not contract
+    float prev_step = 1e30f;
+    while (evals < o.max_evals && guard-- > 0) {
+        float A[NH], d[NP];
+#pragma unroll
+        for (int i = 0; i < NH; ++i) A[i] = H[i];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) A[tri_index(i, i)] += lam * (fabsf(H[tri_index(i, i)]) + o.diag_floor);
+        if (!chol_solve<NP>(A, g, d)) {
+            lam *= o.lambda_up;
+            if (lam > 1e12f) break;
+            continue;
+        }
+        float ma = fmaxf(fabsf(d[0]), fmaxf(fabsf(d[1]), fabsf(d[2])));
+        const bool capped = ma > o.angle_cap;
+        const float scale = capped ? o.angle_cap / ma : 1.0f;
+        float step = 0.f, pn[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            const float di = scale * d[i];
+            step = fmaxf(step, fabsf(di));
+            pn[i] = p[i] - di;
+        }
+        if (step < o.step_tol && lam < 1.0f) {   // converged: a (nearly) undamped correction below the tolerance; take it unevaluated
+#pragma unroll
+            for (int i = 0; i < NP; ++i) p[i] = pn[i];
+            break;
+        }
+        float Ln, gn[NP], Hn[NH];
+        tucker_newton_eval<RI, RY, RP, RR, NAP>(pn, S, q, qstride, scr, sstride, rows_y, rows_p, rows_r, Ln, gn, Hn);
+        ++evals;
+        // FP32 resolution of L (|F1 + F2| ~ 0.5 |x_hat|^2): differences below it carry no information
+        const float resolution = 2e-6f * (1.0f + fabsf(L));
+        if (Ln <= L + resolution) {
+            flat = (step < o.noise_step && step > 0.5f * prev_step && lam < 1.0f) ? flat + 1 : 0;
+            prev_step = step;
+            const bool stalled = flat >= 2;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) { p[i] = pn[i]; g[i] = gn[i]; }
+#pragma unroll
+            for (int i = 0; i < NH; ++i) H[i] = Hn[i];
+            L = Ln;
+            if (stalled) break;
+            if (!capped) lam = fmaxf(lam / o.lambda_down, 1e-9f);
+        } else {
+            lam *= o.lambda_up;
+            if (lam > 1e12f) break;
+        }
+    }
+    Lfinal = L;
+    return evals;
+}
+
 // ---- one-time constant preparation (per Tucker core), identical on host and device ----
 
 // One entry of M = W2 W2^T in double.

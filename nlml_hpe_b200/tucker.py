@@ -98,6 +98,45 @@ class TuckerFitter:
                                                  KERNEL_HINTS[kernel], stream))
         return out
 
+    def solve(self, X, max_evals=0, return_evals=False, out=None):
+        """Converged fit (what TD_Tester.Test computes with scipy Powell, TD_Tester.py:191-199): damped Newton
+        from p = 0 to the local minimum, one thread per sample.  X as in fit().  Returns [N, 3+R_id]
+        (radians + identity coefficients) and, with return_evals, the int32 [N] evaluations used.
+        Ranks (5,3,3,3) only.  Asynchronous on the current stream."""
+        if not (isinstance(X, torch.Tensor) and X.is_cuda):
+            raise TypeError("solve() takes a CUDA tensor; use solve_host() for numpy / CPU tensors")
+        if X.dtype != torch.float32 or X.dim() != 2 or X.shape[1] < self.F:
+            raise ValueError(f"X must be float32 [N, >={self.F}], got {X.dtype} {tuple(X.shape)}")
+        if X.device.index != self.device_index:
+            raise ValueError(f"X is on {X.device}, plan is on {self.device}")
+        if X.shape[0] > 0 and X.stride(1) != 1:
+            X = X.contiguous()
+        n = X.shape[0]
+        if out is None:
+            out = torch.empty((n, self.n_params), dtype=torch.float32, device=X.device)
+        evals = torch.zeros((n,), dtype=torch.int32, device=X.device) if return_evals else None
+        stream = torch.cuda.current_stream(X.device).cuda_stream
+        ldx = X.stride(0) if n > 1 else max(X.shape[1], self.F)
+        _lib.check(self._lib.nlml_tucker_solve_f32(self._h, X.data_ptr(), n, ldx, int(max_evals), out.data_ptr(),
+                                                   out.stride(0) if n > 1 else self.n_params,
+                                                   evals.data_ptr() if return_evals and n > 0 else None, stream))
+        return (out, evals) if return_evals else out
+
+    def solve_host(self, X, max_evals=0, out=None):
+        """solve() for numpy / CPU float32 [N, F] in host memory; pipelined like fit_host()."""
+        if isinstance(X, torch.Tensor):
+            X = X.detach().numpy()
+        X = np.asarray(X)
+        if X.dtype != np.float32 or X.ndim != 2 or X.shape[1] < self.F or (X.size and X.strides[1] != 4):
+            raise ValueError(f"X must be float32 [N, >={self.F}] with unit column stride")
+        n = X.shape[0]
+        if out is None:
+            out = np.empty((n, self.n_params), dtype=np.float32)
+        ldx = X.strides[0] // 4 if n > 1 else X.shape[1]
+        _lib.check(self._lib.nlml_tucker_solve_host_f32(self._h, X.ctypes.data, n, ldx, int(max_evals),
+                                                        out.ctypes.data, self.n_params))
+        return out
+
     def fit_host(self, X, iters=3000, lr=1e-3, clip=1.0, out=None):
         """X: numpy / CPU tensor float32 [N, F] in host memory (pinned memory makes the copies
         asynchronous).  Host->device copy, fit and device->host copy are pipelined inside the

@@ -19,6 +19,8 @@ What is restated (all file:line into /root/reference):
   sgd_batched           the same recurrence with the gradient of :110-125 written out by hand
                         (NOT TD_Tester.compute_gradient, whose u_id part :97 is wrong and dead)
   powell_fit            TD_Tester.py:162-199 (Test) with the objective of :31-58
+  newton_terms, lm_fit  float64 checker of the converged solver: same objective
+                        (:110-125), same start (:164); compared with Powell at the optimum only
 """
 from __future__ import annotations
 
@@ -133,3 +135,78 @@ def powell_fit(W, x, rows_y, rows_p, rows_r):
 
     res = minimize(f, np.zeros(3 + W.shape[0]), method="Powell")
     return np.degrees(res.x[:3]), res.x[3:]
+
+
+def _objective_f64(p, W2, x, rows):
+    """TD_Tester.py:110-125 in float64 for one sample (functional form, for torch.func)."""
+    fs = [r[:, 0] * torch.cos(r[:, 1] * p[k] + r[:, 2]) + r[:, 3] for k, r in enumerate(rows)]
+    z = torch.einsum("i,j,k,l->ijkl", p[3:], *fs).reshape(-1)
+    res = x - z @ W2
+    return 0.5 * (res * res).sum()
+
+
+def newton_terms(P, W, X, rows_y, rows_p, rows_r):
+    """Loss, gradient and exact Hessian of the objective (TD_Tester.py:110-125) at P, float64, batched
+    (torch.func).  P [N,3+R_id], X [N,F] -> L [N], G [N,NP], H [N,NP,NP]."""
+    W = torch.as_tensor(np.asarray(W), dtype=torch.float64)
+    W2 = W.reshape(-1, W.shape[-1])
+    rows = [torch.as_tensor(np.asarray(r), dtype=torch.float64) for r in (rows_y, rows_p, rows_r)]
+    P = torch.as_tensor(np.asarray(P), dtype=torch.float64)
+    X = torch.as_tensor(np.asarray(X), dtype=torch.float64)
+    f = lambda p, x: _objective_f64(p, W2, x, rows)
+    L = torch.func.vmap(f)(P, X)
+    G = torch.func.vmap(torch.func.grad(f))(P, X)
+    H = torch.func.vmap(torch.func.hessian(f))(P, X)
+    return L.numpy(), G.numpy(), H.numpy()
+
+
+def lm_fit(W, X, rows_y, rows_p, rows_r, max_evals=200, lambda0=1e-3, down=10.0, up=4.0, angle_cap=0.15,
+           step_tol=1e-10, diag_floor=1.0):
+    """Converged fit: float64 restatement of csrc/tucker_math.h tucker_lm_solve (damped Newton with the exact
+    Hessian, Marquardt scaling, capped angle step, from p = 0 as TD_Tester.py:164).  parity unpinned against the
+    reference's scipy Powell search (TD_Tester.py:191-194): same objective, same start, compared at the optimum.
+    Returns P f64 [N,3+R_id], final loss [N], evaluations [N]."""
+    X = np.asarray(X, dtype=np.float64)
+    n, NP = X.shape[0], 3 + np.asarray(W).shape[0]
+    P = np.zeros((n, NP))
+    L, G, H = newton_terms(P, W, X, rows_y, rows_p, rows_r)
+    lam = np.full(n, lambda0)
+    active = np.ones(n, bool)
+    evals = np.ones(n, int)
+    eye = np.eye(NP)
+    for _ in range(4 * max_evals):
+        idx = np.nonzero(active)[0]
+        if idx.size == 0:
+            break
+        diag = np.abs(np.einsum("nii->ni", H[idx])) + diag_floor
+        A = H[idx] + lam[idx, None, None] * diag[:, :, None] * eye
+        ok = np.all(np.linalg.eigvalsh(A) > 0, axis=1)
+        lam[idx[~ok]] *= up
+        active[idx[~ok][lam[idx[~ok]] > 1e12]] = False
+        idx, A = idx[ok], A[ok]
+        if idx.size == 0:
+            continue
+        D = np.linalg.solve(A, G[idx][:, :, None])[:, :, 0]
+        ma = np.abs(D[:, :3]).max(1)
+        capped = ma > angle_cap
+        D = D * np.where(capped, angle_cap / np.maximum(ma, 1e-300), 1.0)[:, None]
+        step = np.abs(D).max(1)
+        Pn = P[idx] - D
+        done = (step < step_tol) & (lam[idx] < 1.0)
+        P[idx[done]] = Pn[done]
+        active[idx[done]] = False
+        idx, Pn, capped = idx[~done], Pn[~done], capped[~done]
+        if idx.size == 0:
+            continue
+        Ln, Gn, Hn = newton_terms(Pn, W, X[idx], rows_y, rows_p, rows_r)
+        evals[idx] += 1
+        acc = Ln <= L[idx]
+        a = idx[acc]
+        P[a], L[a], G[a], H[a] = Pn[acc], Ln[acc], Gn[acc], Hn[acc]
+        dn = a[~capped[acc]]
+        lam[dn] = np.maximum(lam[dn] / down, 1e-9)
+        rj = idx[~acc]
+        lam[rj] *= up
+        active[rj[lam[rj] > 1e12]] = False
+        active[evals >= max_evals] = False
+    return P, L, evals

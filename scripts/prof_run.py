@@ -2,6 +2,7 @@
 
   python scripts/prof_run.py tucker --n 37888 --iters 300 [--kernel thread_per_sample]
   python scripts/prof_run.py mlp --n 65536
+  python scripts/prof_run.py solve --n 1000000
 Prints CUDA-event timings; run once plain, then under ncu with the same arguments.
 """
 import argparse
@@ -35,7 +36,7 @@ def timed(fn, reps):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["tucker", "mlp"])
+    ap.add_argument("what", choices=["tucker", "mlp", "solve"])
     ap.add_argument("--n", type=int, default=37888)
     ap.add_argument("--iters", type=int, default=300)
     ap.add_argument("--kernel", default="thread_per_sample")
@@ -49,6 +50,15 @@ def main():
         best = min(ms)
         print(f"tucker {a.kernel} n={a.n} T={a.iters}: ms={['%.3f' % m for m in ms]}  "
               f"{a.n / best * 1e3:.0f} poses/s  {a.n * a.iters / best * 1e3 / 1e9:.3f} G sample-iters/s")
+    elif a.what == "solve":
+        fit = TuckerFitter(art["W"], *rows, device="cuda:0")
+        ms = timed(lambda: fit.solve(X), a.reps)
+        best = min(ms)
+        _, ev = fit.solve(X, return_evals=True)
+        ev = ev.cpu().numpy()
+        wmax = ev[: len(ev) // 32 * 32].reshape(-1, 32).max(1)
+        print(f"solve n={a.n}: ms={['%.3f' % m for m in ms]}  {a.n / best * 1e3:.0f} poses/s  evals mean {ev.mean():.2f} "
+              f"max {ev.max()}  per-warp max mean {wmax.mean():.2f}")
     else:
         model = MB.build_combined_model(*bench.state_dicts(art))
         ms = timed(lambda: model.predict(X), a.reps)

@@ -86,3 +86,76 @@ extern "C" int hostcheck_tucker_grad_5333(const float* W2, int F, const double* 
 extern "C" void hostcheck_sincos_small(const float* x, int64_t n, float* sn, float* cs) {
     for (int64_t i = 0; i < n; ++i) nlml::sincos_small(x[i], sn + i, cs + i);
 }
+
+namespace {
+struct Prepared5333 {
+    static constexpr int RI = 5, RY = 3, RP = 3, RR = 3, R = RI * RY * RP * RR, NP = 3 + RI;
+    static constexpr int nA = tri(RI), NAP = (nA + 3) / 4 * 4, nBCD = tri(RY) * tri(RP) * tri(RR);
+    std::vector<float> S;
+    float ry[12], rp[12], rr[12];
+    Prepared5333(const float* W2, int F, const double* rows_y, const double* rows_p, const double* rows_r)
+        : S((size_t)nBCD * NAP, 0.f) {
+        std::vector<double> M((size_t)R * R);
+        for (int r = 0; r < R; ++r)
+            for (int c = r; c < R; ++c) M[(size_t)r * R + c] = M[(size_t)c * R + r] = gram_entry(W2, F, r, c);
+        for (int a = 0; a < nA; ++a)
+            for (int b = 0; b < tri(RY); ++b)
+                for (int c = 0; c < tri(RP); ++c)
+                    for (int d = 0; d < tri(RR); ++d)
+                        S[(size_t)((b * tri(RP) + c) * tri(RR) + d) * NAP + a] = fold_entry(M.data(), RI, RY, RP, RR, a, b, c, d);
+        for (int i = 0; i < 12; ++i) { ry[i] = (float)rows_y[i]; rp[i] = (float)rows_p[i]; rr[i] = (float)rows_r[i]; }
+    }
+    static void project(const float* W2, int F, const float* x, float* q) {
+        for (int r = 0; r < R; ++r) {
+            float acc = 0.f;
+            for (int f = 0; f < F; ++f) acc = fmaf(W2[(size_t)r * F + f], x[f], acc);
+            q[r] = acc;
+        }
+    }
+};
+}  // namespace
+
+// value (without 0.5 x.x), gradient and packed lower-triangular Hessian at given points (tucker_newton_eval)
+extern "C" int hostcheck_tucker_newton_5333(const float* W2, int F, const double* rows_y, const double* rows_p,
+                                            const double* rows_r, const float* X, int64_t N, int64_t ldx,
+                                            const float* Pin /*[N][8]*/, float* L /*[N]*/, float* G /*[N][8]*/,
+                                            float* H /*[N][36]*/) {
+    using C = Prepared5333;
+    C pre(W2, F, rows_y, rows_p, rows_r);
+    for (int64_t s = 0; s < N; ++s) {
+        float q[C::R], scr[3 * (tri(C::RY) + tri(C::RP))];
+        C::project(W2, F, X + s * ldx, q);
+        float p[C::NP], g[C::NP], h[C::NP * (C::NP + 1) / 2], l;
+        for (int i = 0; i < C::NP; ++i) p[i] = Pin[s * C::NP + i];
+        tucker_newton_eval<C::RI, C::RY, C::RP, C::RR, C::NAP>(p, pre.S.data(), q, 1, scr, 1, pre.ry, pre.rp, pre.rr, l, g, h);
+        L[s] = l;
+        for (int i = 0; i < C::NP; ++i) G[s * C::NP + i] = g[i];
+        for (int i = 0; i < 36; ++i) H[s * 36 + i] = h[i];
+    }
+    return 0;
+}
+
+// converged fit (tucker_lm_solve) from p = 0
+extern "C" int hostcheck_tucker_solve_5333(const float* W2, int F, const double* rows_y, const double* rows_p,
+                                           const double* rows_r, const float* X, int64_t N, int64_t ldx,
+                                           int max_evals, float* P /*[N][8]*/, int* evals /*[N]*/,
+                                           const float* opts /*optional [7]: lambda0, down, up, cap, tol, floor, noise_step*/,
+                                           float* Lout /*optional [N]*/) {
+    using C = Prepared5333;
+    C pre(W2, F, rows_y, rows_p, rows_r);
+    LmOptions o = lm_default_options();
+    if (max_evals > 0) o.max_evals = max_evals;
+    if (opts) {
+        o.lambda0 = opts[0]; o.lambda_down = opts[1]; o.lambda_up = opts[2]; o.angle_cap = opts[3];
+        o.step_tol = opts[4]; o.diag_floor = opts[5]; o.noise_step = opts[6];
+    }
+    for (int64_t s = 0; s < N; ++s) {
+        float q[C::R], scr[3 * (tri(C::RY) + tri(C::RP))];
+        C::project(W2, F, X + s * ldx, q);
+        float p[C::NP], l;
+        evals[s] = tucker_lm_solve<C::RI, C::RY, C::RP, C::RR, C::NAP>(pre.S.data(), q, 1, scr, 1, pre.ry, pre.rp, pre.rr, o, p, l);
+        for (int i = 0; i < C::NP; ++i) P[s * C::NP + i] = p[i];
+        if (Lout) Lout[s] = l;
+    }
+    return 0;
+}
