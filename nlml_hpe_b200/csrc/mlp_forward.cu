@@ -12,6 +12,7 @@
 // head layer.  The batch is processed in chunks whose activations stay L2-resident.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -214,6 +215,7 @@ struct nlml_mlp_plan {
     cudaStream_t streams[2] = {nullptr, nullptr};
     float* x_dev[2] = {nullptr, nullptr};
     float* y_dev[2] = {nullptr, nullptr};
+    float* y_stage[2] = {nullptr, nullptr};   // pinned result staging (see nlml_mlp_forward_host_f32)
     int64_t host_rows = 0;   // capacity of x_dev / y_dev
 };
 
@@ -575,6 +577,7 @@ extern "C" void nlml_mlp_plan_destroy(nlml_mlp_plan* pl) {
         if (pl->streams[i]) cudaStreamDestroy(pl->streams[i]);
         cudaFree(pl->x_dev[i]);
         cudaFree(pl->y_dev[i]);
+        if (pl->y_stage[i]) cudaFreeHost(pl->y_stage[i]);
         free_workspace(pl->ws[i]);
     }
     delete pl;
@@ -615,6 +618,8 @@ extern "C" int nlml_mlp_forward_host_f32(nlml_mlp_plan* pl, const float* X_host,
         if (pl->host_rows) NLML_CUDA(cudaDeviceSynchronize());
         for (int i = 0; i < 2; ++i) {
             cudaFree(pl->x_dev[i]); cudaFree(pl->y_dev[i]);
+            if (pl->y_stage[i]) cudaFreeHost(pl->y_stage[i]);
+            NLML_CUDA(cudaMallocHost(&pl->y_stage[i], sizeof(float) * want * 3));
             NLML_CUDA(cudaMalloc(&pl->x_dev[i], sizeof(float) * want * F));
             NLML_CUDA(cudaMalloc(&pl->y_dev[i], sizeof(float) * want * 3));
         }
@@ -622,20 +627,33 @@ extern "C" int nlml_mlp_forward_host_f32(nlml_mlp_plan* pl, const float* X_host,
     }
     for (int i = 0; i < 2; ++i)
         if (int rc = ensure_workspace(pl, pl->ws[i], N)) return rc;
+    // results go to pinned staging: a D2H copy into pageable user memory would block the host thread until the
+    // chunk's kernels are done, so the next chunk's H2D copy could not overlap them
+    struct Pending { int64_t s0 = 0, n = 0; } pending[2];
+    auto drain = [&](int slot) -> int {
+        if (!pending[slot].n) return 0;
+        NLML_CUDA(cudaStreamSynchronize(pl->streams[slot]));
+        std::memcpy(YPR_out_host + pending[slot].s0 * 3, pl->y_stage[slot], sizeof(float) * 3 * pending[slot].n);
+        pending[slot].n = 0;
+        return 0;
+    };
     int slot = 0;
     for (int64_t s0 = 0; s0 < N; s0 += pl->chunk, slot ^= 1) {
         const int64_t n = std::min<int64_t>(pl->chunk, N - s0);
         cudaStream_t st = pl->streams[slot];
+        if (int rc = drain(slot)) return rc;
         if (ldx == F)   // contiguous rows: one linear DMA instead of a pitched copy
             NLML_CUDA(cudaMemcpyAsync(pl->x_dev[slot], X_host + s0 * ldx, sizeof(float) * F * n, cudaMemcpyHostToDevice, st));
         else
             NLML_CUDA(cudaMemcpy2DAsync(pl->x_dev[slot], sizeof(float) * F, X_host + s0 * ldx, sizeof(float) * ldx,
                                         sizeof(float) * F, (size_t)n, cudaMemcpyHostToDevice, st));
         if (int rc = forward_chunk(pl, pl->x_dev[slot], n, F, pl->y_dev[slot], nullptr, pl->ws[slot], st)) return rc;
-        NLML_CUDA(cudaMemcpyAsync(YPR_out_host + s0 * 3, pl->y_dev[slot], sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
+        NLML_CUDA(cudaMemcpyAsync(pl->y_stage[slot], pl->y_dev[slot], sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
+        pending[slot].s0 = s0;
+        pending[slot].n = n;
     }
-    NLML_CUDA(cudaStreamSynchronize(pl->streams[0]));
-    NLML_CUDA(cudaStreamSynchronize(pl->streams[1]));
+    if (int rc = drain(slot)) return rc;
+    if (int rc = drain(slot ^ 1)) return rc;
     return 0;
 }
 

@@ -14,6 +14,7 @@
 //                          the 3000-step chain matters more than throughput.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -1147,7 +1148,10 @@ struct nlml_tucker_plan {
     cudaStream_t streams[2] = {nullptr, nullptr};
     float* x_dev[2] = {nullptr, nullptr};
     float* p_dev[2] = {nullptr, nullptr};
+    float* p_stage[2] = {nullptr, nullptr};   // pinned: a D2H copy into pageable user memory would block the host
+                                              // thread until the chunk's kernel is done and serialise the pipeline
     int64_t chunk = 0;
+    int64_t host_rows = 0;   // capacity of x_dev / p_dev / p_stage
 };
 
 namespace {
@@ -1241,31 +1245,55 @@ int host_pipeline(nlml_tucker_plan* pl, const float* X_host, int64_t N, int64_t 
     const int np = 3 + pl->ri;
     if (!pl->streams[0]) {
         pl->chunk = (int64_t)pl->num_sms * TcFitCfg::THREADS * 8;   // 8 waves of the tensor-core kernel per chunk
-        for (int i = 0; i < 2; ++i) {
-            NLML_CUDA(cudaStreamCreateWithFlags(&pl->streams[i], cudaStreamNonBlocking));
-            NLML_CUDA(cudaMalloc(&pl->x_dev[i], sizeof(float) * (size_t)pl->chunk * pl->F));
-            NLML_CUDA(cudaMalloc(&pl->p_dev[i], sizeof(float) * (size_t)pl->chunk * np));
-        }
+        for (int i = 0; i < 2; ++i) NLML_CUDA(cudaStreamCreateWithFlags(&pl->streams[i], cudaStreamNonBlocking));
     }
+    // staging grows to the largest chunk seen (single-sample calls through TD_Tester.Test stay small)
+    const int64_t want = std::min<int64_t>(pl->chunk, ceil_div(std::max<int64_t>(N, 1), 128) * 128);
+    if (pl->host_rows < want) {
+        if (pl->host_rows) NLML_CUDA(cudaDeviceSynchronize());
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(pl->x_dev[i]);
+            cudaFree(pl->p_dev[i]);
+            if (pl->p_stage[i]) cudaFreeHost(pl->p_stage[i]);
+            pl->x_dev[i] = pl->p_dev[i] = pl->p_stage[i] = nullptr;
+            NLML_CUDA(cudaMalloc(&pl->x_dev[i], sizeof(float) * (size_t)want * pl->F));
+            NLML_CUDA(cudaMalloc(&pl->p_dev[i], sizeof(float) * (size_t)want * np));
+            NLML_CUDA(cudaMallocHost(&pl->p_stage[i], sizeof(float) * (size_t)want * np));
+        }
+        pl->host_rows = want;
+    }
+    // results land in pinned staging and are handed to the caller's buffer when the slot comes round again
+    struct Pending { int64_t s0 = 0, n = 0; } pending[2];
+    auto drain = [&](int slot) -> int {
+        if (!pending[slot].n) return 0;
+        NLML_CUDA(cudaStreamSynchronize(pl->streams[slot]));
+        const float* src = pl->p_stage[slot];
+        float* dst = P_out_host + pending[slot].s0 * ldp;
+        if (ldp == np) {
+            std::memcpy(dst, src, sizeof(float) * np * pending[slot].n);
+        } else {
+            for (int64_t r = 0; r < pending[slot].n; ++r) std::memcpy(dst + r * ldp, src + r * np, sizeof(float) * np);
+        }
+        pending[slot].n = 0;
+        return 0;
+    };
     int slot = 0;
     for (int64_t s0 = 0; s0 < N; s0 += pl->chunk, slot ^= 1) {
         const int64_t n = std::min<int64_t>(pl->chunk, N - s0);
         cudaStream_t st = pl->streams[slot];
-        // stream order makes the reuse of this slot's buffers safe (previous chunk on the same stream is done)
+        if (int rc = drain(slot)) return rc;   // also makes the reuse of this slot's device buffers safe
         if (ldx == pl->F)   // contiguous rows: one linear DMA instead of a pitched copy
             NLML_CUDA(cudaMemcpyAsync(pl->x_dev[slot], X_host + s0 * ldx, sizeof(float) * pl->F * n, cudaMemcpyHostToDevice, st));
         else
             NLML_CUDA(cudaMemcpy2DAsync(pl->x_dev[slot], sizeof(float) * pl->F, X_host + s0 * ldx, sizeof(float) * ldx,
                                         sizeof(float) * pl->F, (size_t)n, cudaMemcpyHostToDevice, st));
         if (int rc = launch(pl->x_dev[slot], n, pl->p_dev[slot], st)) return rc;
-        if (ldp == np)
-            NLML_CUDA(cudaMemcpyAsync(P_out_host + s0 * ldp, pl->p_dev[slot], sizeof(float) * np * n, cudaMemcpyDeviceToHost, st));
-        else
-            NLML_CUDA(cudaMemcpy2DAsync(P_out_host + s0 * ldp, sizeof(float) * ldp, pl->p_dev[slot], sizeof(float) * np,
-                                        sizeof(float) * np, (size_t)n, cudaMemcpyDeviceToHost, st));
+        NLML_CUDA(cudaMemcpyAsync(pl->p_stage[slot], pl->p_dev[slot], sizeof(float) * np * n, cudaMemcpyDeviceToHost, st));
+        pending[slot].s0 = s0;
+        pending[slot].n = n;
     }
-    NLML_CUDA(cudaStreamSynchronize(pl->streams[0]));
-    NLML_CUDA(cudaStreamSynchronize(pl->streams[1]));
+    if (int rc = drain(slot)) return rc;        // older chunk first
+    if (int rc = drain(slot ^ 1)) return rc;
     return 0;
 }
 }  // namespace
@@ -1366,6 +1394,7 @@ extern "C" void nlml_tucker_plan_destroy(nlml_tucker_plan* pl) {
         if (pl->streams[i]) cudaStreamDestroy(pl->streams[i]);
         cudaFree(pl->x_dev[i]);
         cudaFree(pl->p_dev[i]);
+        if (pl->p_stage[i]) cudaFreeHost(pl->p_stage[i]);
     }
     cudaFree(pl->W2);
     cudaFree(pl->S);

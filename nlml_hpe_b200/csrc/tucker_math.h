@@ -604,10 +604,12 @@ struct LmOptions {
     float angle_cap;    // largest angle change per step (rad): keeps the search in the basin reached from p = 0
     float step_tol;     // stop when max |delta p| falls below this
     float diag_floor;   // added to |H_ii| in the damping term (at p = 0 the angle block of H is exactly zero)
+    float lambda_min;   // damping floor: a smaller floor buys nothing (the step is already Newton's) and costs one
+                        // rejected evaluation per factor lambda_up when a step overshoots in the curved valley
     float noise_step;   // FP32 floor: on ill-conditioned samples the Newton step itself becomes rounding noise
                         // (up to ~1e-4 rad); stop after two accepted steps below this that no longer contract
 };
-NLML_HD LmOptions lm_default_options() { return LmOptions{64, 1e-3f, 10.f, 4.f, 0.15f, 2e-6f, 1.0f, 3e-4f}; }
+NLML_HD LmOptions lm_default_options() { return LmOptions{64, 1e-3f, 5.f, 4.f, 0.15f, 2e-6f, 1.0f, 1e-5f, 3e-4f}; }
 
 // From p = 0 (TD_Tester.py:164) to the local minimum.  Returns the number of evaluations used.
 template <int RI, int RY, int RP, int RR, int NAP>
@@ -665,7 +667,7 @@ NLML_HD int tucker_lm_solve(const float* __restrict__ S, const float* __restrict
             for (int i = 0; i < NH; ++i) H[i] = Hn[i];
             L = Ln;
             if (stalled) break;
-            if (!capped) lam = fmaxf(lam / o.lambda_down, 1e-9f);
+            if (!capped) lam = fmaxf(lam / o.lambda_down, o.lambda_min);
         } else {
             lam *= o.lambda_up;
             if (lam > 1e12f) break;

@@ -160,8 +160,8 @@ def newton_terms(P, W, X, rows_y, rows_p, rows_r):
     return L.numpy(), G.numpy(), H.numpy()
 
 
-def lm_fit(W, X, rows_y, rows_p, rows_r, max_evals=200, lambda0=1e-3, down=10.0, up=4.0, angle_cap=0.15,
-           step_tol=1e-10, diag_floor=1.0):
+def lm_fit(W, X, rows_y, rows_p, rows_r, max_evals=200, lambda0=1e-3, down=5.0, up=4.0, angle_cap=0.15,
+           step_tol=1e-10, diag_floor=1.0, lambda_min=1e-5):
     """Converged fit: float64 restatement of csrc/tucker_math.h tucker_lm_solve (damped Newton with the exact
     Hessian, Marquardt scaling, capped angle step, from p = 0 as TD_Tester.py:164).  parity unpinned against the
     reference's scipy Powell search (TD_Tester.py:191-194): same objective, same start, compared at the optimum.
@@ -204,7 +204,7 @@ def lm_fit(W, X, rows_y, rows_p, rows_r, max_evals=200, lambda0=1e-3, down=10.0,
         a = idx[acc]
         P[a], L[a], G[a], H[a] = Pn[acc], Ln[acc], Gn[acc], Hn[acc]
         dn = a[~capped[acc]]
-        lam[dn] = np.maximum(lam[dn] / down, 1e-9)
+        lam[dn] = np.maximum(lam[dn] / down, lambda_min)
         rj = idx[~acc]
         lam[rj] *= up
         active[rj[lam[rj] > 1e12]] = False

@@ -139,7 +139,7 @@ extern "C" int hostcheck_tucker_newton_5333(const float* W2, int F, const double
 extern "C" int hostcheck_tucker_solve_5333(const float* W2, int F, const double* rows_y, const double* rows_p,
                                            const double* rows_r, const float* X, int64_t N, int64_t ldx,
                                            int max_evals, float* P /*[N][8]*/, int* evals /*[N]*/,
-                                           const float* opts /*optional [7]: lambda0, down, up, cap, tol, floor, noise_step*/,
+                                           const float* opts /*optional [8]: lambda0, down, up, cap, tol, floor, noise_step, lambda_min*/,
                                            float* Lout /*optional [N]*/) {
     using C = Prepared5333;
     C pre(W2, F, rows_y, rows_p, rows_r);
@@ -147,7 +147,7 @@ extern "C" int hostcheck_tucker_solve_5333(const float* W2, int F, const double*
     if (max_evals > 0) o.max_evals = max_evals;
     if (opts) {
         o.lambda0 = opts[0]; o.lambda_down = opts[1]; o.lambda_up = opts[2]; o.angle_cap = opts[3];
-        o.step_tol = opts[4]; o.diag_floor = opts[5]; o.noise_step = opts[6];
+        o.step_tol = opts[4]; o.diag_floor = opts[5]; o.noise_step = opts[6]; o.lambda_min = opts[7];
     }
     for (int64_t s = 0; s < N; ++s) {
         float q[C::R], scr[3 * (tri(C::RY) + tri(C::RP))];
