@@ -109,6 +109,22 @@ int nlml_mlp_forward_f32(nlml_mlp_plan* plan, const float* X_dev, int64_t N, int
 /* HOST buffers, chunked and pipelined like nlml_tucker_fit_host_f32. */
 int nlml_mlp_forward_host_f32(nlml_mlp_plan* plan, const float* X_host, int64_t N, int64_t ldx,
                               float* YPR_out_host);
+/* Feature-side pre/post steps of the reference's callers.
+ *
+ * nlml_mlp_forward_landmarks_f32: like nlml_mlp_forward_f32, but LM_dev holds RAW MediaPipe landmarks
+ * (x,y,z of landmark i at columns 3i..3i+2) and the normalisation of
+ * Read_Landmarks_and_Normalizing_using_IPD (/root/reference/helpers/FeatureExtractor.py:30-66, with the nose-tip
+ * reference point of :89-90 and the .float() of :105) is fused into the first kernel's load stage: subtract
+ * landmark 1, divide by ||landmark 33 - landmark 263|| (1e-6 when zero), in float64, rounded to float32.
+ * Tensor-core path only (NLML_E_UNSUPPORTED after nlml_mlp_set_path(plan, 1)). */
+int nlml_mlp_forward_landmarks_f32(nlml_mlp_plan* plan, const float* LM_dev, int64_t N, int64_t ldx,
+                                   float* YPR_out_dev, void* stream);
+/* nlml_pose_postprocess_f64: YPR_dev float32 [N][3] radians -> DEG_out_dev float64 [N][3]:
+ * round(np.degrees(t.item()), decimals) as NLML_HPE_Test.py:273 (decimals 3) / generatePose_on_video.py:210
+ * (decimals 2) and, when 0 < ema_alpha < 1, the exponential smoothing over consecutive rows (= video frames) of
+ * generatePose_on_video.py:215-224 (alpha 0.4 there).  Bit-identical to the Python statements. */
+int nlml_pose_postprocess_f64(const float* YPR_dev, int64_t N, int decimals, double ema_alpha,
+                              double* DEG_out_dev, void* stream);
 /* Encoder output only: LAT_out DEVICE float32 [N][latent] (for stage-wise parity checks). */
 int nlml_mlp_latent_f32(nlml_mlp_plan* plan, const float* X_dev, int64_t N, int64_t ldx,
                         float* LAT_out_dev, void* stream);

@@ -162,6 +162,39 @@ class CombinedAnglePredictionModel(nn.Module):
                                                  torch.cuda.current_stream(x.device).cuda_stream))
         return out
 
+    def predict_landmarks(self, landmarks):
+        """RAW MediaPipe landmarks, CUDA float32 [B,468,3] or [B,1404] -> CUDA [B,3] radians.  The translation /
+        scale normalisation of FeatureExtractor.Read_Landmarks_and_Normalizing_using_IPD
+        (helpers/FeatureExtractor.py:30-66: subtract the nose tip, divide by the inter-pupillary distance) is
+        fused into the first kernel's load stage, in float64 as the reference's Python floats."""
+        if not landmarks.is_cuda:
+            raise TypeError("predict_landmarks() takes a CUDA tensor")
+        x = landmarks.reshape(landmarks.shape[0], -1)
+        plan = self._get_plan(x.device.index)
+        x = _check_x(x, plan.input_size)
+        out = torch.empty((x.shape[0], 3), dtype=torch.float32, device=x.device)
+        ldx = x.stride(0) if x.shape[0] > 1 else x.shape[1]
+        _lib.check(plan.lib.nlml_mlp_forward_landmarks_f32(plan.h, x.data_ptr(), x.shape[0], ldx, out.data_ptr(),
+                                                           torch.cuda.current_stream(x.device).cuda_stream))
+        return out
+
+    @staticmethod
+    def to_degrees(angles, decimals=3, ema_alpha=None):
+        """angles CUDA float32 [B,3] radians -> CUDA float64 [B,3]: round(np.degrees(t.item()), decimals) as the
+        callers do (NLML_HPE_Test.py:273 decimals=3; generatePose_on_video.py:210 decimals=2) and, with ema_alpha,
+        the exponential smoothing over consecutive rows (= frames) of generatePose_on_video.py:215-224 (alpha 0.4).
+        Bit-identical to those Python statements."""
+        if not (angles.is_cuda and angles.dtype == torch.float32 and angles.dim() == 2 and angles.shape[1] == 3):
+            raise TypeError("to_degrees() takes a CUDA float32 [B,3] tensor")
+        angles = angles.contiguous()
+        out = torch.empty(angles.shape, dtype=torch.float64, device=angles.device)
+        lib = _lib.load()
+        with torch.cuda.device(angles.device):
+            _lib.check(lib.nlml_pose_postprocess_f64(angles.data_ptr(), angles.shape[0], int(decimals),
+                                                     float(ema_alpha) if ema_alpha else 0.0, out.data_ptr(),
+                                                     torch.cuda.current_stream(angles.device).cuda_stream))
+        return out
+
     def predict_host(self, x, device=None):
         """x numpy / CPU tensor float32 [B,input_size] -> numpy [B,3]; copies pipelined in the library."""
         if isinstance(x, torch.Tensor):

@@ -329,8 +329,10 @@ constexpr size_t kTailSmem = sizeof(float) * (kHeadW * kTailMid + tc::kRowsPerBl
 
 // one chunk (n <= pl->chunk samples) through the whole chain
 int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, float* YPR, float* LAT_out, Workspace& w,
-                  cudaStream_t st) {
+                  cudaStream_t st, int pre = 0) {
     if (n == 0) return 0;
+    if (pre && !use_tc(pl, enc_t(0)))
+        return set_error(NLML_E_UNSUPPORTED, "IPD normalisation is fused into the tensor-core path's operand split (path 0)");
     const bool fuse_neck = pl->path == 0 && neck_fusable(pl), fuse_tail = pl->path == 0 && tail_fusable(pl);
     // ---- encoder ----
     const float* cur_f32 = X;
@@ -341,7 +343,7 @@ int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, flo
         const int vec_ok = (K % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
         const long long total = n * (Kp / 4);
         const unsigned grid = (unsigned)std::min<long long>(ceil_div(total, 256), (long long)pl->num_sms * 16);
-        tc::split_planes_kernel<<<grid, 256, 0, st>>>(X, n, ldx, K, Kp, vec_ok, w.hi[1], w.lo[1]);
+        tc::split_planes_kernel<<<grid, 256, 0, st>>>(X, n, ldx, K, Kp, vec_ok, pre, w.hi[1], w.lo[1]);
         NLML_CUDA(cudaGetLastError());
         pl->launches += 1;
         cur_hi = w.hi[1]; cur_lo = w.lo[1];
@@ -436,12 +438,13 @@ int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, flo
     return 0;
 }
 
-int forward_device(nlml_mlp_plan* pl, const float* X, int64_t N, int64_t ldx, float* YPR, float* LAT, cudaStream_t st) {
+int forward_device(nlml_mlp_plan* pl, const float* X, int64_t N, int64_t ldx, float* YPR, float* LAT, cudaStream_t st,
+                   int pre = 0) {
     if (int rc = ensure_workspace(pl, pl->ws[0], N)) return rc;
     for (int64_t s0 = 0; s0 < N; s0 += pl->chunk) {
         const int64_t n = std::min<int64_t>(pl->chunk, N - s0);
         if (int rc = forward_chunk(pl, X + s0 * ldx, n, ldx, YPR ? YPR + s0 * 3 : nullptr,
-                                   LAT ? LAT + s0 * pl->latent : nullptr, pl->ws[0], st))
+                                   LAT ? LAT + s0 * pl->latent : nullptr, pl->ws[0], st, pre))
             return rc;
     }
     return 0;
@@ -595,6 +598,31 @@ extern "C" int nlml_mlp_forward_f32(nlml_mlp_plan* pl, const float* X_dev, int64
     if (N < 0 || ldx < pl->input_size) return set_error(NLML_E_INVALID, "bad sizes: N=%lld ldx=%lld (input_size=%d)", (long long)N, (long long)ldx, pl->input_size);
     DeviceGuard guard(pl->device);
     return forward_device(pl, X_dev, N, ldx, YPR_out_dev, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int nlml_mlp_forward_landmarks_f32(nlml_mlp_plan* pl, const float* LM_dev, int64_t N, int64_t ldx,
+                                              float* YPR_out_dev, void* stream) {
+    if (!pl || (N > 0 && (!LM_dev || !YPR_out_dev))) return set_error(NLML_E_INVALID, "null pointer argument");
+    if (N < 0 || ldx < pl->input_size) return set_error(NLML_E_INVALID, "bad sizes: N=%lld ldx=%lld (input_size=%d)", (long long)N, (long long)ldx, pl->input_size);
+    if (pl->input_size % 3 != 0 || pl->input_size < 3 * 264)
+        return set_error(NLML_E_INVALID, "IPD normalisation needs x,y,z triples up to landmark 263 (input_size=%d)", pl->input_size);
+    DeviceGuard guard(pl->device);
+    return forward_device(pl, LM_dev, N, ldx, YPR_out_dev, nullptr, (cudaStream_t)stream, 1);
+}
+
+extern "C" int nlml_pose_postprocess_f64(const float* YPR_dev, int64_t N, int decimals, double ema_alpha,
+                                         double* DEG_out_dev, void* stream) {
+    if (N > 0 && (!YPR_dev || !DEG_out_dev)) return set_error(NLML_E_INVALID, "null pointer argument");
+    if (N < 0 || decimals < 0 || decimals > 15 || !(ema_alpha < 1.0))
+        return set_error(NLML_E_INVALID, "bad arguments: N=%lld decimals=%d (0..15) ema_alpha=%g (< 1; <= 0 disables)", (long long)N, decimals, ema_alpha);
+    if (N == 0) return 0;
+    double scale = 1.0;
+    for (int i = 0; i < decimals; ++i) scale *= 10.0;   // exact in double for decimals <= 22, as numpy's power-of-ten table
+    const double alpha = ema_alpha > 0.0 ? ema_alpha : 0.0;
+    const unsigned grid = alpha > 0.0 ? 1u : (unsigned)std::min<int64_t>(ceil_div(3 * N, 128), 148 * 8);
+    tc::pose_post_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(YPR_dev, N, scale, alpha, 1.0 - alpha, DEG_out_dev);
+    NLML_CUDA(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int nlml_mlp_latent_f32(nlml_mlp_plan* pl, const float* X_dev, int64_t N, int64_t ldx, float* LAT_out_dev,

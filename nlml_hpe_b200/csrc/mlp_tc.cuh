@@ -608,9 +608,14 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
     }
 }
 
-// FP32 -> (hi, lo) FP16 planes, rows padded with zeros to Kp columns
+// FP32 -> (hi, lo) FP16 planes, rows padded with zeros to Kp columns.
+// ipd_norm: the rows are RAW MediaPipe landmarks (x,y,z of landmark i at columns 3i..3i+2) and the translation /
+// scale normalisation of helpers/FeatureExtractor.py:30-66 (+ :89-90, :105) is applied on the way in: subtract the
+// nose tip (landmark 1), divide by the inter-pupillary distance ||lm33 - lm263|| (1e-6 when zero), in FLOAT64 as
+// the reference's Python floats, then round to float32 (`.float()`) -- so the encoder sees bit-identical inputs.
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ X, long long N, long long ldx, int K,
-                                                          int Kp, int vec_ok, __half* __restrict__ Xhi, __half* __restrict__ Xlo) {
+                                                          int Kp, int vec_ok, int ipd_norm, __half* __restrict__ Xhi,
+                                                          __half* __restrict__ Xlo) {
     const int groups = Kp / 4;
     const long long total = N * groups;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -626,7 +631,19 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
             if (k + 2 < K) v.z = __ldg(src + k + 2);
             if (k + 3 < K) v.w = __ldg(src + k + 3);
         }
-        const float f[4] = {v.x, v.y, v.z, v.w};
+        float f[4] = {v.x, v.y, v.z, v.w};
+        if (ipd_norm) {
+            // the nine values every thread of the row needs come from L1 after the first touch
+            const double ref[3] = {(double)__ldg(src + 3), (double)__ldg(src + 4), (double)__ldg(src + 5)};
+            const double dx = (double)__ldg(src + 99) - (double)__ldg(src + 789);
+            const double dy = (double)__ldg(src + 100) - (double)__ldg(src + 790);
+            const double dz = (double)__ldg(src + 101) - (double)__ldg(src + 791);
+            double ipd = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+            if (ipd == 0.0) ipd = 1e-6;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (k + j < K) f[j] = __double2float_rn(__ddiv_rn(__dsub_rn((double)f[j], ref[(k + j) % 3]), ipd));
+        }
         uint32_t h[2], l[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -638,6 +655,31 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
         *reinterpret_cast<uint2*>(Xhi + row * Kp + k) = make_uint2(h[0], h[1]);
         *reinterpret_cast<uint2*>(Xlo + row * Kp + k) = make_uint2(l[0], l[1]);
     }
+}
+
+// Callers' post-processing of the three angles (radians, float32) in FLOAT64, as their Python statements:
+//   deg = round(np.degrees(t.item()), decimals)       NLML_HPE_Test.py:273 (3), generatePose_on_video.py:210 (2)
+//       = rint(rad * (180/pi) * 10^decimals) / 10^decimals     (numpy's round: scale, rint, divide)
+// and, when alpha > 0, the exponential smoothing over consecutive frames (= consecutive rows) of
+// generatePose_on_video.py:215-224:  s_0 = y_0,  s_t = alpha*y_t + (1-alpha)*s_{t-1}.
+// The recurrence is evaluated in frame order by one thread per angle so the result is bit-identical to the Python
+// loop (a parallel scan would re-associate the sums); it is three multiplies and an add per frame.
+__global__ void __launch_bounds__(128) pose_post_kernel(const float* __restrict__ YPR, long long N, double scale, double alpha,
+                                                       double one_minus_alpha, double* __restrict__ DEG) {
+    constexpr double kRadToDeg = 180.0 / 3.14159265358979323846;
+    if (alpha > 0.0) {
+        const int j = blockIdx.x * blockDim.x + threadIdx.x;
+        if (j >= 3) return;
+        double s = 0.0;
+        for (long long t = 0; t < N; ++t) {
+            const double y = __ddiv_rn(rint(__dmul_rn(__dmul_rn((double)YPR[t * 3 + j], kRadToDeg), scale)), scale);
+            s = (t == 0) ? y : __dadd_rn(__dmul_rn(alpha, y), __dmul_rn(one_minus_alpha, s));
+            DEG[t * 3 + j] = s;
+        }
+        return;
+    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < 3 * N; i += (long long)gridDim.x * blockDim.x)
+        DEG[i] = __ddiv_rn(rint(__dmul_rn(__dmul_rn((double)YPR[i], kRadToDeg), scale)), scale);
 }
 
 // ---------------------------------------------------------------------------------------------------------

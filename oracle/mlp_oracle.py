@@ -68,3 +68,47 @@ def latent(encoder_sd, X, dtype=torch.float32):
             elif li == 4:
                 h = torch.tanh(h)
         return h.numpy()
+
+
+# ---- feature-side pre / post steps of the reference's callers ----------------------
+# PINNED: tests/golden/prepost_golden.npz holds outputs of the reference's own
+# helpers/FeatureExtractor.Read_Landmarks_and_Normalizing_using_IPD run in the build container
+# (tests/golden/make_golden_prepost.py) and of the callers' post-processing statements executed verbatim as Python.
+
+LEFT_EYE, RIGHT_EYE, NOSE = 33, 263, 1    # helpers/FeatureExtractor.py:35-36, :89
+
+
+def ipd_normalize(raw):
+    """helpers/FeatureExtractor.py:30-66 + :89-90 + :105 for a batch: raw [N,468,3] (or [N,1404]) MediaPipe
+    landmarks -> float32 features [N,1404]: subtract the nose tip (landmark 1), divide by the inter-pupillary
+    distance ||lm33 - lm263|| (1e-6 when zero), all in float64 as the Python floats of the reference, then
+    `.float()`."""
+    raw = np.asarray(raw, dtype=np.float64).reshape(len(raw), -1, 3)
+    out = np.empty(raw.shape, dtype=np.float64)
+    for n in range(raw.shape[0]):
+        d = raw[n, LEFT_EYE] - raw[n, RIGHT_EYE]
+        ipd = np.linalg.norm(d)
+        if ipd == 0:
+            ipd = 1e-6
+        out[n] = (raw[n] - raw[n, NOSE]) / ipd
+    return out.reshape(len(raw), -1).astype(np.float32)
+
+
+def degrees_round(rad, decimals=3):
+    """round(np.degrees(t.item()), decimals) per angle (NLML_HPE_Test.py:273 decimals=3,
+    generatePose_on_video.py:210 decimals=2): float32 radians -> float64 degrees."""
+    rad = np.asarray(rad, dtype=np.float32)
+    return np.array([[round(np.degrees(float(v)), decimals) for v in row] for row in rad], dtype=np.float64)
+
+
+def ema(deg, alpha=0.4):
+    """generatePose_on_video.py:215-224: s_0 = y_0; s_t = alpha*y_t + (1-alpha)*s_{t-1}, Python floats."""
+    deg = np.asarray(deg, dtype=np.float64)
+    out = np.empty_like(deg)
+    for j in range(deg.shape[1]):
+        s = 0.0
+        for t in range(deg.shape[0]):
+            y = float(deg[t, j])
+            s = y if t == 0 else alpha * y + (1 - alpha) * s
+            out[t, j] = s
+    return out

@@ -32,6 +32,11 @@ def mlp_golden():
 
 
 @pytest.fixture(scope="session")
+def prepost_golden():
+    return dict(np.load(os.path.join(GOLDEN, "prepost_golden.npz")))
+
+
+@pytest.fixture(scope="session")
 def rows(art):
     """optimized_*[0:3,:] as the reference slices them (TD_Inference.py:56-57)."""
     return tuple(np.ascontiguousarray(art[f"optimized_{k}"][0:3, :]) for k in ("yaw", "pitch", "roll"))

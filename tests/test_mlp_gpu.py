@@ -128,3 +128,68 @@ def test_full_size_properties_1M(model, art, rows):
     assert out.shape == (n, 3) and torch.isfinite(out).all()
     assert (out[:4096] - small).abs().max().item() * DEG < 1e-4
     assert (out[4096 * 200:4096 * 201] - small).abs().max().item() * DEG < 1e-4
+
+
+# ---- feature-side pre / post steps fused around the forward ----
+
+@pytest.fixture(scope="module")
+def tc_model(state_dicts, cuda_lib):
+    from nlml_hpe_b200 import NLML_HPE_Model_Builder as MB
+    return MB.build_combined_model(*state_dicts)
+
+
+def test_fused_ipd_normalisation_is_bit_exact(tc_model, prepost_golden):
+    """Raw landmarks through the fused load stage == the reference-normalised features through the plain forward,
+    bit for bit (so the float64 normalisation on the device reproduces FeatureExtractor.py:30-66 + .float())."""
+    g = prepost_golden
+    raw = _gpu(g["raw"])                                   # [96,468,3]
+    fused = tc_model.predict_landmarks(raw).cpu().numpy()
+    plain = tc_model.predict(_gpu(g["norm_X"])).cpu().numpy()
+    assert np.array_equal(fused, plain)
+    assert np.array_equal(tc_model.predict_landmarks(raw.reshape(96, 1404)).cpu().numpy(), plain)
+    assert np.array_equal(tc_model.predict_landmarks(raw[:1]).cpu().numpy(), plain[:1])
+    # and against the oracle end to end (normalise on the CPU in float64, forward in float32)
+    ok = np.abs(g["norm_X"]).max(1) < 10.0                # the two degenerate faces are outside the 1e-3 degree budget's range
+    ref = mlp_oracle.forward(*[s for s in tc_model_state(tc_model)], mlp_oracle.ipd_normalize(g["raw"])[ok])
+    assert np.abs(fused[ok] - ref).max() * DEG < TOL_DEG
+
+
+def tc_model_state(m):
+    enc = {k: v.detach().cpu().numpy() for k, v in m.encoder.state_dict().items()}
+    heads = [{k: v.detach().cpu().numpy() for k, v in h.state_dict().items()} for h in (m.yaw_network, m.pitch_network, m.roll_network)]
+    return enc, heads[0], heads[1], heads[2]
+
+
+def test_fused_ipd_normalisation_large_batch_and_strides(tc_model, prepost_golden):
+    g = prepost_golden
+    base_raw, base_norm = _gpu(g["raw"].reshape(96, 1404)), _gpu(g["norm_X"])
+    reps = 1700                                            # 163 200 rows: crosses two chunk boundaries
+    fused = tc_model.predict_landmarks(base_raw.repeat(reps, 1))
+    plain = tc_model.predict(base_norm.repeat(reps, 1))
+    assert torch.equal(fused, plain)
+    wide = torch.zeros((96, 1500), device="cuda")
+    wide[:, 3:1407] = base_raw                             # unaligned rows, row stride != 1404
+    assert torch.equal(tc_model.predict_landmarks(wide[:, 3:1407]), plain[:96])
+
+
+def test_fused_ipd_normalisation_fp32_path_fails_loudly(state_dicts, prepost_golden, cuda_lib):
+    from nlml_hpe_b200 import NLML_HPE_Model_Builder as MB
+    m = MB.build_combined_model(*state_dicts)
+    m.set_path("fp32")
+    with pytest.raises(Exception, match="tensor-core"):
+        m.predict_landmarks(_gpu(prepost_golden["raw"]))
+
+
+def test_degrees_rounding_and_ema_are_bit_exact(tc_model, prepost_golden):
+    g = prepost_golden
+    rad = _gpu(g["rad"])
+    assert np.array_equal(tc_model.to_degrees(rad, 3).cpu().numpy(), g["deg3"])                      # NLML_HPE_Test.py:273
+    assert np.array_equal(tc_model.to_degrees(rad, 2, ema_alpha=float(g["alpha"])).cpu().numpy(), g["deg2_ema"])   # video demo
+    assert np.array_equal(tc_model.to_degrees(rad, 2).cpu().numpy(), mlp_oracle.degrees_round(g["rad"], 2))
+    assert tc_model.to_degrees(rad[:0], 3).shape == (0, 3)
+    big = torch.from_numpy(np.random.default_rng(3).uniform(-1.5, 1.5, (200_000, 3)).astype(np.float32)).cuda()
+    out = tc_model.to_degrees(big, 3).cpu().numpy()
+    assert np.array_equal(out[:5000], mlp_oracle.degrees_round(big[:5000].cpu().numpy(), 3))
+    assert np.array_equal(out, np.round(np.degrees(big.cpu().numpy().astype(np.float64)), 3))
+    with pytest.raises(Exception):
+        tc_model.to_degrees(rad, 3, ema_alpha=1.5)
