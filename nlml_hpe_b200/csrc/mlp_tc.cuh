@@ -671,10 +671,17 @@ __global__ void __launch_bounds__(128) pose_post_kernel(const float* __restrict_
         const int j = blockIdx.x * blockDim.x + threadIdx.x;
         if (j >= 3) return;
         double s = 0.0;
-        for (long long t = 0; t < N; ++t) {
-            const double y = __ddiv_rn(rint(__dmul_rn(__dmul_rn((double)YPR[t * 3 + j], kRadToDeg), scale)), scale);
-            s = (t == 0) ? y : __dadd_rn(__dmul_rn(alpha, y), __dmul_rn(one_minus_alpha, s));
-            DEG[t * 3 + j] = s;
+        for (long long t0 = 0; t0 < N; t0 += 8) {
+            double y[8];   // eight independent loads + roundings in flight, then the dependent chain
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                y[i] = (t0 + i < N) ? __ddiv_rn(rint(__dmul_rn(__dmul_rn((double)__ldg(YPR + (t0 + i) * 3 + j), kRadToDeg), scale)), scale) : 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (t0 + i < N) {
+                    s = (t0 + i == 0) ? y[i] : __dadd_rn(__dmul_rn(alpha, y[i]), __dmul_rn(one_minus_alpha, s));
+                    DEG[(t0 + i) * 3 + j] = s;
+                }
         }
         return;
     }
