@@ -204,6 +204,7 @@ struct nlml_mlp_plan {
     int path = 0;  // 0 = tensor-core chain where eligible, 1 = FP32 CUDA-core chain everywhere
     int tc_group = 1;      // k-blocks accumulated in TMEM per promotion (NLML_TC_GROUP).  Max error vs the reference over
                            // 32768 samples: 1 -> 5.3e-4 deg, 2 -> 8.3e-4 deg (+3 % speed), 22 (never promote) -> 3.7e-3 deg
+    bool tc_tail = true;   // heads' last two layers on the tensor cores (NLML_TC_TAIL=0: CUDA-core head_tail_kernel)
     bool two_cta = true;   // 256-wide layers: cta_group::2 kernel (false: 1-CTA MMAs with W multicast; NLML_TC_1CTA=1)
     int input_size = 0, latent = 0, head_in = 0;
     int64_t chunk = 4 * 148 * 128;  // samples per pass: 4 x 148 M-tiles = whole waves of the persistent GEMMs; the per-launch
@@ -274,12 +275,17 @@ int launch_simt(nlml_mlp_plan* pl, LinearArgs& a, int nz, cudaStream_t st) {
 
 // one tensor-core layer for `nz` problems of identical shape (1 = encoder layer, 3 = the heads):
 // A planes [n][Kp] -> planes and/or FP32
+// dot_t: when non-null, tensor ids of the FOLLOWING single-output layers, fused into the epilogue as a dot product
+// (the heads' last two layers: 128 -> 64 relu on the tensor cores, 64 -> 1 in the epilogue); results go to Ydot[row*3+z]
 int launch_tc(nlml_mlp_plan* pl, const int* t, int nz, const __half* const* Ahi, const __half* const* Alo, int64_t n,
-              __half* const* Yhi, __half* const* Ylo, float* const* Yf32, cudaStream_t st) {
+              __half* const* Yhi, __half* const* Ylo, float* const* Yf32, cudaStream_t st, const int* dot_t = nullptr,
+              float* Ydot = nullptr) {
     const int out = pl->out_dims[t[0]], Kp = pl->Kp[t[0]];
     tc::TcMaps maps;
     tc::LinearTcArgs a{};
     a.N = n; a.out = out; a.Kp = Kp; a.act = act_of(t[0]); a.problems = nz; a.ldy = out; a.group = pl->tc_group;
+    a.Ydot = Ydot; a.ldd = 3;
+    for (int z = 0; z < nz && dot_t; ++z) { a.dot_w[z] = pl->W[dot_t[z]]; a.dot_b[z] = pl->B[dot_t[z]]; }
     for (int z = 0; z < nz; ++z) {
         if (int rc = tc::make_plane_map(&maps.a_hi[z], Ahi[z], n, Kp, Kp, tc::BM)) return rc;
         if (int rc = tc::make_plane_map(&maps.a_lo[z], Alo[z], n, Kp, Kp, tc::BM)) return rc;
@@ -305,6 +311,9 @@ int launch_tc(nlml_mlp_plan* pl, const int* t, int nz, const __half* const* Ahi,
         cfg.attrs = attr; cfg.numAttrs = 1;
         if (pl->two_cta) NLML_CUDA(cudaLaunchKernelEx(&cfg, tc::linear_tc2_kernel, maps, a));
         else NLML_CUDA(cudaLaunchKernelEx(&cfg, tc::linear_tc_kernel<256, 2>, maps, a));
+    } else if (out == 64) {
+        const unsigned grid = (unsigned)std::min<int64_t>(tiles_m * nz, pl->num_sms);
+        tc::linear_tc_kernel<64, 1><<<grid, tc::kThreads, tc::Cfg<64>::SMEM_BYTES, st>>>(maps, a);
     } else {
         const unsigned grid = (unsigned)std::min<int64_t>(tiles_m * (out / 128) * nz, pl->num_sms);
         tc::linear_tc_kernel<128, 1><<<grid, tc::kThreads, tc::Cfg<128>::SMEM_BYTES, st>>>(maps, a);
@@ -322,6 +331,10 @@ inline bool neck_fusable(const nlml_mlp_plan* pl) {
 }
 inline bool tail_fusable(const nlml_mlp_plan* pl) {
     return pl->in_dims[head_t(0, 3)] == kHeadW && pl->out_dims[head_t(0, 3)] == kTailMid;
+}
+// heads' last two layers on the tensor cores: 128 -> 64 relu as a BN = 64 tile, 64 -> 1 as a dot product in its epilogue
+inline bool tail_on_tc(const nlml_mlp_plan* pl) {
+    return pl->path == 0 && pl->tc_tail && pl->tc[head_t(0, 2)] && pl->tc[head_t(0, 3)];
 }
 constexpr size_t kNeckSmem = sizeof(float) * (kNeckIn * kNeckMid + tc::kRowsPerBlock * (kNeckIn + 4) + kNeckLat * kNeckMid +
                                               3 * kHeadW * kHeadIn + kNeckMid + kNeckLat + 3 * kHeadW);
@@ -399,6 +412,13 @@ int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, flo
         const int t0 = head_t(0, li), par = li & 1;
         const int out = pl->out_dims[t0];
         const bool last = li == kHead - 1;
+        if (li == 3 && tail_on_tc(pl)) {
+            const int ts[3] = {head_t(0, 3), head_t(1, 3), head_t(2, 3)}, ds[3] = {head_t(0, 4), head_t(1, 4), head_t(2, 4)};
+            __half* none_h[3] = {nullptr, nullptr, nullptr};
+            float* none_f[3] = {nullptr, nullptr, nullptr};
+            if (int rc = launch_tc(pl, ts, 3, hh, hl, n, none_h, none_h, none_f, st, ds, YPR)) return rc;
+            break;
+        }
         if (fuse_tail && li == 3) {
             tc::HeadTailArgs a{};
             a.N = n; a.YPR = YPR;
@@ -412,7 +432,7 @@ int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, flo
             pl->launches += 1;
             break;
         }
-        const bool next_tc = !last && !(fuse_tail && li == 2) && use_tc(pl, head_t(0, li + 1));
+        const bool next_tc = !last && (!(fuse_tail && li == 2) || tail_on_tc(pl)) && use_tc(pl, head_t(0, li + 1));
         float* yf[3]; __half* yh[3]; __half* yl[3];
         for (int h = 0; h < 3; ++h) {
             const size_t off = (size_t)h * w.rows * out;
@@ -475,7 +495,7 @@ int prepare_tc_layer(nlml_mlp_plan* pl, int t, const float* Wh) {
     NLML_CUDA(cudaMemcpy(pl->Wlo[t], lo.data(), bytes, cudaMemcpyHostToDevice));
     pl->Kp[t] = Kp;
     pl->inv_scale[t] = std::ldexp(1.0f, -e);
-    const int box_rows = 128;   // 256-wide tiles are loaded as two 128-row halves, one per CTA of the cluster
+    const int box_rows = std::min(out, 128);   // 256-wide tiles are loaded as two 128-row halves, one per CTA of the cluster
     if (int rc = tc::make_plane_map(&pl->wmap_hi[t], pl->Whi[t], out, Kp, Kp, box_rows)) return rc;
     if (int rc = tc::make_plane_map(&pl->wmap_lo[t], pl->Wlo[t], out, Kp, Kp, box_rows)) return rc;
     return 0;
@@ -541,6 +561,8 @@ extern "C" int nlml_mlp_plan_create(const float* const* weights, const float* co
         const bool first = t == 0;
         pl->tc[t] = out_dims[t] % 128 == 0 && in_dims[t] >= 64 && (first || in_dims[t] % 64 == 0);
     }
+    // the heads' 128 -> 64 layer rides the tensor cores as a 64-wide tile when its successor is the single-output layer
+    if (tail_fusable(pl) && out_dims[head_t(0, 4)] == 1 && in_dims[head_t(0, 4)] == kTailMid) pl->tc[head_t(0, 3)] = true;
     for (int h = 1; h < 3; ++h)
         for (int li = 0; li < kHead; ++li) pl->tc[head_t(h, li)] = pl->tc[head_t(0, li)];
     for (int t = 0; t < kNumT; ++t)
@@ -549,6 +571,8 @@ extern "C" int nlml_mlp_plan_create(const float* const* weights, const float* co
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg2::SMEM_BYTES));
     if (const char* e = std::getenv("NLML_TC_1CTA")) pl->two_cta = !(e[0] == '1');
     if (const char* e = std::getenv("NLML_TC_GROUP")) pl->tc_group = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("NLML_TC_TAIL")) pl->tc_tail = !(e[0] == '0');   // measurement: 0 = CUDA-core head_tail_kernel
+    NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<64>::SMEM_BYTES));
     if (const char* e = std::getenv("NLML_MLP_CHUNK_WAVES")) pl->chunk = (int64_t)pl->num_sms * 128 * std::max(1, std::atoi(e));
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<256>::SMEM_BYTES));
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<128>::SMEM_BYTES));

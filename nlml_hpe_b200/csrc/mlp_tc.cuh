@@ -38,7 +38,8 @@ struct Cfg {
     static constexpr int W_BYTES = BN * BK * 2;           // one plane of the W tile
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;              // two accumulator buffers
-    static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ + kEpilogueWarps * (BN / 2) * 4 /*bias*/;
+    static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ +
+                                         2 * kEpilogueWarps * (BN / 2) * 4 /*bias, dot weights*/ + 2 * BM * 4 /*dot exchange*/;
 };
 
 constexpr int kMaxProblems = 3;   // the three heads ride one launch
@@ -55,6 +56,11 @@ struct LinearTcArgs {
     __half* Ylo[kMaxProblems];
     float* Yf32[kMaxProblems];        // [N][ldy] or null
     long long ldy;
+    // fused final layer (out == BN only): Ydot[row*ldd + z] = dot_b[z] + sum_j act(y[row][j]) * dot_w[z][j]
+    const float* dot_w[kMaxProblems];   // [out] or null
+    const float* dot_b[kMaxProblems];   // [1]
+    float* Ydot;
+    int ldd;
 };
 
 // operand maps of up to three problems: A_hi, A_lo, W_hi, W_lo each
@@ -198,6 +204,8 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
     uint64_t* tempty = tfull + 2;             // [2]  partial accumulator drained into registers
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* bias_all = reinterpret_cast<float*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256);   // [warp][HALF], private per epilogue warp
+    float* dotw_all = bias_all + kEpilogueWarps * HALF;                                            // [warp][HALF]
+    float* dot_xch = dotw_all + kEpilogueWarps * HALF;                                             // [2][BM] partial dots of the upper column half
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = a.Kp / BK;
@@ -291,6 +299,7 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
         // ===== epilogue warps: TMEM lane quadrant = warp id % 4, column half = (warp - 2) / 4 =====
         const int quad = warp & 3, half = (warp - 2) >> 2;
         int acc = 0; uint32_t acc_phase = 0;
+        int tile_parity = 0;
         for (long long t = first; t < num_tiles; t += step) {
             const int z = (int)(t / tiles_per_problem);
             const long long tt = t % tiles_per_problem;
@@ -302,8 +311,13 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
             __half* __restrict__ Yhi = a.Yhi[z];
             __half* __restrict__ Ylo = a.Ylo[z];
             float* bias_s = bias_all + (warp - 2) * HALF;   // this warp's slice of the bias, read back as broadcasts
+            float* dotw_s = dotw_all + (warp - 2) * HALF;
+            const float* __restrict__ dot_w = a.dot_w[z];
             __syncwarp();
-            for (int j = lane; j < HALF; j += 32) bias_s[j] = __ldg(bias + n0 + j);
+            for (int j = lane; j < HALF; j += 32) {
+                bias_s[j] = __ldg(bias + n0 + j);
+                if (dot_w) dotw_s[j] = __ldg(dot_w + n0 + j);
+            }
             __syncwarp();
             float sum[HALF];
 #pragma unroll
@@ -325,7 +339,20 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
                 if (lane == 0) mbar_arrive(&tempty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (row < a.N) {
+            if (dot_w) {
+                // fused final layer: this thread's share of the row's dot product, then the two column halves
+                // of a lane quadrant meet through shared memory (named barrier of the two warps)
+                float part = 0.f;
+#pragma unroll
+                for (int j = 0; j < HALF; ++j)
+                    part = fmaf(act_apply(fmaf(sum[j], inv_scale, bias_s[j]), a.act), dotw_s[j], part);
+                float* slot = dot_xch + (tile_parity * BM) + quad * 32 + lane;
+                if (half == 1) *slot = part;
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+                if (half == 0 && row < a.N) a.Ydot[row * a.ldd + z] = (part + *slot) + __ldg(a.dot_b[z]);
+                tile_parity ^= 1;
+            }
+            if (row < a.N && (Yf32 || Yhi)) {
 #pragma unroll
                 for (int c0 = 0; c0 < HALF; c0 += 32) {
                     float y[32];
@@ -440,6 +467,8 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
     uint64_t* tempty = tfull + 2;             // [2]  (leader's copy) drained by all 16 epilogue warps of the pair
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* bias_all = reinterpret_cast<float*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256);   // [warp][HALF], private per epilogue warp
+    float* dotw_all = bias_all + kEpilogueWarps * HALF;                                            // [warp][HALF]
+    float* dot_xch = dotw_all + kEpilogueWarps * HALF;                                             // [2][BM] partial dots of the upper column half
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = cluster_ctarank();
@@ -534,8 +563,13 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
             __half* __restrict__ Yhi = a.Yhi[z];
             __half* __restrict__ Ylo = a.Ylo[z];
             float* bias_s = bias_all + (warp - 2) * HALF;   // this warp's slice of the bias, read back as broadcasts
+            float* dotw_s = dotw_all + (warp - 2) * HALF;
+            const float* __restrict__ dot_w = a.dot_w[z];
             __syncwarp();
-            for (int j = lane; j < HALF; j += 32) bias_s[j] = __ldg(bias + n0 + j);
+            for (int j = lane; j < HALF; j += 32) {
+                bias_s[j] = __ldg(bias + n0 + j);
+                if (dot_w) dotw_s[j] = __ldg(dot_w + n0 + j);
+            }
             __syncwarp();
             float sum[HALF];
 #pragma unroll
