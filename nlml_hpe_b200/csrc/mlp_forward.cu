@@ -204,6 +204,7 @@ struct nlml_mlp_plan {
     int path = 0;  // 0 = tensor-core chain where eligible, 1 = FP32 CUDA-core chain everywhere
     int tc_group = 1;      // k-blocks accumulated in TMEM per promotion (NLML_TC_GROUP).  Max error vs the reference over
                            // 32768 samples: 1 -> 5.3e-4 deg, 2 -> 8.3e-4 deg (+3 % speed), 22 (never promote) -> 3.7e-3 deg
+    bool tc_neck = true;   // encoder.8 on the tensor cores with the narrow layers in its epilogue (NLML_TC_NECK=0: neck_kernel)
     bool tc_tail = true;   // heads' last two layers on the tensor cores (NLML_TC_TAIL=0: CUDA-core head_tail_kernel)
     bool two_cta = true;   // 256-wide layers: cta_group::2 kernel (false: 1-CTA MMAs with W multicast; NLML_TC_1CTA=1)
     int input_size = 0, latent = 0, head_in = 0;
@@ -333,6 +334,10 @@ inline bool tail_fusable(const nlml_mlp_plan* pl) {
     return pl->in_dims[head_t(0, 3)] == kHeadW && pl->out_dims[head_t(0, 3)] == kTailMid;
 }
 // heads' last two layers on the tensor cores: 128 -> 64 relu as a BN = 64 tile, 64 -> 1 as a dot product in its epilogue
+// encoder.8 (128 -> 64 tanh) on the tensor cores with encoder.10 and the heads' model.0 in its epilogue
+inline bool neck_on_tc(const nlml_mlp_plan* pl) {
+    return pl->path == 0 && pl->tc_neck && neck_fusable(pl) && pl->tc[enc_t(3)] && pl->tc[enc_t(4)] && pl->tc[head_t(0, 1)];
+}
 inline bool tail_on_tc(const nlml_mlp_plan* pl) {
     return pl->path == 0 && pl->tc_tail && pl->tc[head_t(0, 2)] && pl->tc[head_t(0, 3)];
 }
@@ -365,7 +370,7 @@ int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, flo
     for (int li = 0; li < enc_layers; ++li) {
         const int t = enc_t(li), par = li & 1;
         const bool last = li == kEnc - 1;
-        const bool next_tc = !last && !(fuse_neck && li == 3) && use_tc(pl, enc_t(li + 1));
+        const bool next_tc = !last && (!(fuse_neck && li == 3) || neck_on_tc(pl)) && use_tc(pl, enc_t(li + 1));
         float* yf = last ? (LAT_out ? LAT_out : w.lat) : (next_tc ? nullptr : w.f32[par]);
         __half* yh = next_tc ? w.hi[par] : nullptr;
         __half* yl = next_tc ? w.lo[par] : nullptr;
@@ -385,7 +390,31 @@ int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, flo
     const __half *hh[3] = {nullptr, nullptr, nullptr}, *hl[3] = {nullptr, nullptr, nullptr};
     long long hld = pl->latent;
     int first_head_layer = 0;
-    if (fuse_neck) {
+    if (fuse_neck && neck_on_tc(pl)) {
+        const int t4 = enc_t(4);
+        tc::TcMaps maps;
+        tc::LinearTcArgs a{};
+        a.N = n; a.out = pl->out_dims[t4]; a.Kp = pl->Kp[t4]; a.act = act_of(t4); a.problems = 1; a.ldy = a.out; a.group = pl->tc_group;
+        if (int rc = tc::make_plane_map(&maps.a_hi[0], cur_hi, n, a.Kp, a.Kp, tc::BM)) return rc;
+        if (int rc = tc::make_plane_map(&maps.a_lo[0], cur_lo, n, a.Kp, a.Kp, tc::BM)) return rc;
+        maps.w_hi[0] = pl->wmap_hi[t4]; maps.w_lo[0] = pl->wmap_lo[t4];
+        for (int z = 1; z < tc::kMaxProblems; ++z) { maps.a_hi[z] = maps.a_hi[0]; maps.a_lo[z] = maps.a_lo[0]; maps.w_hi[z] = maps.w_hi[0]; maps.w_lo[z] = maps.w_lo[0]; }
+        a.inv_scale[0] = pl->inv_scale[t4]; a.bias[0] = pl->B[t4];
+        a.neck = 1; a.neck_w5 = pl->W[5]; a.neck_b5 = pl->B[5];
+        a.neck_lat = LAT_out ? LAT_out : w.lat;
+        for (int h = 0; h < 3; ++h) {
+            const size_t off = (size_t)h * w.rows * kHeadW;
+            a.neck_wh[h] = pl->W[head_t(h, 0)]; a.neck_bh[h] = pl->B[head_t(h, 0)];
+            a.neck_hi[h] = w.hi[0] + off; a.neck_lo[h] = w.lo[0] + off;
+            hx[h] = nullptr; hh[h] = a.neck_hi[h]; hl[h] = a.neck_lo[h];
+        }
+        const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n, tc::BM), pl->num_sms);
+        tc::linear_tc_kernel<64, 1><<<grid, tc::kThreads, tc::Cfg<64>::SMEM_BYTES, st>>>(maps, a);
+        NLML_CUDA(cudaGetLastError());
+        pl->launches += 1;
+        hld = kHeadW;
+        first_head_layer = 1;
+    } else if (fuse_neck) {
         tc::NeckArgs a{};
         a.X = cur_f32; a.N = n;
         a.W4t = pl->Wt[4]; a.B4 = pl->B[4]; a.W5 = pl->W[5]; a.B5 = pl->B[5];
@@ -561,6 +590,8 @@ extern "C" int nlml_mlp_plan_create(const float* const* weights, const float* co
         const bool first = t == 0;
         pl->tc[t] = out_dims[t] % 128 == 0 && in_dims[t] >= 64 && (first || in_dims[t] % 64 == 0);
     }
+    // encoder.8 (128 -> 64) rides the tensor cores as a 64-wide tile when the fused neck epilogue applies
+    if (neck_fusable(pl)) pl->tc[enc_t(4)] = true;
     // the heads' 128 -> 64 layer rides the tensor cores as a 64-wide tile when its successor is the single-output layer
     if (tail_fusable(pl) && out_dims[head_t(0, 4)] == 1 && in_dims[head_t(0, 4)] == kTailMid) pl->tc[head_t(0, 3)] = true;
     for (int h = 1; h < 3; ++h)
@@ -571,6 +602,7 @@ extern "C" int nlml_mlp_plan_create(const float* const* weights, const float* co
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg2::SMEM_BYTES));
     if (const char* e = std::getenv("NLML_TC_1CTA")) pl->two_cta = !(e[0] == '1');
     if (const char* e = std::getenv("NLML_TC_GROUP")) pl->tc_group = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("NLML_TC_NECK")) pl->tc_neck = !(e[0] == '0');
     if (const char* e = std::getenv("NLML_TC_TAIL")) pl->tc_tail = !(e[0] == '0');   // measurement: 0 = CUDA-core head_tail_kernel
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<64>::SMEM_BYTES));
     if (const char* e = std::getenv("NLML_MLP_CHUNK_WAVES")) pl->chunk = (int64_t)pl->num_sms * 128 * std::max(1, std::atoi(e));

@@ -31,6 +31,10 @@ constexpr int UMMA_K = 16;
 constexpr int kEpilogueWarps = 8;
 constexpr int kThreads = 32 * (2 + kEpilogueWarps);   // TMA warp, MMA warp, 8 promotion/epilogue warps
 
+// fused neck epilogue (BN = 64 only): W5 [9][64], B5 [12], head rows (w0,w1,w2,b) [3][128] float4, latent exchange [2][9][128]
+constexpr int kNeckLatent = 9, kNeckHeadW = 128;
+constexpr int kNeckSmemFloats = kNeckLatent * 64 + 12 + 3 * kNeckHeadW * 4 + 2 * kNeckLatent * BM;
+
 template <int BN>
 struct Cfg {
     static constexpr int STAGES = BN == 256 ? 2 : 3;
@@ -39,7 +43,8 @@ struct Cfg {
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;              // two accumulator buffers
     static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ +
-                                         2 * kEpilogueWarps * (BN / 2) * 4 /*bias, dot weights*/ + 2 * BM * 4 /*dot exchange*/;
+                                         2 * kEpilogueWarps * (BN / 2) * 4 /*bias, dot weights*/ + 2 * BM * 4 /*dot exchange*/ +
+                                         (BN == 64 ? kNeckSmemFloats * 4 : 0) /*fused neck epilogue*/;
 };
 
 constexpr int kMaxProblems = 3;   // the three heads ride one launch
@@ -61,6 +66,15 @@ struct LinearTcArgs {
     const float* dot_b[kMaxProblems];   // [1]
     float* Ydot;
     int ldd;
+    // fused neck (out == BN == 64, act = tanh): latent = B5 + W5 . y (64 -> 9), LAT[row][9] (optional), then for each
+    // head h the first hidden layer relu(Bh + Wh . latent[3h..3h+2]) (3 -> 128) written as FP16 hi/lo planes
+    int neck;
+    const float *neck_w5, *neck_b5;       // [9][64], [9]
+    const float* neck_wh[3];              // [128][3]
+    const float* neck_bh[3];              // [128]
+    float* neck_lat;                      // [N][9] or null
+    __half* neck_hi[3];                   // [N][128]
+    __half* neck_lo[3];
 };
 
 // operand maps of up to three problems: A_hi, A_lo, W_hi, W_lo each
@@ -206,6 +220,10 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
     float* bias_all = reinterpret_cast<float*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256);   // [warp][HALF], private per epilogue warp
     float* dotw_all = bias_all + kEpilogueWarps * HALF;                                            // [warp][HALF]
     float* dot_xch = dotw_all + kEpilogueWarps * HALF;                                             // [2][BM] partial dots of the upper column half
+    float* neck_w5s = dot_xch + 2 * BM;                                   // [9][64]          (BN == 64 only, see Cfg)
+    float* neck_b5s = neck_w5s + kNeckLatent * 64;                        // [12]
+    float4* neck_whs = reinterpret_cast<float4*>(neck_b5s + 12);          // [3][128] (w0, w1, w2, bias)
+    float* neck_xch = reinterpret_cast<float*>(neck_whs + 3 * kNeckHeadW);   // [2 halves][9][BM]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = a.Kp / BK;
@@ -229,6 +247,19 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
     if (CL > 1) cluster_sync_all();   // the peer's barriers must exist before anything is multicast into them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if constexpr (BN == 64) {
+        if (a.neck && warp >= 2) {   // the epilogue warps stage the narrow layers' constants once per CTA
+            const int e = threadIdx.x - 64, ne = 32 * kEpilogueWarps;
+            for (int i = e; i < kNeckLatent * 64; i += ne) neck_w5s[i] = __ldg(a.neck_w5 + i);
+            for (int i = e; i < kNeckLatent; i += ne) neck_b5s[i] = __ldg(a.neck_b5 + i);
+            for (int i = e; i < 3 * kNeckHeadW; i += ne) {
+                const int h = i / kNeckHeadW, j = i % kNeckHeadW;
+                const float* w = a.neck_wh[h] + 3 * j;
+                neck_whs[i] = make_float4(__ldg(w), __ldg(w + 1), __ldg(w + 2), __ldg(a.neck_bh[h] + j));
+            }
+            asm volatile("bar.sync 5, %0;" ::"r"(32 * kEpilogueWarps) : "memory");
+        }
+    }
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -338,6 +369,57 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if constexpr (BN == 64) {
+                if (a.neck) {
+                    // y = tanh(.) of this warp's 32 of the 64 columns -> partial latent -> exchange -> heads' first layers
+                    float lat[kNeckLatent];
+#pragma unroll
+                    for (int m = 0; m < kNeckLatent; ++m) lat[m] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < HALF; ++j) {
+                        const float y = act_apply(fmaf(sum[j], inv_scale, bias_s[j]), a.act);
+#pragma unroll
+                        for (int m = 0; m < kNeckLatent; ++m) lat[m] = fmaf(y, neck_w5s[m * 64 + n0 + j], lat[m]);
+                    }
+                    const int r = quad * 32 + lane;
+#pragma unroll
+                    for (int m = 0; m < kNeckLatent; ++m) neck_xch[(half * kNeckLatent + m) * BM + r] = lat[m];
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+#pragma unroll
+                    for (int m = 0; m < kNeckLatent; ++m)
+                        lat[m] = (neck_xch[m * BM + r] + neck_xch[(kNeckLatent + m) * BM + r]) + neck_b5s[m];
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // exchange buffer free for the next tile
+                    if (row < a.N) {
+                        if (half == 0 && a.neck_lat) {
+#pragma unroll
+                            for (int m = 0; m < kNeckLatent; ++m) a.neck_lat[row * kNeckLatent + m] = lat[m];
+                        }
+                        // 3 x 128 first-hidden-layer outputs per row; each column half takes 192 of them, 16 at a time
+#pragma unroll 1
+                        for (int g = 0; g < 12; ++g) {
+                            const int o0 = half * 192 + 16 * g, h = o0 / kNeckHeadW, j0 = o0 % kNeckHeadW;
+                            const float l0 = h == 0 ? lat[0] : (h == 1 ? lat[3] : lat[6]);
+                            const float l1 = h == 0 ? lat[1] : (h == 1 ? lat[4] : lat[7]);
+                            const float l2 = h == 0 ? lat[2] : (h == 1 ? lat[5] : lat[8]);
+                            uint32_t hi[8], lo[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float4 w0 = neck_whs[h * kNeckHeadW + j0 + 2 * e], w1 = neck_whs[h * kNeckHeadW + j0 + 2 * e + 1];
+                                const float v0 = fmaxf(fmaf(l2, w0.z, fmaf(l1, w0.y, fmaf(l0, w0.x, w0.w))), 0.f);
+                                const float v1 = fmaxf(fmaf(l2, w1.z, fmaf(l1, w1.y, fmaf(l0, w1.x, w1.w))), 0.f);
+                                const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+                                const __half q0 = __float2half_rn(v0 - __half2float(h0)), q1 = __float2half_rn(v1 - __half2float(h1));
+                                hi[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                                lo[e] = (uint32_t)__half_as_ushort(q0) | ((uint32_t)__half_as_ushort(q1) << 16);
+                            }
+                            __half* dh = (h == 0 ? a.neck_hi[0] : (h == 1 ? a.neck_hi[1] : a.neck_hi[2])) + row * kNeckHeadW + j0;
+                            __half* dl = (h == 0 ? a.neck_lo[0] : (h == 1 ? a.neck_lo[1] : a.neck_lo[2])) + row * kNeckHeadW + j0;
+                            st_global_v8(dh, hi);
+                            st_global_v8(dl, lo);
+                        }
+                    }
+                }
             }
             if (dot_w) {
                 // fused final layer: this thread's share of the row's dot product, then the two column halves
@@ -469,6 +551,10 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
     float* bias_all = reinterpret_cast<float*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256);   // [warp][HALF], private per epilogue warp
     float* dotw_all = bias_all + kEpilogueWarps * HALF;                                            // [warp][HALF]
     float* dot_xch = dotw_all + kEpilogueWarps * HALF;                                             // [2][BM] partial dots of the upper column half
+    float* neck_w5s = dot_xch + 2 * BM;                                   // [9][64]          (BN == 64 only, see Cfg)
+    float* neck_b5s = neck_w5s + kNeckLatent * 64;                        // [12]
+    float4* neck_whs = reinterpret_cast<float4*>(neck_b5s + 12);          // [3][128] (w0, w1, w2, bias)
+    float* neck_xch = reinterpret_cast<float*>(neck_whs + 3 * kNeckHeadW);   // [2 halves][9][BM]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = cluster_ctarank();
