@@ -34,7 +34,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
+    path = os.environ.get("NLML_HPE_LIB") or _build.LIB_PATH   # override: development builds only
     if not os.path.exists(path):
         raise NlmlError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(nvcc, sm_100a).  nlml_hpe_b200 has no CPU fallback.")

@@ -549,12 +549,6 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
     uint64_t* tempty = tfull + 2;             // [2]  (leader's copy) drained by all 16 epilogue warps of the pair
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* bias_all = reinterpret_cast<float*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256);   // [warp][HALF], private per epilogue warp
-    float* dotw_all = bias_all + kEpilogueWarps * HALF;                                            // [warp][HALF]
-    float* dot_xch = dotw_all + kEpilogueWarps * HALF;                                             // [2][BM] partial dots of the upper column half
-    float* neck_w5s = dot_xch + 2 * BM;                                   // [9][64]          (BN == 64 only, see Cfg)
-    float* neck_b5s = neck_w5s + kNeckLatent * 64;                        // [12]
-    float4* neck_whs = reinterpret_cast<float4*>(neck_b5s + 12);          // [3][128] (w0, w1, w2, bias)
-    float* neck_xch = reinterpret_cast<float*>(neck_whs + 3 * kNeckHeadW);   // [2 halves][9][BM]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = cluster_ctarank();
@@ -649,13 +643,8 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
             __half* __restrict__ Yhi = a.Yhi[z];
             __half* __restrict__ Ylo = a.Ylo[z];
             float* bias_s = bias_all + (warp - 2) * HALF;   // this warp's slice of the bias, read back as broadcasts
-            float* dotw_s = dotw_all + (warp - 2) * HALF;
-            const float* __restrict__ dot_w = a.dot_w[z];
             __syncwarp();
-            for (int j = lane; j < HALF; j += 32) {
-                bias_s[j] = __ldg(bias + n0 + j);
-                if (dot_w) dotw_s[j] = __ldg(dot_w + n0 + j);
-            }
+            for (int j = lane; j < HALF; j += 32) bias_s[j] = __ldg(bias + n0 + j);
             __syncwarp();
             float sum[HALF];
 #pragma unroll

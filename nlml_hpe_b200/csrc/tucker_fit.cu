@@ -939,8 +939,19 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
     for (int i = 0; i < C::NP; ++i) p[i] = 0.f;  // zero init, TD_Tester.py:130
     const float lr = a.lr, clip = a.clip;
     uint32_t phase = 0;
+#ifdef NLML_TC_TIMING
+    // development build only (scripts/time_tucker_tc.py): per-phase cycle counts of one thread per role
+    float tacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint32_t tprev = 0;
+#define NLML_TSTAMP(i) { const uint32_t tnow = (uint32_t)clock(); tacc[i] += (float)(tnow - tprev); tprev = tnow; }
+#define NLML_TSTART() { tprev = (uint32_t)clock(); }
+#else
+#define NLML_TSTAMP(i)
+#define NLML_TSTART()
+#endif
 #pragma unroll 1
     for (int it = 0; it < a.T; ++it) {
+        NLML_TSTART();
         float cy[3], dcy[3], cp[3], dcp[3], cr[3], dcr[3], u[5];
 #pragma unroll
         for (int i = 0; i < 5; ++i) u[i] = p[3 + i];
@@ -969,6 +980,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
                 ttc::umma_commit_to(bar);
             }
         }
+        NLML_TSTAMP(0);   // role 0: UU publish + T GEMM issue
         // pitch and roll features first: they are all the V GEMM's operand needs; yaw follows once it is launched
         cos_features_fast<3>(p[1], a.rows_p, cp, dcp);
         cos_features_fast<3>(p[2], a.rows_r, cr, dcr);
@@ -1000,6 +1012,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
                 ttc::umma_commit_to(bar + 1);
             }
         }
+        NLML_TSTAMP(1);   // pitch/roll features (+ role 1: PP(x)RR publish + V GEMM issue)
         cos_features_fast<3>(p[0], a.rows_y, cy, dcy);
         sym_products<3>(cy, YY);
         // the linear term does not depend on the MMAs: it runs while they execute.  Each role keeps only the outputs it
@@ -1013,6 +1026,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             linear_term<5, 3, 3, 3>(qa, 0, cy, cp, cr, u, lin_u, u0, u1, u2);
         }
 
+        NLML_TSTAMP(2);   // yaw features + linear term
         if (role == 1) {
             // V[A,b] = sum_{c,D} PP_c RR_D S[A,b,c,D]  ->  GU[A] = sum_b YY_b V[A,b]  ->  d/du
             float GU[15];
@@ -1020,6 +1034,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             for (int i = 0; i < 15; ++i) GU[i] = 0.f;
             if (a.dbg != 1) ttc::mbar_wait(bar + 1, phase);   // V GEMM
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            NLML_TSTAMP(3);   // wait for the GEMM
             if (a.dbg != 2) {
 #pragma unroll
                 for (int ci = 0; ci < C::NV / 32; ++ci) {
@@ -1041,6 +1056,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             float GR[6], GP[6], GY[6], GR2[6], GP2[6], GY3[3];
             if (a.dbg != 1) ttc::mbar_wait(bar, phase);       // T GEMM (launched first, long done)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            NLML_TSTAMP(3);
             if (a.dbg != 2) {
                 tc_reduce_t<0>(lane_addr + C::COL_T, YY, PP, RRv, GR, GP, GY3);
 #pragma unroll
@@ -1066,14 +1082,25 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             gx[1 * 128 + row] = gp;
             gx[2 * 128 + row] = gr;
         }
+        NLML_TSTAMP(4);   // TMEM read-back + reduction + gradient part
         phase ^= 1;
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();   // all 8 gradient parts in gx
+        NLML_TSTAMP(5);   // CTA barrier
         float g[C::NP];
 #pragma unroll
         for (int i = 0; i < C::NP; ++i) g[i] = gx[i * 128 + row];
         clip_and_step<C::NP>(p, g, lr, clip);
+        NLML_TSTAMP(6);   // clip + step
     }
+#ifdef NLML_TC_TIMING
+    if ((tid == 0 || tid == 128) && s0 + 1 < a.N) {
+        float* out = a.P + (s0 + (tid == 128)) * a.ldp;
+        for (int i = 0; i < 8; ++i) out[i] = tacc[i] / (float)a.T;
+        return;
+    }
+    if (tid == 1) return;
+#endif
     if (role == 0 && s0 + row < a.N) {
         float* out = a.P + (s0 + row) * a.ldp;
 #pragma unroll
