@@ -988,7 +988,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         sym_products<3>(cp, PP);
         sym_products<3>(cr, RRv);
         RRv[6] = RRv[7] = 0.f;
-        // the identity threads publish the PP (x) RR operand; thread 128 launches the V GEMM (named barrier 2)
+        // the identity threads publish the PP (x) RR operand; thread 160 launches the V GEMM (named barrier 2)
         if (role == 1) {
 #pragma unroll
             for (int k4 = 0; k4 < C::KV / 4; ++k4) {
@@ -1005,7 +1005,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             ttc::fence_async_smem();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync 2, 128;" ::: "memory");
-            if (tid == 128 && a.dbg != 1) {
+            if (tid == 160 && a.dbg != 1) {   // warp 5: not on the sub-partition of the T GEMM's issuer (warp 0)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 ttc::issue_gemm_3xtf32(tmem + C::COL_V, ttc::smem_u32(av_hi), ttc::smem_u32(av_lo), ttc::smem_u32(bv_hi),
                                        ttc::smem_u32(bv_lo), C::KV, C::NV, true);
@@ -1094,12 +1094,13 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         NLML_TSTAMP(6);   // clip + step
     }
 #ifdef NLML_TC_TIMING
-    if ((tid == 0 || tid == 128) && s0 + 1 < a.N) {
-        float* out = a.P + (s0 + (tid == 128)) * a.ldp;
+    // rows 0..7 of the CTA's output <- the lane-0 timings of warps 0..7
+    if ((tid & 31) == 0 && s0 + 8 <= a.N) {
+        float* out = a.P + (s0 + warp) * a.ldp;
         for (int i = 0; i < 8; ++i) out[i] = tacc[i] / (float)a.T;
         return;
     }
-    if (tid == 1) return;
+    if (tid < 8) return;
 #endif
     if (role == 0 && s0 + row < a.N) {
         float* out = a.P + (s0 + row) * a.ldp;
