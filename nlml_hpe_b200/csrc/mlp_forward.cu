@@ -361,7 +361,8 @@ int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, flo
         const int vec_ok = (K % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
         const long long total = n * (Kp / 4);
         const unsigned grid = (unsigned)std::min<long long>(ceil_div(total, 256), (long long)pl->num_sms * 16);
-        tc::split_planes_kernel<<<grid, 256, 0, st>>>(X, n, ldx, K, Kp, vec_ok, pre, w.hi[1], w.lo[1]);
+        if (pre) tc::split_planes_kernel<true><<<grid, 256, 0, st>>>(X, n, ldx, K, Kp, vec_ok, w.hi[1], w.lo[1]);
+        else tc::split_planes_kernel<false><<<grid, 256, 0, st>>>(X, n, ldx, K, Kp, vec_ok, w.hi[1], w.lo[1]);
         NLML_CUDA(cudaGetLastError());
         pl->launches += 1;
         cur_hi = w.hi[1]; cur_lo = w.lo[1];

@@ -718,12 +718,13 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
 }
 
 // FP32 -> (hi, lo) FP16 planes, rows padded with zeros to Kp columns.
-// ipd_norm: the rows are RAW MediaPipe landmarks (x,y,z of landmark i at columns 3i..3i+2) and the translation /
+// IPD: the rows are RAW MediaPipe landmarks (x,y,z of landmark i at columns 3i..3i+2) and the translation /
 // scale normalisation of helpers/FeatureExtractor.py:30-66 (+ :89-90, :105) is applied on the way in: subtract the
 // nose tip (landmark 1), divide by the inter-pupillary distance ||lm33 - lm263|| (1e-6 when zero), in FLOAT64 as
 // the reference's Python floats, then round to float32 (`.float()`) -- so the encoder sees bit-identical inputs.
+template <bool IPD>
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ X, long long N, long long ldx, int K,
-                                                          int Kp, int vec_ok, int ipd_norm, __half* __restrict__ Xhi,
+                                                          int Kp, int vec_ok, __half* __restrict__ Xhi,
                                                           __half* __restrict__ Xlo) {
     const int groups = Kp / 4;
     const long long total = N * groups;
@@ -741,7 +742,7 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
             if (k + 3 < K) v.w = __ldg(src + k + 3);
         }
         float f[4] = {v.x, v.y, v.z, v.w};
-        if (ipd_norm) {
+        if constexpr (IPD) {
             // the nine values every thread of the row needs come from L1 after the first touch
             const double ref[3] = {(double)__ldg(src + 3), (double)__ldg(src + 4), (double)__ldg(src + 5)};
             const double dx = (double)__ldg(src + 99) - (double)__ldg(src + 789);
