@@ -39,6 +39,9 @@ TUCKER_FLOP_PER_POSE_REFERENCE = T_ITERS * 2 * 2 * 135 * F                      
 SOLVE_FLOP_PER_EVAL = 2 * (216 * (15 + 60 + 20) + 5 * 3 * 54 + 400)
 TUCKER_TC_FLOP_PER_POSE = T_ITERS * 2 * 3 * (224 * 16 + 96 * 40)
 TUCKER_BYTES_PER_POSE = F * 4 + 8 * 4
+# DRAM traffic of tucker_fit_tc_kernel per sample, from the committed `ncu --set full` capture (profiles/r01_tucker_tc_ncu.txt:
+# dram__bytes_read 218.43 MB + dram__bytes_write 5.36 MB for a 37 888-sample launch); scaled to the bench launch
+TUCKER_TC_NCU_DRAM_BYTES_PER_POSE = (218.431232e6 + 5.357056e6) / 37888
 MLP_FLOP_PER_POSE = 4_714_240
 MLP_BYTES_PER_POSE = F * 4 + 3 * 4
 
@@ -316,7 +319,10 @@ def run_b200(args):
         "gpu_launches": int(t_launches),
         "roofline": {"bound": "tensor", "achieved": per_gpu_t * TUCKER_TC_FLOP_PER_POSE / 1e12,
                      "peak": peaks["bf16_tflops_sustained"] / 2, "unit": "TFLOP/s",
-                     "frac": per_gpu_t * TUCKER_TC_FLOP_PER_POSE / 1e12 / (peaks["bf16_tflops_sustained"] / 2), "traffic": None,
+                     "frac": per_gpu_t * TUCKER_TC_FLOP_PER_POSE / 1e12 / (peaks["bf16_tflops_sustained"] / 2),
+                     "traffic": TUCKER_TC_NCU_DRAM_BYTES_PER_POSE * n,
+                     "traffic_note": "bytes per launch = ncu dram__bytes_read+write of a 37 888-sample launch (profiles/r01_tucker_tc_ncu.txt), "
+                                     f"{TUCKER_TC_NCU_DRAM_BYTES_PER_POSE:.0f} B/sample against {TUCKER_BYTES_PER_POSE} algorithmic, x samples per launch",
                      "kernel": "tucker_fit_tc_kernel",
                      "peak_source": peaks["source"] + " (TF32 dense = half of the measured sustained bf16 rate)",
                      "note": "issued TF32 tensor work: per sample-iteration two 3xTF32 GEMM rows (128x224x16 and 128x96x40 per 128 "
@@ -333,7 +339,8 @@ def run_b200(args):
                                   "kernel (kernel_hint 1) reaches frac_3reg 0.87; values above 1 here mean the tensor cores took the "
                                   "two big contractions off the FP32 pipe."},
         "roofline_hbm": {"bound": "hbm", "achieved": per_gpu_t * TUCKER_BYTES_PER_POSE / 1e9, "peak": peaks["hbm_gbs"],
-                         "unit": "GB/s", "frac": per_gpu_t * TUCKER_BYTES_PER_POSE / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                         "unit": "GB/s", "frac": per_gpu_t * TUCKER_BYTES_PER_POSE / 1e9 / peaks["hbm_gbs"],
+                         "traffic": TUCKER_TC_NCU_DRAM_BYTES_PER_POSE * n,
                          "peak_source": peaks["source"]},
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
         "converged": {
