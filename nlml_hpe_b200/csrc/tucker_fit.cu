@@ -966,7 +966,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             for (int k4 = 0; k4 < C::K1 / 4; ++k4) {
                 float h[4], l[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) ttc::split_tf32(UU[4 * k4 + e], h[e], l[e]);
+                for (int e = 0; e < 4; ++e) ttc::split_tf32_fast(UU[4 * k4 + e], h[e], l[e]);
                 *reinterpret_cast<float4*>(a1_hi + ttc::op_offset(row, 4 * k4, C::K1)) = make_float4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<float4*>(a1_lo + ttc::op_offset(row, 4 * k4, C::K1)) = make_float4(l[0], l[1], l[2], l[3]);
             }
@@ -997,7 +997,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
                 for (int e = 0; e < 4; ++e) {
                     const int kk = 4 * k4 + e;
                     const float v = kk < 36 ? PP[kk / 6] * RRv[kk % 6] : 0.f;
-                    ttc::split_tf32(v, h[e], l[e]);
+                    ttc::split_tf32_fast(v, h[e], l[e]);
                 }
                 *reinterpret_cast<float4*>(av_hi + ttc::op_offset(row, 4 * k4, C::KV)) = make_float4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<float4*>(av_lo + ttc::op_offset(row, 4 * k4, C::KV)) = make_float4(l[0], l[1], l[2], l[3]);

@@ -135,9 +135,15 @@ NLML_HD void clip_and_step(float* p, float* g, float lr, float clip) {
     float ss = 0.f;
 #pragma unroll
     for (int i = 0; i < NP; ++i) ss = fmaf(g[i], g[i], ss);
-    const float norm = sqrtf(ss);
-    float coef = clip / (norm + 1e-6f);
-    coef = coef < 1.0f ? coef : 1.0f;
+    // coef = min(1, clip / (sqrt(ss) + 1e-6)) is exactly 1 whenever sqrt(ss) + 1e-6 <= clip; the test below is 1 %
+    // inside that boundary, so the square root and the division are only evaluated while the clip is (nearly) active
+    const float lim = clip - 1e-6f;
+    float coef = 1.0f;
+    if (!(lim > 0.f && ss < 0.98f * lim * lim)) {
+        const float norm = sqrtf(ss);
+        coef = clip / (norm + 1e-6f);
+        coef = coef < 1.0f ? coef : 1.0f;
+    }
 #pragma unroll
     for (int i = 0; i < NP; ++i) p[i] = sub_rn(p[i], mul_rn(lr, mul_rn(g[i], coef)));
 }

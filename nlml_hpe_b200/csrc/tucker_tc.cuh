@@ -78,6 +78,15 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     lo = v - hi;
 }
 
+// The same split for operands rebuilt every iteration: one cvt.rna (round to nearest, ties away) instead of the
+// integer sequence; lo = v - hi is exact either way.
+__device__ __forceinline__ void split_tf32_fast(float v, float& hi, float& lo) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
+    hi = __uint_as_float(h);
+    lo = v - hi;
+}
+
 // D += A * B^T over K (multiple of 8) with the 3-pass split; a/b tiles in the no-swizzle layout above.
 // Issued by ONE thread.  `first` = overwrite the accumulator with the first MMA.
 __device__ __forceinline__ void issue_gemm_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
