@@ -128,6 +128,11 @@ __device__ __forceinline__ void tmem_store32(uint32_t taddr, const float* v) {
           "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
         : "memory");
 }
+__device__ __forceinline__ void tmem_store4(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_store_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // q accessor for the TMEM-resident variant (same interface as QStrided in tucker_math.h)
@@ -769,14 +774,17 @@ struct TcFitCfg {
     static constexpr int OFF_BV = OFF_B1 + 2 * B1_BYTES;               // hi, lo
     static constexpr int OFF_A1 = OFF_BV + 2 * BV_BYTES;               // hi, lo
     static constexpr int OFF_AV = OFF_A1 + 2 * A1_BYTES;               // hi, lo
-    static constexpr int OFF_Q = OFF_AV + 2 * AV_BYTES;                // q [R][128] floats; phase-A tiles alias it
-    static constexpr int OFF_BAR = OFF_Q + RPAD * THREADS * 4;         // q stored as [RPAD/4][128] float4
+    // q lives in TENSOR MEMORY (columns COL_Q .. COL_Q+135 of each sample's lane): the 17 KB per warp and iteration that
+    // both roles read would otherwise be 38 % of the SM's shared-memory traffic (the UMMA operand reads and the operand
+    // stores share the same 128 B/clk).  The region below only holds the phase-A staging tiles.
+    static constexpr int FC = 16, XSTR = THREADS + 2;                  // phase-A tiles, as in the thread-per-sample kernel
+    static constexpr int OFF_Q = OFF_AV + 2 * AV_BYTES;                // phase-A tiles [FC][XSTR] + [FC][RPAD]
+    static constexpr int OFF_BAR = OFF_Q + (FC * XSTR + FC * RPAD) * 4;
     static constexpr int OFF_GX = OFF_BAR + 64;                        // exchange between the two roles [NGX][128] floats
     static constexpr int NGX = 8 + 15;                                 // 8 gradient parts + role 1's partial GR, GP, GY
     static constexpr size_t SMEM_BYTES = OFF_GX + NGX * THREADS * 4;
     static constexpr int TMEM_COLS = 512;
-    static constexpr int COL_T = 0, COL_V = 224;
-    static constexpr int FC = 16, XSTR = THREADS + 2; // phase-A tiles, as in the thread-per-sample kernel
+    static constexpr int COL_T = 0, COL_V = 224, COL_Q = 320;
 };
 
 // Half of T (3 of the 6 b's = 108 columns) -> partial GR[6], GP[6] and the 3 GY of those b's
@@ -852,6 +860,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc_cols(tmem_slot, C::TMEM_COLS);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // (phase A's barriers publish the allocation)
 
     // ---- constant B operands: the folded Gram tensor in both GEMM views, split hi/lo ----
     //   B1[n = bcd][k = A]          = S[A,b,c,d]
@@ -920,18 +929,21 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             }
             __syncthreads();
         }
-        __syncthreads();   // tiles dead before q (vectorised layout [R/4][128] float4) overwrites the region
-#pragma unroll
-        for (int r4 = 0; r4 < RH / 4; ++r4)
-            reinterpret_cast<float4*>(q_s)[(role * (RH / 4) + r4) * C::THREADS + row] =
-                make_float4(acc[4 * r4], acc[4 * r4 + 1], acc[4 * r4 + 2], acc[4 * r4 + 3]);
+        // q -> tensor memory: this thread's 68 rows into columns COL_Q + 68*role .. of its sample's lane
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t qdst = *tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + C::COL_Q + role * RH;
+        static_assert(RH == 68, "two 32-column stores and one 4-column store");
+        tmem_store32(qdst, acc);
+        tmem_store32(qdst + 32, acc + 32);
+        tmem_store4(qdst + 64, acc + 64);
+        tmem_store_wait();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const QVec4 qa{reinterpret_cast<const float4*>(q_s) + row, C::THREADS};
+    const QTmem qa{lane_addr + C::COL_Q};
 
     // ---- phase B ----
     float p[C::NP];
