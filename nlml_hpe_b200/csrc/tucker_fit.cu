@@ -768,12 +768,10 @@ struct TcFitCfg {
     static constexpr int KV = 40, NV = 96;            // V GEMM: K = (c,D) (36 -> 40), N = (A,b) (90 -> 96)
     static constexpr int B1_BYTES = ttc::op_bytes(N1, K1);    // 14336 per plane
     static constexpr int BV_BYTES = ttc::op_bytes(NV, KV);    // 15360 per plane
-    static constexpr int A1_BYTES = ttc::op_bytes(128, K1);   // 8192 per plane
     static constexpr int AV_BYTES = ttc::op_bytes(128, KV);   // 20480 per plane
     static constexpr int OFF_B1 = 0;                                   // hi, lo
     static constexpr int OFF_BV = OFF_B1 + 2 * B1_BYTES;               // hi, lo
-    static constexpr int OFF_A1 = OFF_BV + 2 * BV_BYTES;               // hi, lo
-    static constexpr int OFF_AV = OFF_A1 + 2 * A1_BYTES;               // hi, lo
+    static constexpr int OFF_AV = OFF_BV + 2 * BV_BYTES;               // hi, lo   (the T GEMM's A operand lives in tensor memory)
     // q lives in TENSOR MEMORY (columns COL_Q .. COL_Q+135 of each sample's lane): the 17 KB per warp and iteration that
     // both roles read would otherwise be 38 % of the SM's shared-memory traffic (the UMMA operand reads and the operand
     // stores share the same 128 B/clk).  The region below only holds the phase-A staging tiles.
@@ -784,7 +782,7 @@ struct TcFitCfg {
     static constexpr int NGX = 8 + 15;                                 // 8 gradient parts + role 1's partial GR, GP, GY
     static constexpr size_t SMEM_BYTES = OFF_GX + NGX * THREADS * 4;
     static constexpr int TMEM_COLS = 512;
-    static constexpr int COL_T = 0, COL_V = 224, COL_Q = 320;
+    static constexpr int COL_T = 0, COL_V = 224, COL_Q = 320, COL_A1 = 456;   // A1: the T GEMM's A operand (UU hi | lo, 2 x 16 columns)
 };
 
 // Half of T (3 of the 6 b's = 108 columns) -> partial GR[6], GP[6] and the 3 GY of those b's
@@ -839,8 +837,6 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
     uint8_t* b1_lo = b1_hi + C::B1_BYTES;
     uint8_t* bv_hi = tsm + C::OFF_BV;
     uint8_t* bv_lo = bv_hi + C::BV_BYTES;
-    uint8_t* a1_hi = tsm + C::OFF_A1;
-    uint8_t* a1_lo = a1_hi + C::A1_BYTES;
     uint8_t* av_hi = tsm + C::OFF_AV;
     uint8_t* av_lo = av_hi + C::AV_BYTES;
     float* q_s = reinterpret_cast<float*>(tsm + C::OFF_Q);
@@ -971,24 +967,20 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         // before anybody evaluates a cosine; it runs underneath the feature computation.  (Named barrier 1: the 128
         // angle threads only.)
         if (role == 0) {
-            float UU[16];
+            // the UU operand goes to TENSOR MEMORY (one 32-column store: hi | lo), not through shared memory: no operand
+            // stores, no generic->async proxy fence, and the MMA reads A without touching the shared-memory ports
+            float UU[16], hl[32];
             sym_products<5>(u, UU);
             UU[15] = 0.f;
 #pragma unroll
-            for (int k4 = 0; k4 < C::K1 / 4; ++k4) {
-                float h[4], l[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) ttc::split_tf32_fast(UU[4 * k4 + e], h[e], l[e]);
-                *reinterpret_cast<float4*>(a1_hi + ttc::op_offset(row, 4 * k4, C::K1)) = make_float4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<float4*>(a1_lo + ttc::op_offset(row, 4 * k4, C::K1)) = make_float4(l[0], l[1], l[2], l[3]);
-            }
-            ttc::fence_async_smem();
+            for (int k = 0; k < 16; ++k) ttc::split_tf32_fast(UU[k], hl[k], hl[16 + k]);
+            tmem_store32(lane_addr + C::COL_A1, hl);
+            tmem_store_wait();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (tid == 0 && a.dbg != 1) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                ttc::issue_gemm_3xtf32(tmem + C::COL_T, ttc::smem_u32(a1_hi), ttc::smem_u32(a1_lo), ttc::smem_u32(b1_hi),
-                                       ttc::smem_u32(b1_lo), C::K1, C::N1, true);
+                ttc::issue_gemm_3xtf32_ta(tmem + C::COL_T, tmem + C::COL_A1, ttc::smem_u32(b1_hi), ttc::smem_u32(b1_lo), C::K1, C::N1, true);
                 ttc::umma_commit_to(bar);
             }
         }

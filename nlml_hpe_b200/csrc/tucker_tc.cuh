@@ -47,6 +47,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// the same MMA with the A operand in TENSOR MEMORY (lane = row, 8 consecutive 32-bit columns = one K step)
+__device__ __forceinline__ void umma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit_to(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -98,6 +107,18 @@ __device__ __forceinline__ void issue_gemm_3xtf32(uint32_t tmem_d, uint32_t a_hi
         umma_tf32(tmem_d, dal, dbh, idesc, !(first && k0 == 0));   // small terms first
         umma_tf32(tmem_d, dah, dbl, idesc, 1);
         umma_tf32(tmem_d, dah, dbh, idesc, 1);
+    }
+}
+
+// 3xTF32 GEMM with the A operand in tensor memory: hi part in columns [a_tmem, a_tmem + K), lo part in the next K.
+__device__ __forceinline__ void issue_gemm_3xtf32_ta(uint32_t tmem_d, uint32_t a_tmem, uint32_t b_hi, uint32_t b_lo, int K, int N,
+                                                     bool first) {
+    const uint32_t idesc = make_idesc_tf32(128, N);
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        const uint64_t dbh = make_desc_noswz(b_hi, K, k0), dbl = make_desc_noswz(b_lo, K, k0);
+        umma_tf32_ta(tmem_d, a_tmem + K + k0, dbh, idesc, !(first && k0 == 0));   // lo * hi: small terms first
+        umma_tf32_ta(tmem_d, a_tmem + k0, dbl, idesc, 1);
+        umma_tf32_ta(tmem_d, a_tmem + k0, dbh, idesc, 1);
     }
 }
 
