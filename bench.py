@@ -327,7 +327,7 @@ def run_b200(args):
                      "peak_source": peaks["source"] + " (TF32 dense = half of the measured sustained bf16 rate)",
                      "note": "issued TF32 tensor work: per sample-iteration two 3xTF32 GEMM rows (128x224x16 and 128x96x40 per 128 "
                              f"samples, 3 MMAs per MAC) = {TUCKER_TC_FLOP_PER_POSE / 1e6:.1f} MFLOP/pose at T=3000. The tensor pipe is NOT "
-                             "the binding unit of this kernel (ncu: tensor pipe ~20-25 % active): each iteration is a serial chain "
+                             "the binding unit of this kernel (ncu: tensor pipe ~31 % active): each iteration is a serial chain "
                              "features -> operand rows -> GEMMs -> tcgen05.ld -> gradient -> step, and the kernel is bound by that "
                              "chain's latency plus the FP32 work left on the CUDA cores (roofline_fp32)."},
         "roofline_fp32": {"bound": "fp32_fma", "achieved": per_gpu_t * TUCKER_FLOP_PER_POSE / 1e12, "peak": fp32_peak,
