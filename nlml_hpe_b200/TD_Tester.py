@@ -41,9 +41,12 @@ def _as_numpy(a, dtype):
 def _fitter(W, params_y, params_p, params_r, device=None):
     W = _as_numpy(W, np.float32)
     rows = [_as_numpy(p, np.float64) for p in (params_y, params_p, params_r)]
+    # content key of the constants: the reference passes W on every call (TD_Inference.py:56), so this runs per
+    # sample -- two vector reductions over the 758 KB instead of a cryptographic hash (0.7 ms)
+    w64 = W.reshape(-1).view(np.uint32).astype(np.uint64, copy=False) if W.size % 2 else W.reshape(-1).view(np.uint64)
     h = hashlib.blake2b(digest_size=16)
     h.update(str(W.shape).encode())
-    h.update(W.tobytes())
+    h.update(np.array([np.add.reduce(w64), np.bitwise_xor.reduce(w64), w64[:: max(1, w64.size // 257)].sum()], dtype=np.uint64).tobytes())
     for r in rows:
         h.update(r.tobytes())
     key = (h.hexdigest(), str(device))
