@@ -882,6 +882,8 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         *reinterpret_cast<float*>(bv_lo + ttc::op_offset(n, k, C::KV)) = lo;
     }
 
+    ttc::fence_async_smem();   // every thread's share of the B operand writes -> visible to the tensor core's async proxy
+                               // (phase A's barriers order it before the first MMA)
     // ---- phase A: q[r] = sum_f W2[r][f] * x[f]; the two threads of a sample take half of the rows r each ----
     {
         constexpr int RH = C::RPAD / 2;   // 68 rows per role
