@@ -556,7 +556,12 @@ extern "C" int nlml_mlp_plan_create(const float* const* weights, const float* co
     DeviceGuard guard(device);
     if (!guard.ok) return set_error(NLML_E_NO_DEVICE, "cudaSetDevice(%d) failed", device);
 
-    auto* pl = new nlml_mlp_plan();
+    // owned until the end of this function: every early error return below frees the plan and its device buffers
+    struct PlanOwner {
+        nlml_mlp_plan* p;
+        ~PlanOwner() { if (p) nlml_mlp_plan_destroy(p); }
+    } owner{new nlml_mlp_plan()};
+    nlml_mlp_plan* pl = owner.p;
     pl->device = device;
     pl->input_size = in_dims[0];
     pl->latent = latent;
@@ -599,7 +604,7 @@ extern "C" int nlml_mlp_plan_create(const float* const* weights, const float* co
         for (int li = 0; li < kHead; ++li) pl->tc[head_t(h, li)] = pl->tc[head_t(0, li)];
     for (int t = 0; t < kNumT; ++t)
         if (pl->tc[t])
-            if (int rc = prepare_tc_layer(pl, t, weights[t])) { nlml_mlp_plan_destroy(pl); return rc; }
+            if (int rc = prepare_tc_layer(pl, t, weights[t])) return rc;
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg2::SMEM_BYTES));
     if (const char* e = std::getenv("NLML_TC_1CTA")) pl->two_cta = !(e[0] == '1');
     if (const char* e = std::getenv("NLML_TC_GROUP")) pl->tc_group = std::max(1, std::atoi(e));
@@ -623,6 +628,7 @@ extern "C" int nlml_mlp_plan_create(const float* const* weights, const float* co
         if (pl->tc[head_t(0, li + 1)]) pl->plane_width[li & 1] = std::max(pl->plane_width[li & 1], w3);
     }
     for (int i = 0; i < 2; ++i) pl->f32_width[i] = std::max<size_t>(pl->f32_width[i], 4);
+    owner.p = nullptr;
     *plan_out = pl;
     return 0;
 }

@@ -1348,7 +1348,12 @@ extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, i
     DeviceGuard guard(device);
     if (!guard.ok) return set_error(NLML_E_NO_DEVICE, "cudaSetDevice(%d) failed", device);
 
-    auto* pl = new nlml_tucker_plan();
+    // owned until the end of this function: every early error return below frees the plan and its device buffers
+    struct PlanOwner {
+        nlml_tucker_plan* p;
+        ~PlanOwner() { if (p) nlml_tucker_plan_destroy(p); }
+    } owner{new nlml_tucker_plan()};
+    nlml_tucker_plan* pl = owner.p;
     pl->device = device;
     pl->ri = r_id; pl->ry = r_y; pl->rp = r_p; pl->rr = r_r; pl->F = F;
     pl->R = r_id * r_y * r_p * r_r;
@@ -1357,7 +1362,6 @@ extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, i
     pl->nBCD = tri(r_y) * tri(r_p) * tri(r_r);
     pl->nBCDp = (pl->nBCD + 31) / 32 * 32;
     if (pl->nBCD > kMaxBCD) {
-        delete pl;
         return set_error(NLML_E_UNSUPPORTED, "angle-mode ranks (%d,%d,%d) give %d folded entries per identity pair; limit %d",
                          r_y, r_p, r_r, tri(r_y) * tri(r_p) * tri(r_r), kMaxBCD);
     }
@@ -1366,7 +1370,11 @@ extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, i
     pl->num_sms = prop.multiProcessorCount;
 
     const size_t w_bytes = sizeof(float) * (size_t)pl->R * F;
-    double* M = nullptr;
+    struct DevScratch {   // the float64 Gram matrix is only needed while the folded tensor is built
+        double* p = nullptr;
+        ~DevScratch() { cudaFree(p); }
+    } gram;
+    double*& M = gram.p;
     NLML_CUDA(cudaMalloc(&pl->W2, w_bytes));
     NLML_CUDA(cudaMalloc(&pl->S, sizeof(float) * (size_t)pl->nBCD * pl->NAP));
     NLML_CUDA(cudaMalloc(&pl->St, sizeof(float) * (size_t)pl->nA * pl->nBCDp));
@@ -1383,7 +1391,6 @@ extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, i
         NLML_CUDA(cudaDeviceSynchronize());
         pl->launches += 2;
     }
-    NLML_CUDA(cudaFree(M));
 
     TuckerArgs& a = pl->base;
     a.W2 = pl->W2; a.S = pl->S; a.St = pl->St;
@@ -1417,6 +1424,7 @@ extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, i
         NLML_CUDA(cudaFuncSetAttribute(tucker_fit_cta_kernel<kCtaThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)pl->cta_smem));
     }
+    owner.p = nullptr;
     *plan_out = pl;
     return 0;
 }
