@@ -197,6 +197,18 @@ __device__ __forceinline__ float act_apply(float v, int act) {
     return v;
 }
 
+// Two FP32 values -> packed FP16 (hi, lo) words, value 0 in the low half.  Packed conversions (one F2FP per pair, the
+// way back through HADD2.F32) instead of six scalar F2F per pair: the scalar form runs at a quarter of the ALU rate
+// and made the epilogues of the short-K layers conversion-bound (ncu: F2F 10 % of the samples of the heads' layers).
+// Same roundings (cvt.rn), bit-identical planes.
+__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // CL = CTAs per cluster (1 or 2).  With CL = 2 the two CTAs of a cluster work on M-tiles (2p, 2p+1) of the same
 // N-tile: each loads its own A planes and HALF of the W tile, multicast into both CTAs' shared memory, which cuts
 // the L2->SMEM operand traffic per MMA by a third (the wide layers are L2-bandwidth bound at 128x256 tiles).
@@ -408,10 +420,7 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
                                 const float4 w0 = neck_whs[h * kNeckHeadW + j0 + 2 * e], w1 = neck_whs[h * kNeckHeadW + j0 + 2 * e + 1];
                                 const float v0 = fmaxf(fmaf(l2, w0.z, fmaf(l1, w0.y, fmaf(l0, w0.x, w0.w))), 0.f);
                                 const float v1 = fmaxf(fmaf(l2, w1.z, fmaf(l1, w1.y, fmaf(l0, w1.x, w1.w))), 0.f);
-                                const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-                                const __half q0 = __float2half_rn(v0 - __half2float(h0)), q1 = __float2half_rn(v1 - __half2float(h1));
-                                hi[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                                lo[e] = (uint32_t)__half_as_ushort(q0) | ((uint32_t)__half_as_ushort(q1) << 16);
+                                split_pair(v0, v1, hi[e], lo[e]);
                             }
                             __half* dh = (h == 0 ? a.neck_hi[0] : (h == 1 ? a.neck_hi[1] : a.neck_hi[2])) + row * kNeckHeadW + j0;
                             __half* dl = (h == 0 ? a.neck_lo[0] : (h == 1 ? a.neck_lo[1] : a.neck_lo[2])) + row * kNeckHeadW + j0;
@@ -455,11 +464,7 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
                         uint32_t hi[16], lo[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const __half h0 = __float2half_rn(y[2 * j]), h1 = __float2half_rn(y[2 * j + 1]);
-                            const __half l0 = __float2half_rn(y[2 * j] - __half2float(h0));
-                            const __half l1 = __float2half_rn(y[2 * j + 1] - __half2float(h1));
-                            hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                            lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                            split_pair(y[2 * j], y[2 * j + 1], hi[j], lo[j]);
                         }
                         __half* dh = Yhi + row * a.ldy + n0 + c0;
                         __half* dl = Ylo + row * a.ldy + n0 + c0;
@@ -687,11 +692,7 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
                         uint32_t hi[16], lo[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const __half h0 = __float2half_rn(y[2 * j]), h1 = __float2half_rn(y[2 * j + 1]);
-                            const __half l0 = __float2half_rn(y[2 * j] - __half2float(h0));
-                            const __half l1 = __float2half_rn(y[2 * j + 1] - __half2float(h1));
-                            hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                            lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                            split_pair(y[2 * j], y[2 * j + 1], hi[j], lo[j]);
                         }
                         __half* dh = Yhi + row * a.ldy + n0 + c0;
                         __half* dl = Ylo + row * a.ldy + n0 + c0;
@@ -757,10 +758,7 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
         uint32_t h[2], l[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const __half h0 = __float2half_rn(f[2 * j]), h1 = __float2half_rn(f[2 * j + 1]);
-            const __half l0 = __float2half_rn(f[2 * j] - __half2float(h0)), l1 = __float2half_rn(f[2 * j + 1] - __half2float(h1));
-            h[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-            l[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            split_pair(f[2 * j], f[2 * j + 1], h[j], l[j]);
         }
         *reinterpret_cast<uint2*>(Xhi + row * Kp + k) = make_uint2(h[0], h[1]);
         *reinterpret_cast<uint2*>(Xlo + row * Kp + k) = make_uint2(l[0], l[1]);
@@ -932,10 +930,7 @@ __global__ void __launch_bounds__(kNarrowThreads) neck_kernel(const __grid_const
                 uint32_t hi[4], lo[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const __half h0 = __float2half_rn(y[2 * j]), h1 = __float2half_rn(y[2 * j + 1]);
-                    const __half l0 = __float2half_rn(y[2 * j] - __half2float(h0)), l1 = __float2half_rn(y[2 * j + 1] - __half2float(h1));
-                    hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                    lo[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                    split_pair(y[2 * j], y[2 * j + 1], hi[j], lo[j]);
                 }
                 *reinterpret_cast<uint4*>(a.Hhi[z] + row * HW + j0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 *reinterpret_cast<uint4*>(a.Hlo[z] + row * HW + j0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
