@@ -207,11 +207,11 @@ def cpu_baseline_mlp(art, cores, n=16384, reps=3):
     rows = tuple(art[f"optimized_{k}"][0:3] for k in ("yaw", "pitch", "roll"))
     X = synthetic.make_features(n, art["W"], *rows, U_id=art["U_id"], seed=1234)
     torch.set_num_threads(cores)
-    mlp_oracle.forward(*sds, X[:1024])
+    mlp_oracle.forward(*sds, X[:1024], threads=cores)
     best = 1e30
     for _ in range(reps):
         t0 = time.perf_counter()
-        mlp_oracle.forward(*sds, X)
+        mlp_oracle.forward(*sds, X, threads=cores)
         best = min(best, time.perf_counter() - t0)
     return {"value": n / best, "unit": "poses/s", "cores": cores, "kind": "port",
             "sample": f"{n} vectors in one batched call, best of {reps}, torch CPU f32 ({cores} threads), "

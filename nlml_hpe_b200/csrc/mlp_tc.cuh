@@ -221,7 +221,9 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
     constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
     constexpr int HALF = BN / 2;   // columns owned by one epilogue warp
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array (a round trip through uintptr_t makes the compiler
+    // lose the address space: the epilogue's bias reads became generic LD.E instead of LDS)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* stage_base = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
     uint64_t* full = bars;                    // [STAGES]  operand stage landed
@@ -545,7 +547,9 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
     using C = Cfg2;
     constexpr int BN = C::BN, HALF = BN / 2;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array (a round trip through uintptr_t makes the compiler
+    // lose the address space: the epilogue's bias reads became generic LD.E instead of LDS)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* stage_base = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
     uint64_t* full = bars;                    // [STAGES]  (leader's copy is the live one) both CTAs' operand stage landed

@@ -35,8 +35,19 @@ def forward(encoder_sd, yaw_sd, pitch_sd, roll_sd, X, dtype=torch.float32, threa
     dtype=float32 is the reference arithmetic (torch.nn.Linear on CPU); float64 gives the
     error-budget reference used to state tolerances.
     """
-    if threads is not None:
-        torch.set_num_threads(threads)
+    # As a CHECKER (threads=None) the forward runs single-threaded: on the GPU boxes' host the multi-threaded f32 GEMM
+    # of torch CPU was observed to return slightly different rows (2.9e-3 degrees on every other row) in about one
+    # process out of ten (scripts/dbg_mlp_chunk2.py), which made a parity test flaky.  bench.py's CPU baseline passes
+    # `threads` explicitly and keeps all host threads.
+    prev_threads = torch.get_num_threads()
+    torch.set_num_threads(1 if threads is None else threads)
+    try:
+        return _forward_impl(encoder_sd, yaw_sd, pitch_sd, roll_sd, X, dtype)
+    finally:
+        torch.set_num_threads(prev_threads)
+
+
+def _forward_impl(encoder_sd, yaw_sd, pitch_sd, roll_sd, X, dtype):
     with torch.no_grad():
         h = _t(X, dtype)
         for li, key in enumerate(ENCODER_KEYS):
@@ -58,16 +69,21 @@ def forward(encoder_sd, yaw_sd, pitch_sd, roll_sd, X, dtype=torch.float32, threa
 
 
 def latent(encoder_sd, X, dtype=torch.float32):
-    """Encoder output [B,9] only (for intermediate-stage checks)."""
-    with torch.no_grad():
-        h = _t(X, dtype)
-        for li, key in enumerate(ENCODER_KEYS):
-            h = F.linear(h, _t(encoder_sd[key + ".weight"], dtype), _t(encoder_sd[key + ".bias"], dtype))
-            if li < 4:
-                h = torch.relu(h)
-            elif li == 4:
-                h = torch.tanh(h)
-        return h.numpy()
+    """Encoder output [B,9] only (for intermediate-stage checks); single-threaded like the checker forward."""
+    prev_threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        with torch.no_grad():
+            h = _t(X, dtype)
+            for li, key in enumerate(ENCODER_KEYS):
+                h = F.linear(h, _t(encoder_sd[key + ".weight"], dtype), _t(encoder_sd[key + ".bias"], dtype))
+                if li < 4:
+                    h = torch.relu(h)
+                elif li == 4:
+                    h = torch.tanh(h)
+            return h.numpy()
+    finally:
+        torch.set_num_threads(prev_threads)
 
 
 # ---- feature-side pre / post steps of the reference's callers (SURVEY.md section 8f row 3) ----------------------
