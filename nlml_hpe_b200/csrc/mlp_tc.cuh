@@ -371,13 +371,15 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
+                // the next 32-column load is in flight while the previous one is added (two register buffers)
+                uint32_t v[2][32];
+                tmem_ld32(taddr, v[0]);
 #pragma unroll
                 for (int c0 = 0; c0 < HALF; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + c0, v);
                     tmem_ld_wait();
+                    if (c0 + 32 < HALF) tmem_ld32(taddr + c0 + 32, v[((c0 >> 5) + 1) & 1]);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+                    for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[(c0 >> 5) & 1][j]);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -662,13 +664,15 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
+                // the next 32-column load is in flight while the previous one is added (two register buffers)
+                uint32_t v[2][32];
+                tmem_ld32(taddr, v[0]);
 #pragma unroll
                 for (int c0 = 0; c0 < HALF; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + c0, v);
                     tmem_ld_wait();
+                    if (c0 + 32 < HALF) tmem_ld32(taddr + c0 + 32, v[((c0 >> 5) + 1) & 1]);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[j]);
+                    for (int j = 0; j < 32; ++j) sum[c0 + j] += __uint_as_float(v[(c0 >> 5) & 1][j]);
                 }
                 tc_fence_before();
                 __syncwarp();
