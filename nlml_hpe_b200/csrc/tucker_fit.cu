@@ -1042,14 +1042,16 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             NLML_TSTAMP(3);   // wait for the GEMM
             if (a.dbg != 2) {
+                uint32_t vb[2][32];   // the next 32 columns are in flight while these are reduced
+                tmem_load32_async(lane_addr + C::COL_V, vb[0]);
 #pragma unroll
                 for (int ci = 0; ci < C::NV / 32; ++ci) {
-                    float v[32];
-                    tmem_load32(lane_addr + C::COL_V + 32 * ci, v);
+                    tmem_load_wait();
+                    if (ci + 1 < C::NV / 32) tmem_load32_async(lane_addr + C::COL_V + 32 * (ci + 1), vb[(ci + 1) & 1]);
 #pragma unroll
                     for (int x = 0; x < 32; ++x) {
                         const int n = 32 * ci + x;
-                        if (n < 90) GU[n / 6] = fmaf(v[x], YY[n % 6], GU[n / 6]);
+                        if (n < 90) GU[n / 6] = fmaf(__uint_as_float(vb[ci & 1][x]), YY[n % 6], GU[n / 6]);
                     }
                 }
             }
