@@ -29,7 +29,12 @@ constexpr int BM = 128;   // samples per tile (TMEM lanes)
 constexpr int BK = 64;    // fp16 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kEpilogueWarps = 8;
-constexpr int kThreads = 32 * (2 + kEpilogueWarps);   // TMA warp, MMA warp, 8 promotion/epilogue warps
+// Three warp groups: group 0 = TMA warp, MMA warp (+ two idle warps), groups 1 and 2 = the eight promotion / epilogue
+// warps.  With ten warps on a uniform budget one SM sub-partition holds three of them and every thread is capped at 168
+// registers (the epilogue keeps 128 FP32 partial sums per thread and spilled); setmaxnreg hands group 0's registers over.
+constexpr int kFirstEpilogueWarp = 4;
+constexpr int kThreads = 32 * (kFirstEpilogueWarp + kEpilogueWarps);
+constexpr int kProducerRegs = 40, kEpilogueRegs = 232;   // (40 + 232 + 232) * 32 <= 16384 registers per sub-partition
 
 // fused neck epilogue (BN = 64 only): W5 [9][64], B5 [12], head rows (w0,w1,w2,b) [3][128] float4, latent exchange [2][9][128]
 constexpr int kNeckLatent = 9, kNeckHeadW = 128;
@@ -262,8 +267,8 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if constexpr (BN == 64) {
-        if (a.neck && warp >= 2) {   // the epilogue warps stage the narrow layers' constants once per CTA
-            const int e = threadIdx.x - 64, ne = 32 * kEpilogueWarps;
+        if (a.neck && warp >= kFirstEpilogueWarp) {   // the epilogue warps stage the narrow layers' constants once per CTA
+            const int e = threadIdx.x - 32 * kFirstEpilogueWarp, ne = 32 * kEpilogueWarps;
             for (int i = e; i < kNeckLatent * 64; i += ne) neck_w5s[i] = __ldg(a.neck_w5 + i);
             for (int i = e; i < kNeckLatent; i += ne) neck_b5s[i] = __ldg(a.neck_b5 + i);
             for (int i = e; i < 3 * kNeckHeadW; i += ne) {
@@ -277,6 +282,7 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
 
     if (warp == 0) {
         // ===== TMA producer =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));   // register hand-over, see kThreads
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (long long t = first; t < num_tiles; t += step) {
@@ -304,6 +310,7 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));   // register hand-over, see kThreads
         // The tensor core's FP32 accumulate truncates instead of rounding, which biases long accumulation
         // chains (measured: 3.6e-3 deg at the output when all K/16*3 steps of a layer went into one TMEM
         // accumulator).  So one TMEM accumulator only ever sums ONE k-block (4 k-steps x 3 passes = 12 MMAs);
@@ -340,9 +347,12 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
                 }
             }
         }
+    } else if (warp < kFirstEpilogueWarp) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));   // idle warps of group 0
     } else {
-        // ===== epilogue warps: TMEM lane quadrant = warp id % 4, column half = (warp - 2) / 4 =====
-        const int quad = warp & 3, half = (warp - 2) >> 2;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpilogueRegs));
+        // ===== epilogue warps: TMEM lane quadrant = warp id % 4, column half = (warp - 4) / 4 =====
+        const int quad = warp & 3, half = (warp - kFirstEpilogueWarp) >> 2;
         int acc = 0; uint32_t acc_phase = 0;
         int tile_parity = 0;
         for (long long t = first; t < num_tiles; t += step) {
@@ -355,8 +365,8 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
             float* __restrict__ Yf32 = a.Yf32[z];
             __half* __restrict__ Yhi = a.Yhi[z];
             __half* __restrict__ Ylo = a.Ylo[z];
-            float* bias_s = bias_all + (warp - 2) * HALF;   // this warp's slice of the bias, read back as broadcasts
-            float* dotw_s = dotw_all + (warp - 2) * HALF;
+            float* bias_s = bias_all + (warp - kFirstEpilogueWarp) * HALF;   // this warp's slice of the bias, read back as broadcasts
+            float* dotw_s = dotw_all + (warp - kFirstEpilogueWarp) * HALF;
             const float* __restrict__ dot_w = a.dot_w[z];
             __syncwarp();
             for (int j = lane; j < HALF; j += 32) {
@@ -587,6 +597,7 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));   // register hand-over, see kThreads
         // ===== TMA producer (both CTAs): own A rows, own half of the W tile; bytes are counted on the leader's barrier =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
@@ -608,6 +619,7 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
             }
         }
     } else if (warp == 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));   // register hand-over, see kThreads
         // ===== MMA issuer (leader CTA only; one instruction drives both SMs' tensor cores) =====
         if (leader && lane == 0) {
             constexpr uint32_t idesc = make_idesc_f16(2 * BM, BN);
@@ -639,9 +651,12 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
                 }
             }
         }
+    } else if (warp < kFirstEpilogueWarp) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));   // idle warps of group 0
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpilogueRegs));
         // ===== epilogue warps of this CTA: rows of its own 128-row half =====
-        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int quad = warp & 3, half = (warp - kFirstEpilogueWarp) >> 2;
         int acc = 0; uint32_t acc_phase = 0;
         for (long long t = first; t < num_tiles; t += step) {
             const int z = (int)(t / tiles_per_problem);
@@ -653,7 +668,7 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
             float* __restrict__ Yf32 = a.Yf32[z];
             __half* __restrict__ Yhi = a.Yhi[z];
             __half* __restrict__ Ylo = a.Ylo[z];
-            float* bias_s = bias_all + (warp - 2) * HALF;   // this warp's slice of the bias, read back as broadcasts
+            float* bias_s = bias_all + (warp - kFirstEpilogueWarp) * HALF;   // this warp's slice of the bias, read back as broadcasts
             __syncwarp();
             for (int j = lane; j < HALF; j += 32) bias_s[j] = __ldg(bias + n0 + j);
             __syncwarp();
