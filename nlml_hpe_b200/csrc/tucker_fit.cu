@@ -1313,9 +1313,12 @@ int host_pipeline(nlml_tucker_plan* pl, const float* X_host, int64_t N, int64_t 
         pending[slot].n = 0;
         return 0;
     };
-    int slot = 0;
-    for (int64_t s0 = 0; s0 < N; s0 += pl->chunk, slot ^= 1) {
-        const int64_t n = std::min<int64_t>(pl->chunk, N - s0);
+    // Chunk sizes ramp up (1, 2, 4 waves, then the full 8): only the first, small copy is exposed; every later copy is
+    // shorter than the kernel of the chunk before it (a wave is ~2 ms of PCIe against ~7 ms of fit at T = 3000).
+    int slot = 0, k = 0;
+    const int64_t wave = (int64_t)pl->num_sms * TcFitCfg::THREADS;
+    for (int64_t s0 = 0, n = 0; s0 < N; s0 += n, slot ^= 1, ++k) {
+        n = std::min<int64_t>(k < 3 ? std::min<int64_t>(pl->chunk, wave << k) : pl->chunk, N - s0);
         cudaStream_t st = pl->streams[slot];
         if (int rc = drain(slot)) return rc;   // also makes the reuse of this slot's device buffers safe
         if (ldx == pl->F)   // contiguous rows: one linear DMA instead of a pitched copy
@@ -1464,8 +1467,10 @@ extern "C" int nlml_tucker_fit_host_f32(nlml_tucker_plan* pl, const float* X_hos
     if (N < 0 || ldx < pl->F || ldp < 3 + pl->ri || iters < 0) return set_error(NLML_E_INVALID, "bad sizes");
     DeviceGuard guard(pl->device);
     const int np = 3 + pl->ri;
+    // every chunk runs the kernel the whole batch would get (the first chunks of the ramp are below the cross-over)
+    const int hint = (pl->fast && N >= kTcCrossover) ? 5 : 0;
     return host_pipeline(pl, X_host, N, ldx, P_out_host, ldp, [&](const float* x, int64_t n, float* p, cudaStream_t st) {
-        return launch_fit(pl, x, n, pl->F, iters, lr, clip, p, np, 0, st);
+        return launch_fit(pl, x, n, pl->F, iters, lr, clip, p, np, hint, st);
     });
 }
 
