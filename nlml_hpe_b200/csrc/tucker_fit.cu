@@ -1,17 +1,20 @@
-// Batched fixed-iteration Tucker fit for sm_100a.
+// Batched Tucker fit for sm_100a: the fixed-iteration fit of TD_Tester.optimize_with_sgd
+// (/root/reference/TD_Tester.py:127-159) and the converged fit TD_Tester.Test searches for (:191-199), for a whole
+// batch of feature vectors.  Same arithmetic everywhere (tucker_math.h); kernels chosen by batch size and ranks:
 //
-// Replaces TD_Tester.optimize_with_sgd (/root/reference/TD_Tester.py:127-159) for a whole batch of
-// feature vectors.  Two kernels, same arithmetic (tucker_math.h), chosen by batch size:
-//
-//   tucker_fit_tps_kernel  thread-per-sample, ranks fixed at compile time (5,3,3,3 = the shipped /
-//                          configured ranks, configs/config_TD_main.yaml:8-13).  A CTA owns THREADS
-//                          consecutive samples: phase A streams their rows of X once from HBM and
-//                          leaves q = W2 x in shared memory; phase B runs all T iterations with p, the
-//                          monomials and the gradient in registers, the folded Gram tensor S broadcast
-//                          from shared memory.  No global memory traffic between iterations.
-//   tucker_fit_cta_kernel  CTA-per-sample, ranks at run time (enlarged cores, BASELINE.json config 5)
-//                          and the small-N / single-image case of TD_Inference.py, where latency of
-//                          the 3000-step chain matters more than throughput.
+//   tucker_fit_tc_kernel   large batches (the default from 37 888 samples): 128 samples per CTA, two threads per
+//                          sample; the two contractions with the folded Gram tensor run as 3xTF32 tcgen05 GEMMs,
+//                          tensor memory holds the accumulators, each sample's q = W2 x and one MMA operand.
+//   tucker_fit_tps_kernel  thread-per-sample, FP32 only, ranks fixed at compile time (5,3,3,3 = the shipped /
+//                          configured ranks, configs/config_TD_main.yaml:8-13).  A CTA owns THREADS consecutive
+//                          samples: phase A streams their rows of X once from HBM and leaves q in shared memory;
+//                          phase B runs all T iterations with p, the monomials and the gradient in registers, the
+//                          folded Gram tensor S broadcast from shared memory.  Its SOLVE variant runs the damped-Newton
+//                          converged fit instead of the T iterations.
+//   tucker_fit_wps_kernel  warp-per-sample: small batches and the single-image case of TD_Inference.py, where the
+//                          latency of the 3000-step chain matters more than throughput.
+//   tucker_fit_cta_kernel  CTA-per-sample, ranks at run time (enlarged cores, BASELINE.json config 5).
+// No kernel touches global memory between iterations.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -1223,7 +1226,7 @@ int launch_fit(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int
     if (const char* e = std::getenv("NLML_TUCKER_DBG")) a.dbg = std::atoi(e);
     // crossover: below ~one thread-per-sample wave the 3000-step chain is latency bound and the
     // CTA-per-sample kernel finishes sooner
-    // large batches: the tensor-core iteration kernel (1.45 M poses/s) beats the FP32 thread-per-sample kernel (0.92 M)
+    // large batches: the tensor-core iteration kernel (2.6 M poses/s) beats the FP32 thread-per-sample kernel (0.92 M)
     const bool use_tc = pl->fast && (hint == 5 || (hint == 0 && N >= kTcCrossover));
     const bool use_tps = pl->fast && !use_tc && (hint == 1 || hint == 4 || (hint == 0 && N >= kWpsCrossover));
     const bool use_wps = pl->fast && !use_tc && (hint == 3 || (hint == 0 && N < kWpsCrossover));
