@@ -131,6 +131,17 @@ def test_host_path_equals_device_path(fitter, X1k):
     assert np.array_equal(fitter.fit_host(pinned, 200), dev)
 
 
+def test_host_path_ramped_chunks(fitter, X1k):
+    """Batches above one wave go through the host pipeline in chunks of 1, 2, 4, 8 waves: same kernel, same bits as
+    the device-resident call, for the fixed-iteration fit and the converged solve."""
+    X = np.tile(X1k, (60, 1))[:59_999]                      # 18 944 + 37 888 + 3 167 rows
+    dev = fitter.fit(_gpu(X), 40).cpu().numpy()
+    assert np.array_equal(fitter.fit_host(X, 40), dev)
+    assert np.array_equal(dev[:1000], dev[1000:2000])       # periodic input, periodic output
+    sdev = fitter.solve(_gpu(X)).cpu().numpy()
+    assert np.array_equal(fitter.solve_host(X), sdev)
+
+
 def test_reference_entry_points(art, rows, X1k, tucker_golden, cuda_lib):
     """TD_Tester.optimize_with_sgd / Test with the reference's signatures and conventions."""
     from nlml_hpe_b200 import TD_Tester
