@@ -208,8 +208,9 @@ struct nlml_mlp_plan {
     bool tc_tail = true;   // heads' last two layers on the tensor cores (NLML_TC_TAIL=0: CUDA-core head_tail_kernel)
     bool two_cta = true;   // 256-wide layers: cta_group::2 kernel (false: 1-CTA MMAs with W multicast; NLML_TC_1CTA=1)
     int input_size = 0, latent = 0, head_in = 0;
-    int64_t chunk = 4 * 148 * 128;  // samples per pass: 4 x 148 M-tiles = whole waves of the persistent GEMMs; the per-launch
-                                    // fixed costs of the 9 kernels amortise over it (1 wave: 42.1, 4 waves: 47.5 M poses/s)
+    int64_t chunk = 8 * 148 * 128;  // samples per pass: 8 x 148 M-tiles = whole waves of the persistent GEMMs; the per-launch
+                                    // fixed costs of the 9 kernels amortise over it (final kernels, per 1M samples:
+                                    // 4 waves 16.9 ms, 8 waves 16.5 ms, 16 waves 16.5 ms; workspaces 2.6 GB at 8)
     size_t f32_width[2] = {0, 0}, plane_width[2] = {0, 0};
     Workspace ws[2];
     int num_sms = 148;
