@@ -290,3 +290,15 @@ def test_solve_full_size_1M(fitter, art, rows):
     torch.cuda.synchronize()
     small = fitter.solve(base)
     assert torch.isfinite(P).all() and torch.equal(P[:4096], small) and torch.equal(P[4096 * 200: 4096 * 201], small)
+
+
+def test_solve_synthetic_core(rows, cuda_lib):
+    """BASELINE.json config 2 core: converged solve vs the float64 restatement (well conditioned: far below the budget)."""
+    from nlml_hpe_b200 import synthetic
+    from nlml_hpe_b200.tucker import TuckerFitter
+    G = synthetic.synthetic_core((5, 3, 3, 3), 1404, seed=7)
+    Xg = synthetic.make_features(128, G, *rows, U_id=None, seed=4321)
+    P = TuckerFitter(G, *rows, device="cuda:0").solve(_gpu(Xg)).cpu().numpy()
+    ref, _, _ = tucker_oracle.lm_fit(G, Xg, *rows)
+    d = np.abs(P[:, :3] - ref[:, :3]).max(1) * DEG
+    assert d.max() < 2e-3 and np.median(d) < 2e-4
