@@ -119,6 +119,9 @@ int nlml_mlp_forward_host_f32(nlml_mlp_plan* plan, const float* X_host, int64_t 
  * Tensor-core path only (NLML_E_UNSUPPORTED after nlml_mlp_set_path(plan, 1)). */
 int nlml_mlp_forward_landmarks_f32(nlml_mlp_plan* plan, const float* LM_dev, int64_t N, int64_t ldx,
                                    float* YPR_out_dev, void* stream);
+/* The same with HOST buffers (MediaPipe delivers its landmarks on the host), pipelined like nlml_mlp_forward_host_f32. */
+int nlml_mlp_forward_landmarks_host_f32(nlml_mlp_plan* plan, const float* LM_host, int64_t N, int64_t ldx,
+                                        float* YPR_out_host);
 /* nlml_pose_postprocess_f64: YPR_dev float32 [N][3] radians -> DEG_out_dev float64 [N][3]:
  * round(np.degrees(t.item()), decimals) as NLML_HPE_Test.py:273 (decimals 3) / generatePose_on_video.py:210
  * (decimals 2) and, when 0 < ema_alpha < 1, the exponential smoothing over consecutive rows (= video frames) of

@@ -178,6 +178,20 @@ class CombinedAnglePredictionModel(nn.Module):
                                                            torch.cuda.current_stream(x.device).cuda_stream))
         return out
 
+    def predict_landmarks_host(self, landmarks, device=None):
+        """predict_landmarks() for raw landmarks in HOST memory (numpy / CPU tensor, [B,468,3] or [B,1404]) -> numpy [B,3]
+        radians; copies pipelined in the library."""
+        if isinstance(landmarks, torch.Tensor):
+            landmarks = landmarks.detach().numpy()
+        x = np.ascontiguousarray(landmarks, dtype=np.float32)
+        x = x.reshape(x.shape[0], -1)
+        plan = self._get_plan(_device_index(device))
+        if x.shape[1] != plan.input_size:
+            raise ValueError(f"expected [B,{plan.input_size}] (or [B,{plan.input_size // 3},3]), got {landmarks.shape}")
+        out = np.empty((x.shape[0], 3), dtype=np.float32)
+        _lib.check(plan.lib.nlml_mlp_forward_landmarks_host_f32(plan.h, x.ctypes.data, x.shape[0], x.shape[1], out.ctypes.data))
+        return out
+
     @staticmethod
     def to_degrees(angles, decimals=3, ema_alpha=None):
         """angles CUDA float32 [B,3] radians -> CUDA float64 [B,3]: round(np.degrees(t.item()), decimals) as the

@@ -18,7 +18,7 @@ EXPORTS = [
     "nlml_tucker_plan_create", "nlml_tucker_plan_destroy", "nlml_tucker_fit_f32",
     "nlml_tucker_fit_host_f32", "nlml_tucker_solve_f32", "nlml_tucker_solve_host_f32", "nlml_tucker_launch_count",
     "nlml_mlp_plan_create", "nlml_mlp_plan_destroy", "nlml_mlp_forward_f32",
-    "nlml_mlp_forward_host_f32", "nlml_mlp_forward_landmarks_f32", "nlml_pose_postprocess_f64", "nlml_mlp_latent_f32", "nlml_mlp_launch_count", "nlml_mlp_set_path",
+    "nlml_mlp_forward_host_f32", "nlml_mlp_forward_landmarks_f32", "nlml_mlp_forward_landmarks_host_f32", "nlml_pose_postprocess_f64", "nlml_mlp_latent_f32", "nlml_mlp_launch_count", "nlml_mlp_set_path",
     "nlml_measure_fp32_tflops", "nlml_measure_fp32_tflops_3reg", "nlml_debug_tf32_gemm",
 ]
 
@@ -58,6 +58,7 @@ def load():
     lib.nlml_mlp_forward_host_f32.argtypes = [vp, vp, i64, i64, vp]
     lib.nlml_mlp_latent_f32.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.nlml_mlp_forward_landmarks_f32.argtypes = [vp, vp, i64, i64, vp, vp]
+    lib.nlml_mlp_forward_landmarks_host_f32.argtypes = [vp, vp, i64, i64, vp]
     lib.nlml_pose_postprocess_f64.argtypes = [vp, i64, i32, ctypes.c_double, vp, vp]
     lib.nlml_mlp_launch_count.argtypes = [vp]
     lib.nlml_mlp_launch_count.restype = i64

@@ -697,10 +697,28 @@ extern "C" int nlml_mlp_latent_f32(nlml_mlp_plan* pl, const float* X_dev, int64_
     return forward_device(pl, X_dev, N, ldx, nullptr, LAT_out_dev, (cudaStream_t)stream);
 }
 
+namespace {
+int forward_host(nlml_mlp_plan* pl, const float* X_host, int64_t N, int64_t ldx, float* YPR_out_host, int pre);
+}
+
 extern "C" int nlml_mlp_forward_host_f32(nlml_mlp_plan* pl, const float* X_host, int64_t N, int64_t ldx,
                                          float* YPR_out_host) {
     if (!pl || (N > 0 && (!X_host || !YPR_out_host))) return set_error(NLML_E_INVALID, "null pointer argument");
     if (N < 0 || ldx < pl->input_size) return set_error(NLML_E_INVALID, "bad sizes");
+    return forward_host(pl, X_host, N, ldx, YPR_out_host, 0);
+}
+
+extern "C" int nlml_mlp_forward_landmarks_host_f32(nlml_mlp_plan* pl, const float* LM_host, int64_t N, int64_t ldx,
+                                                   float* YPR_out_host) {
+    if (!pl || (N > 0 && (!LM_host || !YPR_out_host))) return set_error(NLML_E_INVALID, "null pointer argument");
+    if (N < 0 || ldx < pl->input_size) return set_error(NLML_E_INVALID, "bad sizes");
+    if (pl->input_size % 3 != 0 || pl->input_size < 3 * 264)
+        return set_error(NLML_E_INVALID, "IPD normalisation needs x,y,z triples up to landmark 263 (input_size=%d)", pl->input_size);
+    return forward_host(pl, LM_host, N, ldx, YPR_out_host, 1);
+}
+
+namespace {
+int forward_host(nlml_mlp_plan* pl, const float* X_host, int64_t N, int64_t ldx, float* YPR_out_host, int pre) {
     DeviceGuard guard(pl->device);
     const int F = pl->input_size;
     if (!pl->streams[0])
@@ -739,7 +757,7 @@ extern "C" int nlml_mlp_forward_host_f32(nlml_mlp_plan* pl, const float* X_host,
         else
             NLML_CUDA(cudaMemcpy2DAsync(pl->x_dev[slot], sizeof(float) * F, X_host + s0 * ldx, sizeof(float) * ldx,
                                         sizeof(float) * F, (size_t)n, cudaMemcpyHostToDevice, st));
-        if (int rc = forward_chunk(pl, pl->x_dev[slot], n, F, pl->y_dev[slot], nullptr, pl->ws[slot], st)) return rc;
+        if (int rc = forward_chunk(pl, pl->x_dev[slot], n, F, pl->y_dev[slot], nullptr, pl->ws[slot], st, pre)) return rc;
         NLML_CUDA(cudaMemcpyAsync(pl->y_stage[slot], pl->y_dev[slot], sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
         pending[slot].s0 = s0;
         pending[slot].n = n;
@@ -748,5 +766,6 @@ extern "C" int nlml_mlp_forward_host_f32(nlml_mlp_plan* pl, const float* X_host,
     if (int rc = drain(slot ^ 1)) return rc;
     return 0;
 }
+}  // namespace
 
 extern "C" int64_t nlml_mlp_launch_count(const nlml_mlp_plan* pl) { return pl ? pl->launches : 0; }

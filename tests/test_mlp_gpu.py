@@ -148,6 +148,7 @@ def test_fused_ipd_normalisation_is_bit_exact(tc_model, prepost_golden):
     assert np.array_equal(fused, plain)
     assert np.array_equal(tc_model.predict_landmarks(raw.reshape(96, 1404)).cpu().numpy(), plain)
     assert np.array_equal(tc_model.predict_landmarks(raw[:1]).cpu().numpy(), plain[:1])
+    assert np.array_equal(tc_model.predict_landmarks_host(g["raw"]), plain)                     # host buffers
     # and against the oracle end to end (normalise on the CPU in float64, forward in float32)
     ok = np.abs(g["norm_X"]).max(1) < 10.0                # the two degenerate faces are outside the 1e-3 degree budget's range
     ref = mlp_oracle.forward(*[s for s in tc_model_state(tc_model)], mlp_oracle.ipd_normalize(g["raw"])[ok])
