@@ -183,6 +183,29 @@ def cpu_baseline_tucker(art, rows, cores, seconds_cap=40.0):
                       f"oracle.tucker_oracle.sgd_reference_form = autograd restatement of TD_Tester.py:127-159; {dt:.1f} s"}
 
 
+def cpu_baseline_powell(art, rows, cores):
+    """What TD_Tester.Test runs by default: scipy Powell over the float64 objective (oracle.tucker_oracle.powell_fit =
+    restatement of TD_Tester.py:162-199), one sample per worker process."""
+    from concurrent.futures import ProcessPoolExecutor
+    from nlml_hpe_b200 import synthetic
+    X = synthetic.make_features(cores, art["W"], *rows, U_id=art["U_id"], seed=1234)
+    with ProcessPoolExecutor(max_workers=cores) as pool:
+        list(pool.map(_cpu_warm_worker, range(cores)))
+        t0 = time.perf_counter()
+        list(pool.map(_cpu_powell_worker, [(art["W"], X[i], rows) for i in range(cores)]))
+        dt = time.perf_counter() - t0
+    return {"value": cores / dt, "unit": "poses/s", "cores": cores, "kind": "port",
+            "sample": f"{cores} samples (one per worker process), scipy Powell as TD_Tester.Test (TD_Tester.py:191-199); {dt:.1f} s"}
+
+
+def _cpu_powell_worker(args):
+    import torch
+    torch.set_num_threads(1)
+    from oracle import tucker_oracle
+    W, x, rows = args
+    return tucker_oracle.powell_fit(W, x, *rows)[0]
+
+
 def _cpu_warm_worker(_):
     import torch
     torch.set_num_threads(1)
@@ -380,6 +403,7 @@ def run_b200(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_tucker(art, rows, cores)
+        line["converged"]["cpu_baseline"] = cpu_baseline_powell(art, rows, cores)
         line["mlp"]["cpu_baseline"] = cpu_baseline_mlp(art, cores)
     print(json.dumps(line), flush=True)
     if world > 1:
