@@ -204,6 +204,8 @@ struct nlml_mlp_plan {
     int path = 0;  // 0 = tensor-core chain where eligible, 1 = FP32 CUDA-core chain everywhere
     int tc_group = 1;      // k-blocks accumulated in TMEM per promotion (NLML_TC_GROUP).  Max error vs the reference over
                            // 32768 samples: 1 -> 5.3e-4 deg, 2 -> 8.3e-4 deg (+3 % speed), 22 (never promote) -> 3.7e-3 deg
+    int short_k_group2 = 256;   // layers with K <= 256 sum two k-blocks per TMEM accumulator (16.5 -> 16.2 ms per 1M samples;
+                                // max error over 32 k samples 5.8e-4 -> 6.0e-4 degrees); NLML_TC_SHORTK_GROUP2=0 turns it off
     bool tc_neck = true;   // encoder.8 on the tensor cores with the narrow layers in its epilogue (NLML_TC_NECK=0: neck_kernel)
     bool tc_tail = true;   // heads' last two layers on the tensor cores (NLML_TC_TAIL=0: CUDA-core head_tail_kernel)
     bool two_cta = true;   // 256-wide layers: cta_group::2 kernel (false: 1-CTA MMAs with W multicast; NLML_TC_1CTA=1)
@@ -275,6 +277,11 @@ int launch_simt(nlml_mlp_plan* pl, LinearArgs& a, int nz, cudaStream_t st) {
     return 0;
 }
 
+// k-blocks summed in one TMEM accumulator before promotion.  The long reductions promote after every k-block (the
+// truncating accumulate of the tensor core biases long chains); layers with K <= short_k_group2 (256: the heads and
+// encoder layers 3-4, two or four k-blocks in all) sum two: the chain stays 24 MMAs long.
+inline int group_for(const nlml_mlp_plan* pl, int Kp) { return Kp <= pl->short_k_group2 ? std::max(pl->tc_group, 2) : pl->tc_group; }
+
 // one tensor-core layer for `nz` problems of identical shape (1 = encoder layer, 3 = the heads):
 // A planes [n][Kp] -> planes and/or FP32
 // dot_t: when non-null, tensor ids of the FOLLOWING single-output layers, fused into the epilogue as a dot product
@@ -285,7 +292,7 @@ int launch_tc(nlml_mlp_plan* pl, const int* t, int nz, const __half* const* Ahi,
     const int out = pl->out_dims[t[0]], Kp = pl->Kp[t[0]];
     tc::TcMaps maps;
     tc::LinearTcArgs a{};
-    a.N = n; a.out = out; a.Kp = Kp; a.act = act_of(t[0]); a.problems = nz; a.ldy = out; a.group = pl->tc_group;
+    a.N = n; a.out = out; a.Kp = Kp; a.act = act_of(t[0]); a.problems = nz; a.ldy = out; a.group = group_for(pl, Kp);
     a.Ydot = Ydot; a.ldd = 3;
     for (int z = 0; z < nz && dot_t; ++z) { a.dot_w[z] = pl->W[dot_t[z]]; a.dot_b[z] = pl->B[dot_t[z]]; }
     for (int z = 0; z < nz; ++z) {
@@ -396,7 +403,7 @@ int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, flo
         const int t4 = enc_t(4);
         tc::TcMaps maps;
         tc::LinearTcArgs a{};
-        a.N = n; a.out = pl->out_dims[t4]; a.Kp = pl->Kp[t4]; a.act = act_of(t4); a.problems = 1; a.ldy = a.out; a.group = pl->tc_group;
+        a.N = n; a.out = pl->out_dims[t4]; a.Kp = pl->Kp[t4]; a.act = act_of(t4); a.problems = 1; a.ldy = a.out; a.group = group_for(pl, a.Kp);
         if (int rc = tc::make_plane_map(&maps.a_hi[0], cur_hi, n, a.Kp, a.Kp, tc::BM)) return rc;
         if (int rc = tc::make_plane_map(&maps.a_lo[0], cur_lo, n, a.Kp, a.Kp, tc::BM)) return rc;
         maps.w_hi[0] = pl->wmap_hi[t4]; maps.w_lo[0] = pl->wmap_lo[t4];
@@ -609,6 +616,7 @@ extern "C" int nlml_mlp_plan_create(const float* const* weights, const float* co
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg2::SMEM_BYTES));
     if (const char* e = std::getenv("NLML_TC_1CTA")) pl->two_cta = !(e[0] == '1');
     if (const char* e = std::getenv("NLML_TC_GROUP")) pl->tc_group = std::max(1, std::atoi(e));
+    if (const char* e = std::getenv("NLML_TC_SHORTK_GROUP2")) pl->short_k_group2 = std::atoi(e);
     if (const char* e = std::getenv("NLML_TC_NECK")) pl->tc_neck = !(e[0] == '0');
     if (const char* e = std::getenv("NLML_TC_TAIL")) pl->tc_tail = !(e[0] == '0');   // measurement: 0 = CUDA-core head_tail_kernel
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<64>::SMEM_BYTES));
