@@ -97,3 +97,27 @@ def test_sharded_run_gathers_in_order_gloo_world2(n):
     for p in procs:
         p.join(30)
     assert sorted(results) == [(0, True), (1, True)]
+
+
+def test_plan_cache_key_follows_the_constants(art, rows):
+    """TD_Tester re-uses device plans across the reference's per-sample calls; the key must change with any change of
+    W, of the cosine rows or of the device, and only then."""
+    from nlml_hpe_b200 import TD_Tester
+    W = np.ascontiguousarray(art["W"], dtype=np.float32)
+    r = [np.ascontiguousarray(x, dtype=np.float64) for x in rows]
+    k0 = TD_Tester._content_key(W, r, None)
+    assert TD_Tester._content_key(W.copy(), [x.copy() for x in r], None) == k0
+    W2 = W.copy()
+    W2[3, 1, 2, 0, 777] = np.nextafter(W2[3, 1, 2, 0, 777], np.float32(np.inf))       # one ulp in one entry
+    assert TD_Tester._content_key(W2, r, None) != k0
+    W3 = W.copy()
+    W3[0, 0, 0, 0, 0], W3[0, 0, 0, 0, 1] = W[0, 0, 0, 0, 1], W[0, 0, 0, 0, 0]         # a swap keeps sum and xor of 32-bit words...
+    assert TD_Tester._content_key(W3, r, None) != k0                                   # ...but not of the 64-bit ones
+    W4 = W.copy()
+    W4[[0, 1]] = W4[[1, 0]]                                                             # two identity slices swapped: same multiset of words
+    assert TD_Tester._content_key(W4, r, None) != k0
+    r2 = [x.copy() for x in r]
+    r2[1][2, 3] += 1e-12
+    assert TD_Tester._content_key(W, r2, None) != k0
+    assert TD_Tester._content_key(W, r, "cuda:1") != k0
+    assert TD_Tester._content_key(W.reshape(5, 3, 3, 1, 3 * 1404), r, None) != k0      # same bytes, other ranks
