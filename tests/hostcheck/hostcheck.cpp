@@ -159,3 +159,14 @@ extern "C" int hostcheck_tucker_solve_5333(const float* W2, int F, const double*
     }
     return 0;
 }
+
+// packed 8x8 Cholesky solve of the converged solver (tucker_math.h chol_solve): A lower triangle packed row-major,
+// returns 1 when every pivot was positive
+extern "C" int hostcheck_chol_solve8(const float* A /*[36]*/, const float* g /*[8]*/, float* d /*[8]*/) {
+    float a[36], gg[8], dd[8];
+    for (int i = 0; i < 36; ++i) a[i] = A[i];
+    for (int i = 0; i < 8; ++i) gg[i] = g[i];
+    const bool ok = nlml::chol_solve<8>(a, gg, dd);
+    for (int i = 0; i < 8; ++i) d[i] = dd[i];
+    return ok ? 1 : 0;
+}

@@ -143,3 +143,22 @@ def test_solve_synthetic_core(hostcheck, rows):
     ref, _, _ = tucker_oracle.lm_fit(G, Xg, *rows)
     d = np.abs(P[:, :3] - ref[:, :3]).max(1) * DEG
     assert d.max() < 2e-3 and np.median(d) < 2e-4
+
+
+def test_packed_cholesky_solve(hostcheck):
+    """The 8x8 register Cholesky of the converged solver against numpy, and its pivot test on indefinite matrices."""
+    rng = np.random.default_rng(11)
+    hostcheck.hostcheck_chol_solve8.restype = ctypes.c_int
+    for trial in range(50):
+        B = rng.standard_normal((8, 8))
+        A = B @ B.T + 0.5 * np.eye(8)
+        A *= 10.0 ** rng.integers(-3, 4)
+        g = rng.standard_normal(8)
+        packed = np.array([A[r, c] for r in range(8) for c in range(r + 1)], np.float32)
+        d = np.zeros(8, np.float32)
+        ok = hostcheck.hostcheck_chol_solve8(_ptr(packed), _ptr(g.astype(np.float32)), _ptr(d))
+        ref = np.linalg.solve(A, g)
+        assert ok == 1 and np.abs(d - ref).max() <= 2e-4 * np.abs(ref).max() * np.linalg.cond(A) ** 0.5
+    A = np.diag([1.0, 2.0, -0.5, 1.0, 1.0, 1.0, 1.0, 1.0])           # one negative pivot -> the solver raises its damping
+    packed = np.array([A[r, c] for r in range(8) for c in range(r + 1)], np.float32)
+    assert hostcheck.hostcheck_chol_solve8(_ptr(packed), _ptr(np.ones(8, np.float32)), _ptr(np.zeros(8, np.float32))) == 0
