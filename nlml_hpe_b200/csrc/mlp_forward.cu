@@ -282,6 +282,13 @@ int launch_simt(nlml_mlp_plan* pl, LinearArgs& a, int nz, cudaStream_t st) {
 // encoder layers 3-4, two or four k-blocks in all) sum two: the chain stays 24 MMAs long.
 inline int group_for(const nlml_mlp_plan* pl, int Kp) { return Kp <= pl->short_k_group2 ? std::max(pl->tc_group, 2) : pl->tc_group; }
 
+#ifdef NLML_MLP_TIMING
+// development build only: every linear_tc2_kernel launch writes its per-warp phase cycles into the next slice of this buffer
+static float* g_mlp_timing_buf = nullptr;
+static int g_mlp_timing_slices = 0, g_mlp_timing_next = 0;
+extern "C" void nlml_debug_mlp_timing(float* dev_buf, int slices) { g_mlp_timing_buf = dev_buf; g_mlp_timing_slices = slices; g_mlp_timing_next = 0; }
+#endif
+
 // one tensor-core layer for `nz` problems of identical shape (1 = encoder layer, 3 = the heads):
 // A planes [n][Kp] -> planes and/or FP32
 // dot_t: when non-null, tensor ids of the FOLLOWING single-output layers, fused into the epilogue as a dot product
@@ -318,6 +325,10 @@ int launch_tc(nlml_mlp_plan* pl, const int* t, int nz, const __half* const* Ahi,
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
+#ifdef NLML_MLP_TIMING
+        a.timing = (g_mlp_timing_buf && g_mlp_timing_next < g_mlp_timing_slices)
+                       ? g_mlp_timing_buf + (size_t)(g_mlp_timing_next++) * pl->num_sms * tc::kEpilogueWarps * 4 : nullptr;
+#endif
         if (pl->two_cta) NLML_CUDA(cudaLaunchKernelEx(&cfg, tc::linear_tc2_kernel, maps, a));
         else NLML_CUDA(cudaLaunchKernelEx(&cfg, tc::linear_tc_kernel<256, 2>, maps, a));
     } else if (out == 64) {

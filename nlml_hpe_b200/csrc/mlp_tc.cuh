@@ -80,6 +80,9 @@ struct LinearTcArgs {
     float* neck_lat;                      // [N][9] or null
     __half* neck_hi[3];                   // [N][128]
     __half* neck_lo[3];
+#ifdef NLML_MLP_TIMING
+    float* timing;   // development build only (scripts/time_mlp_tc.py): [CTA][epilogue warp][4] cycles per tile
+#endif
 };
 
 // operand maps of up to three problems: A_hi, A_lo, W_hi, W_lo each
@@ -512,6 +515,18 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
 // The leader CTA (cluster rank 0) issues every MMA; accumulators land in each CTA's own TMEM (its 128 rows),
 // and each CTA's eight epilogue warps promote / finish their half exactly as in the 1-CTA kernel.
 // ---------------------------------------------------------------------------------------------------------
+#ifdef NLML_MLP_TIMING
+// development build only: cycles the epilogue warps of linear_tc2_kernel spend per tile in (0) bias staging, (1) waiting for
+// a partial accumulator, (2) promotion (TMEM loads + adds), (3) activation / plane split / stores
+#define NLML_MT_DECL float mt_acc[4] = {0.f, 0.f, 0.f, 0.f}; uint32_t mt_prev = (uint32_t)clock(); int mt_tiles = 0;
+#define NLML_MT_STAMP(i) { const uint32_t mt_now = (uint32_t)clock(); mt_acc[i] += (float)(mt_now - mt_prev); mt_prev = mt_now; }
+#define NLML_MT_RESET() { mt_prev = (uint32_t)clock(); }
+#else
+#define NLML_MT_DECL
+#define NLML_MT_STAMP(i)
+#define NLML_MT_RESET()
+#endif
+
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's even CTA
 
 struct Cfg2 {
@@ -658,7 +673,9 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
         // ===== epilogue warps of this CTA: rows of its own 128-row half =====
         const int quad = warp & 3, half = (warp - kFirstEpilogueWarp) >> 2;
         int acc = 0; uint32_t acc_phase = 0;
+        NLML_MT_DECL
         for (long long t = first; t < num_tiles; t += step) {
+            NLML_MT_RESET();
             const int z = (int)(t / tiles_per_problem);
             const long long tt = t % tiles_per_problem;
             const long long row = ((tt / tiles_n) * 2 + crank) * BM + quad * 32 + lane;
@@ -672,12 +689,14 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
             __syncwarp();
             for (int j = lane; j < HALF; j += 32) bias_s[j] = __ldg(bias + n0 + j);
             __syncwarp();
+            NLML_MT_STAMP(0);
             float sum[HALF];
 #pragma unroll
             for (int j = 0; j < HALF; ++j) sum[j] = 0.f;
             for (int kb = 0; kb < num_kb; kb += a.group) {
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
+                NLML_MT_STAMP(1);
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
                 // the next 32-column load is in flight while the previous one is added (two register buffers)
                 uint32_t v[2][32];
@@ -693,6 +712,7 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
                 __syncwarp();
                 if (lane == 0) mbar_arrive_leader(&tempty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                NLML_MT_STAMP(2);
             }
             if (row < a.N) {
 #pragma unroll
@@ -730,7 +750,16 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
                     }
                 }
             }
+            NLML_MT_STAMP(3);
+#ifdef NLML_MLP_TIMING
+            ++mt_tiles;
+#endif
         }
+#ifdef NLML_MLP_TIMING
+        if (lane == 0 && a.timing && mt_tiles > 0)
+            for (int i = 0; i < 4; ++i)
+                a.timing[((size_t)blockIdx.x * kEpilogueWarps + (warp - kFirstEpilogueWarp)) * 4 + i] = mt_acc[i] / (float)mt_tiles;
+#endif
     }
     tc_fence_before();
     __syncthreads();
