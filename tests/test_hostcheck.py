@@ -162,3 +162,27 @@ def test_packed_cholesky_solve(hostcheck):
     A = np.diag([1.0, 2.0, -0.5, 1.0, 1.0, 1.0, 1.0, 1.0])           # one negative pivot -> the solver raises its damping
     packed = np.array([A[r, c] for r in range(8) for c in range(r + 1)], np.float32)
     assert hostcheck.hostcheck_chol_solve8(_ptr(packed), _ptr(np.ones(8, np.float32)), _ptr(np.zeros(8, np.float32))) == 0
+
+
+def test_folded_form_on_random_cores_and_feature_counts(hostcheck):
+    """Value / gradient / Hessian from the folded Gram tensor against torch.func on the reference objective for random
+    cores with other feature counts (F = 5, 24, 97) and random cosine rows: nothing in the algebra depends on the shipped
+    artefacts."""
+    from oracle import tucker_oracle
+    rng = np.random.default_rng(2024)
+    for F in (5, 24, 97):
+        W = rng.standard_normal((5, 3, 3, 3, F)).astype(np.float32)
+        rws = [np.ascontiguousarray(np.stack([rng.uniform(-1, 1, 3), rng.uniform(0.5, 3, 3), rng.uniform(-np.pi, np.pi, 3),
+                                              rng.uniform(-0.2, 0.2, 3)], 1)) for _ in range(3)]
+        n = 16
+        X = np.ascontiguousarray(rng.standard_normal((n, F)).astype(np.float32))
+        Pq = np.ascontiguousarray(np.concatenate([rng.uniform(-1, 1, (n, 3)), rng.normal(0, 0.3, (n, 5))], 1).astype(np.float32))
+        W2 = np.ascontiguousarray(W.reshape(135, F))
+        L, G, H = np.zeros(n, np.float32), np.zeros((n, 8), np.float32), np.zeros((n, 36), np.float32)
+        hostcheck.hostcheck_tucker_newton_5333(_ptr(W2), F, _ptr(rws[0]), _ptr(rws[1]), _ptr(rws[2]), _ptr(X),
+                                               ctypes.c_int64(n), ctypes.c_int64(F), _ptr(Pq), _ptr(L), _ptr(G), _ptr(H))
+        Lr, Gr, Hr = tucker_oracle.newton_terms(Pq, W, X, *rws)
+        scale = np.abs(Lr).max()
+        assert np.abs(L - (Lr - 0.5 * (X.astype(np.float64) ** 2).sum(1))).max() < 2e-5 * scale
+        assert np.abs(G - Gr).max() < 2e-5 * np.abs(Gr).max()
+        assert np.abs(_unpack(H) - Hr).max() < 2e-5 * np.abs(Hr).max()
