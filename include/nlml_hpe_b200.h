@@ -57,7 +57,11 @@ void nlml_tucker_plan_destroy(nlml_tucker_plan* plan);
  * kernel_hint: 0 = choose by N and ranks, 1 = thread-per-sample kernel (throughput, ranks 5,3,3,3),
  * 2 = CTA-per-sample kernel (run-time ranks), 3 = warp-per-sample kernel (latency, ranks 5,3,3,3),
  * 4 = thread-per-sample kernel with q resident in tensor memory (12 warps per SM; measured equal to 1),
- * 5 = tensor-core iteration kernel (3xTF32 tcgen05 GEMMs for the folded-Gram contractions; the large-batch default). */
+ * 5 = tensor-core iteration kernel (3xTF32 tcgen05 GEMMs for the folded-Gram contractions; the large-batch default),
+ * 6 = run-time-rank tensor-core kernel (any ranks up to 16 per mode with a roll rank <= 8; the folded Gram tensor is
+ *     streamed through a shared-memory ring by TMA when it exceeds one tile; the default for every rank set other than
+ *     (5,3,3,3), i.e. the enlarged cores of BASELINE.json configs[4]; the reference takes the ranks from the arrays,
+ *     TD_Inference.py:56-57). */
 int nlml_tucker_fit_f32(nlml_tucker_plan* plan, const float* X_dev, int64_t N, int64_t ldx,
                         int iters, float lr, float clip, float* P_out_dev, int64_t ldp,
                         int kernel_hint, void* stream);
@@ -149,6 +153,9 @@ int nlml_measure_fp32_tflops_3reg(int device, double* tflops_out);
 /* Test hook (current device): D[128][N] = A[128][K] * B[N][K]^T through the 3xTF32 tcgen05 building block used by
  * the tensor-core Tucker iteration.  K in 8..64 (multiple of 8), N in 16..256 (multiple of 16).  Synchronous. */
 int nlml_debug_tf32_gemm(const float* A_dev, const float* B_dev, int K, int N, float* D_dev);
+/* mode 0: as above.  mode 1: the B tile is stored as the K-major image of its transpose and read as an MN-major operand
+ * (the form that lets one shared-memory copy of a folded-Gram tile serve both GEMMs of the run-time-rank kernel). */
+int nlml_debug_tf32_gemm_mode(const float* A_dev, const float* B_dev, int K, int N, float* D_dev, int mode);
 
 #ifdef __cplusplus
 }

@@ -38,28 +38,36 @@ def _as_numpy(a, dtype):
     return np.ascontiguousarray(np.asarray(a, dtype=dtype))
 
 
-_WEIGHTS = {}
+_FAST = {}   # (id(W), data pointer, shape) -> (cheap digest, full key): skips re-hashing an array object already seen
 
 
-def _position_weights(n):
-    w = _WEIGHTS.get(n)
-    if w is None:
-        if len(_WEIGHTS) > 8:
-            _WEIGHTS.clear()
-        w = _WEIGHTS[n] = (np.arange(n, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15) | np.uint64(1))
-    return w
+def _cheap_digest(W):
+    """Three vector reductions over W's words (0.1 ms for the 758 KB shipped tensor): detects an in-place change of an
+    array object that was hashed before.  It is NOT the cache key (the key is the cryptographic digest below)."""
+    w = W.reshape(-1).view(np.uint32)
+    return (int(np.add.reduce(w, dtype=np.uint64)), int(np.bitwise_xor.reduce(w)), int(np.add.reduce(w[::7], dtype=np.uint64)))
 
 
 def _content_key(W, rows, device):
-    """Cache key of one set of constants (W float32 contiguous, rows float64): shape + cheap content digests.
-    The reference passes W on every call (TD_Inference.py:56), so this runs per sample: three vector reductions
-    over the 758 KB (0.1 ms) instead of a cryptographic hash of it (2 ms)."""
-    w64 = W.reshape(-1).view(np.uint32).astype(np.uint64, copy=False) if W.size % 2 else W.reshape(-1).view(np.uint64)
-    h = hashlib.blake2b(digest_size=16)
+    """Cache key of one set of constants: BLAKE2b over the full contents of W (float32, contiguous) and the cosine rows
+    (float64) -- two different tensors cannot share a plan.  The reference passes W on every call (TD_Inference.py:56),
+    so the 2 ms hash is taken once per array OBJECT: a later call with the same object (same id, buffer address and
+    shape, unchanged cheap digest) reuses its key."""
+    ident = (id(W), W.ctypes.data, W.shape)
+    cheap = _cheap_digest(W)
+    hit = _FAST.get(ident)
+    if hit is not None and hit[0] == cheap:
+        wkey = hit[1]
+    else:
+        wkey = hashlib.blake2b(W.tobytes(), digest_size=20).hexdigest()
+        if len(_FAST) > 16:
+            _FAST.clear()
+        _FAST[ident] = (cheap, wkey)
+    h = hashlib.blake2b(digest_size=20)
     h.update(str(W.shape).encode())
-    weights = _position_weights(w64.size)   # odd multipliers: a permutation of the words changes the weighted sum
-    h.update(np.array([np.add.reduce(w64), np.bitwise_xor.reduce(w64), np.add.reduce(w64 * weights)], dtype=np.uint64).tobytes())
+    h.update(wkey.encode())
     for r in rows:
+        h.update(str(r.shape).encode())
         h.update(r.tobytes())
     return (h.hexdigest(), str(device))
 

@@ -187,6 +187,31 @@ struct Workspace {
 };
 }  // namespace
 
+// Accuracy / kernel-selection constants.  These are COMPILE-TIME: the product library reads no environment variable
+// (a stray variable must not be able to change the angles).  Development builds override them with -D.
+#ifndef NLML_MLP_TC_GROUP
+#define NLML_MLP_TC_GROUP 1          // k-blocks accumulated in TMEM per promotion.  Max error vs the reference over 32768
+#endif                               // samples: 1 -> 5.3e-4 deg, 2 -> 8.3e-4 deg (+3 % speed), never promote -> 3.7e-3 deg
+#ifndef NLML_MLP_SHORTK_GROUP2
+#define NLML_MLP_SHORTK_GROUP2 256   // layers with K <= this sum two k-blocks per TMEM accumulator (16.5 -> 16.2 ms per 1M
+#endif                               // samples; max error over 32 k samples 5.8e-4 -> 6.0e-4 degrees); 0 turns it off
+#ifndef NLML_MLP_TC_NECK
+#define NLML_MLP_TC_NECK 1           // encoder.8 on the tensor cores with the narrow layers in its epilogue (0: neck_kernel)
+#endif
+#ifndef NLML_MLP_TC_TAIL
+#define NLML_MLP_TC_TAIL 1           // heads' last two layers on the tensor cores (0: CUDA-core head_tail_kernel)
+#endif
+#ifndef NLML_MLP_TWO_CTA
+#define NLML_MLP_TWO_CTA 1           // 256-wide layers: cta_group::2 kernel (0: 1-CTA MMAs with W multicast)
+#endif
+#ifndef NLML_MLP_CHUNK_WAVES
+#define NLML_MLP_CHUNK_WAVES 8       // samples per pass = waves x num_sms x 128 (4 waves 16.9 ms / 1M, 8 waves 16.5, 16 waves 16.5)
+#endif
+namespace {
+constexpr int kTcGroup = NLML_MLP_TC_GROUP, kShortKGroup2 = NLML_MLP_SHORTK_GROUP2;
+constexpr bool kTcNeck = NLML_MLP_TC_NECK != 0, kTcTail = NLML_MLP_TC_TAIL != 0, kTwoCta = NLML_MLP_TWO_CTA != 0;
+}  // namespace
+
 struct nlml_mlp_plan {
     int device = 0;
     int out_dims[kNumT];
@@ -202,19 +227,15 @@ struct nlml_mlp_plan {
     CUtensorMap wmap_hi[kNumT], wmap_lo[kNumT];
     float* Wt[kNumT] = {};   // transposed FP32 copies [in][out] for the fused narrow-layer kernels
     int path = 0;  // 0 = tensor-core chain where eligible, 1 = FP32 CUDA-core chain everywhere
-    int tc_group = 1;      // k-blocks accumulated in TMEM per promotion (NLML_TC_GROUP).  Max error vs the reference over
-                           // 32768 samples: 1 -> 5.3e-4 deg, 2 -> 8.3e-4 deg (+3 % speed), 22 (never promote) -> 3.7e-3 deg
-    int short_k_group2 = 256;   // layers with K <= 256 sum two k-blocks per TMEM accumulator (16.5 -> 16.2 ms per 1M samples;
-                                // max error over 32 k samples 5.8e-4 -> 6.0e-4 degrees); NLML_TC_SHORTK_GROUP2=0 turns it off
-    bool tc_neck = true;   // encoder.8 on the tensor cores with the narrow layers in its epilogue (NLML_TC_NECK=0: neck_kernel)
-    bool tc_tail = true;   // heads' last two layers on the tensor cores (NLML_TC_TAIL=0: CUDA-core head_tail_kernel)
-    bool two_cta = true;   // 256-wide layers: cta_group::2 kernel (false: 1-CTA MMAs with W multicast; NLML_TC_1CTA=1)
     int input_size = 0, latent = 0, head_in = 0;
     int64_t chunk = 8 * 148 * 128;  // samples per pass: 8 x 148 M-tiles = whole waves of the persistent GEMMs; the per-launch
                                     // fixed costs of the 9 kernels amortise over it (final kernels, per 1M samples:
                                     // 4 waves 16.9 ms, 8 waves 16.5 ms, 16 waves 16.5 ms; workspaces 2.6 GB at 8)
     size_t f32_width[2] = {0, 0}, plane_width[2] = {0, 0};
-    Workspace ws[2];
+    Workspace ws_dev;        // device-buffer entry points (ordered across caller streams by ws_dev_done)
+    Workspace ws_host[2];    // the host pipeline's two slots (its own internal streams); never touched by the device path
+    cudaEvent_t ws_dev_done = nullptr;   // recorded after the last device-path call's kernels: a later call on ANOTHER stream
+                                         // waits for it before reusing ws_dev (two unordered streams must not share the buffers)
     int num_sms = 148;
     int64_t launches = 0;
     cudaStream_t streams[2] = {nullptr, nullptr};
@@ -280,7 +301,7 @@ int launch_simt(nlml_mlp_plan* pl, LinearArgs& a, int nz, cudaStream_t st) {
 // k-blocks summed in one TMEM accumulator before promotion.  The long reductions promote after every k-block (the
 // truncating accumulate of the tensor core biases long chains); layers with K <= short_k_group2 (256: the heads and
 // encoder layers 3-4, two or four k-blocks in all) sum two: the chain stays 24 MMAs long.
-inline int group_for(const nlml_mlp_plan* pl, int Kp) { return Kp <= pl->short_k_group2 ? std::max(pl->tc_group, 2) : pl->tc_group; }
+inline int group_for(const nlml_mlp_plan* pl, int Kp) { return Kp <= kShortKGroup2 ? std::max(kTcGroup, 2) : kTcGroup; }
 
 #ifdef NLML_MLP_TIMING
 // development build only: every linear_tc2_kernel launch writes its per-warp phase cycles into the next slice of this buffer
@@ -320,7 +341,7 @@ int launch_tc(nlml_mlp_plan* pl, const int* t, int nz, const __half* const* Ahi,
         const unsigned grid = 2 * (unsigned)std::min<int64_t>(work, pl->num_sms / 2);
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc::kThreads);
-        cfg.dynamicSmemBytes = pl->two_cta ? tc::Cfg2::SMEM_BYTES : tc::Cfg<256>::SMEM_BYTES; cfg.stream = st;
+        cfg.dynamicSmemBytes = kTwoCta ? tc::Cfg2::SMEM_BYTES : tc::Cfg<256>::SMEM_BYTES; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -329,7 +350,7 @@ int launch_tc(nlml_mlp_plan* pl, const int* t, int nz, const __half* const* Ahi,
         a.timing = (g_mlp_timing_buf && g_mlp_timing_next < g_mlp_timing_slices)
                        ? g_mlp_timing_buf + (size_t)(g_mlp_timing_next++) * pl->num_sms * tc::kEpilogueWarps * 4 : nullptr;
 #endif
-        if (pl->two_cta) NLML_CUDA(cudaLaunchKernelEx(&cfg, tc::linear_tc2_kernel, maps, a));
+        if (kTwoCta) NLML_CUDA(cudaLaunchKernelEx(&cfg, tc::linear_tc2_kernel, maps, a));
         else NLML_CUDA(cudaLaunchKernelEx(&cfg, tc::linear_tc_kernel<256, 2>, maps, a));
     } else if (out == 64) {
         const unsigned grid = (unsigned)std::min<int64_t>(tiles_m * nz, pl->num_sms);
@@ -355,10 +376,10 @@ inline bool tail_fusable(const nlml_mlp_plan* pl) {
 // heads' last two layers on the tensor cores: 128 -> 64 relu as a BN = 64 tile, 64 -> 1 as a dot product in its epilogue
 // encoder.8 (128 -> 64 tanh) on the tensor cores with encoder.10 and the heads' model.0 in its epilogue
 inline bool neck_on_tc(const nlml_mlp_plan* pl) {
-    return pl->path == 0 && pl->tc_neck && neck_fusable(pl) && pl->tc[enc_t(3)] && pl->tc[enc_t(4)] && pl->tc[head_t(0, 1)];
+    return pl->path == 0 && kTcNeck && neck_fusable(pl) && pl->tc[enc_t(3)] && pl->tc[enc_t(4)] && pl->tc[head_t(0, 1)];
 }
 inline bool tail_on_tc(const nlml_mlp_plan* pl) {
-    return pl->path == 0 && pl->tc_tail && pl->tc[head_t(0, 2)] && pl->tc[head_t(0, 3)];
+    return pl->path == 0 && kTcTail && pl->tc[head_t(0, 2)] && pl->tc[head_t(0, 3)];
 }
 constexpr size_t kNeckSmem = sizeof(float) * (kNeckIn * kNeckMid + tc::kRowsPerBlock * (kNeckIn + 4) + kNeckLat * kNeckMid +
                                               3 * kHeadW * kHeadIn + kNeckMid + kNeckLat + 3 * kHeadW);
@@ -509,13 +530,17 @@ int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, flo
 
 int forward_device(nlml_mlp_plan* pl, const float* X, int64_t N, int64_t ldx, float* YPR, float* LAT, cudaStream_t st,
                    int pre = 0) {
-    if (int rc = ensure_workspace(pl, pl->ws[0], N)) return rc;
+    if (N == 0) return 0;
+    if (int rc = ensure_workspace(pl, pl->ws_dev, N)) return rc;
+    if (!pl->ws_dev_done) NLML_CUDA(cudaEventCreateWithFlags(&pl->ws_dev_done, cudaEventDisableTiming));
+    else NLML_CUDA(cudaStreamWaitEvent(st, pl->ws_dev_done, 0));   // the previous call may have run on another stream
     for (int64_t s0 = 0; s0 < N; s0 += pl->chunk) {
         const int64_t n = std::min<int64_t>(pl->chunk, N - s0);
         if (int rc = forward_chunk(pl, X + s0 * ldx, n, ldx, YPR ? YPR + s0 * 3 : nullptr,
-                                   LAT ? LAT + s0 * pl->latent : nullptr, pl->ws[0], st, pre))
+                                   LAT ? LAT + s0 * pl->latent : nullptr, pl->ws_dev, st, pre))
             return rc;
     }
+    NLML_CUDA(cudaEventRecord(pl->ws_dev_done, st));
     return 0;
 }
 
@@ -625,13 +650,8 @@ extern "C" int nlml_mlp_plan_create(const float* const* weights, const float* co
         if (pl->tc[t])
             if (int rc = prepare_tc_layer(pl, t, weights[t])) return rc;
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg2::SMEM_BYTES));
-    if (const char* e = std::getenv("NLML_TC_1CTA")) pl->two_cta = !(e[0] == '1');
-    if (const char* e = std::getenv("NLML_TC_GROUP")) pl->tc_group = std::max(1, std::atoi(e));
-    if (const char* e = std::getenv("NLML_TC_SHORTK_GROUP2")) pl->short_k_group2 = std::atoi(e);
-    if (const char* e = std::getenv("NLML_TC_NECK")) pl->tc_neck = !(e[0] == '0');
-    if (const char* e = std::getenv("NLML_TC_TAIL")) pl->tc_tail = !(e[0] == '0');   // measurement: 0 = CUDA-core head_tail_kernel
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<64>::SMEM_BYTES));
-    if (const char* e = std::getenv("NLML_MLP_CHUNK_WAVES")) pl->chunk = (int64_t)pl->num_sms * 128 * std::max(1, std::atoi(e));
+    pl->chunk = (int64_t)pl->num_sms * 128 * NLML_MLP_CHUNK_WAVES;
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<256>::SMEM_BYTES));
     NLML_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::Cfg<128>::SMEM_BYTES));
     NLML_CUDA(cudaFuncSetAttribute(tc::neck_kernel<kNeckIn, kNeckMid, kNeckLat, kHeadIn, kHeadW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNeckSmem));
@@ -664,8 +684,10 @@ extern "C" void nlml_mlp_plan_destroy(nlml_mlp_plan* pl) {
         cudaFree(pl->x_dev[i]);
         cudaFree(pl->y_dev[i]);
         if (pl->y_stage[i]) cudaFreeHost(pl->y_stage[i]);
-        free_workspace(pl->ws[i]);
+        free_workspace(pl->ws_host[i]);
     }
+    free_workspace(pl->ws_dev);
+    if (pl->ws_dev_done) cudaEventDestroy(pl->ws_dev_done);
     delete pl;
 }
 
@@ -745,9 +767,13 @@ int forward_host(nlml_mlp_plan* pl, const float* X_host, int64_t N, int64_t ldx,
     const int64_t want = std::min<int64_t>(pl->chunk, ceil_div(std::max<int64_t>(N, 1), 128) * 128);
     if (pl->host_rows < want) {
         if (pl->host_rows) NLML_CUDA(cudaDeviceSynchronize());
+        pl->host_rows = 0;   // nothing below is usable until every allocation has succeeded
         for (int i = 0; i < 2; ++i) {
             cudaFree(pl->x_dev[i]); cudaFree(pl->y_dev[i]);
             if (pl->y_stage[i]) cudaFreeHost(pl->y_stage[i]);
+            pl->x_dev[i] = pl->y_dev[i] = pl->y_stage[i] = nullptr;
+        }
+        for (int i = 0; i < 2; ++i) {
             NLML_CUDA(cudaMallocHost(&pl->y_stage[i], sizeof(float) * want * 3));
             NLML_CUDA(cudaMalloc(&pl->x_dev[i], sizeof(float) * want * F));
             NLML_CUDA(cudaMalloc(&pl->y_dev[i], sizeof(float) * want * 3));
@@ -755,7 +781,7 @@ int forward_host(nlml_mlp_plan* pl, const float* X_host, int64_t N, int64_t ldx,
         pl->host_rows = want;
     }
     for (int i = 0; i < 2; ++i)
-        if (int rc = ensure_workspace(pl, pl->ws[i], N)) return rc;
+        if (int rc = ensure_workspace(pl, pl->ws_host[i], N)) return rc;
     // results go to pinned staging: a D2H copy into pageable user memory would block the host thread until the
     // chunk's kernels are done, so the next chunk's H2D copy could not overlap them
     struct Pending { int64_t s0 = 0, n = 0; } pending[2];
@@ -776,7 +802,7 @@ int forward_host(nlml_mlp_plan* pl, const float* X_host, int64_t N, int64_t ldx,
         else
             NLML_CUDA(cudaMemcpy2DAsync(pl->x_dev[slot], sizeof(float) * F, X_host + s0 * ldx, sizeof(float) * ldx,
                                         sizeof(float) * F, (size_t)n, cudaMemcpyHostToDevice, st));
-        if (int rc = forward_chunk(pl, pl->x_dev[slot], n, F, pl->y_dev[slot], nullptr, pl->ws[slot], st, pre)) return rc;
+        if (int rc = forward_chunk(pl, pl->x_dev[slot], n, F, pl->y_dev[slot], nullptr, pl->ws_host[slot], st, pre)) return rc;
         NLML_CUDA(cudaMemcpyAsync(pl->y_stage[slot], pl->y_dev[slot], sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
         pending[slot].s0 = s0;
         pending[slot].n = n;

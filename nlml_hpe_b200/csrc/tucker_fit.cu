@@ -42,7 +42,9 @@ struct TuckerArgs {
     int ri, ry, rp, rr;
     int nBCDp;
     int vec_ok;  // X rows and W2 rows are 16-byte aligned and F % 4 == 0
-    int dbg;     // measurement only (NLML_TUCKER_DBG): tensor-core kernel 1 = no MMAs / waits, 2 = no TMEM consumption
+#ifdef NLML_TC_DBG
+    int dbg;     // development build only (-DNLML_TC_DBG): tensor-core kernel 1 = no MMAs / waits, 2 = no TMEM consumption
+#endif
     LmOptions lm;   // converged solve only
     int* evals;     // converged solve only: optional [N] evaluations used per sample
     float rows_y[4 * kMaxModeRank], rows_p[4 * kMaxModeRank], rows_r[4 * kMaxModeRank];
@@ -147,6 +149,7 @@ struct QTmem {
 
 }  // namespace nlml
 #include "tucker_tc.cuh"
+#include "tucker_gen.cuh"
 namespace nlml {
 
 // ---------------------------------------------------------------------------------------------
@@ -833,6 +836,14 @@ __device__ __forceinline__ void tc_reduce_t(uint32_t taddr, const float (&YY)[6]
 //   role 0 ("angle thread", warps 0-3): writes the UU operand, consumes the first half of T, finishes d/d(angles)
 //   role 1 ("identity thread", warps 4-7): writes the PP (x) RR operand, consumes the second half of T and V -> d/du
 // Both keep a bitwise-identical copy of p; partial sums and gradient parts cross through shared memory.
+// development build only (-DNLML_TC_DBG): the product kernel has no switch that skips work
+#ifdef NLML_TC_DBG
+#define NLML_DBG_MMA (a.dbg != 1)
+#define NLML_DBG_READ (a.dbg != 2)
+#else
+#define NLML_DBG_MMA true
+#define NLML_DBG_READ true
+#endif
 __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_constant__ TuckerArgs a) {
     using C = TcFitCfg;
     extern __shared__ __align__(1024) uint8_t tsm[];
@@ -983,7 +994,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             tmem_store_wait();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (tid == 0 && a.dbg != 1) {
+            if (tid == 0 && NLML_DBG_MMA) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 ttc::issue_gemm_3xtf32_ta(tmem + C::COL_T, tmem + C::COL_A1, ttc::smem_u32(b1_hi), ttc::smem_u32(b1_lo), C::K1, C::N1, true);
                 ttc::umma_commit_to(bar);
@@ -1014,7 +1025,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             ttc::fence_async_smem();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync 2, 128;" ::: "memory");
-            if (tid == 160 && a.dbg != 1) {   // warp 5: not on the sub-partition of the T GEMM's issuer (warp 0)
+            if (tid == 160 && NLML_DBG_MMA) {   // warp 5: not on the sub-partition of the T GEMM's issuer (warp 0)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 ttc::issue_gemm_3xtf32(tmem + C::COL_V, ttc::smem_u32(av_hi), ttc::smem_u32(av_lo), ttc::smem_u32(bv_hi),
                                        ttc::smem_u32(bv_lo), C::KV, C::NV, true);
@@ -1041,10 +1052,10 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             float GU[15];
 #pragma unroll
             for (int i = 0; i < 15; ++i) GU[i] = 0.f;
-            if (a.dbg != 1) ttc::mbar_wait(bar + 1, phase);   // V GEMM
+            if (NLML_DBG_MMA) ttc::mbar_wait(bar + 1, phase);   // V GEMM
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             NLML_TSTAMP(3);   // wait for the GEMM
-            if (a.dbg != 2) {
+            if (NLML_DBG_READ) {
                 uint32_t vb[2][32];   // the next 32 columns are in flight while these are reduced
                 tmem_load32_async(lane_addr + C::COL_V, vb[0]);
 #pragma unroll
@@ -1065,10 +1076,10 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         } else {
             // all of T -> GR, GP, GY -> d/d(yaw, pitch, roll)
             float GR[6], GP[6], GY[6], GR2[6], GP2[6], GY3[3];
-            if (a.dbg != 1) ttc::mbar_wait(bar, phase);       // T GEMM (launched first, long done)
+            if (NLML_DBG_MMA) ttc::mbar_wait(bar, phase);       // T GEMM (launched first, long done)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             NLML_TSTAMP(3);
-            if (a.dbg != 2) {
+            if (NLML_DBG_READ) {
                 tc_reduce_t<0>(lane_addr + C::COL_T, YY, PP, RRv, GR, GP, GY3);
 #pragma unroll
                 for (int i = 0; i < 3; ++i) GY[i] = GY3[i];
@@ -1179,6 +1190,13 @@ struct nlml_tucker_plan {
     float* St = nullptr;
     TuckerArgs base{};
     bool fast = false;        // ranks (5,3,3,3): thread-per-sample kernel available
+    bool cta_ok = false;      // CTA-per-sample kernel usable (its working set fits shared memory)
+    bool gen_ok = false;      // run-time-rank tensor-core kernel usable (tucker_gen.cuh)
+    tgen::GenCfg gen{};
+    uint8_t* gen_tiles = nullptr;           // tile images of S (hi/lo, UMMA layout), streamed by TMA
+    float* q_ws[3] = {nullptr, nullptr, nullptr};   // q = W2 x slabs: [0],[1] host-pipeline slots, [2] device-buffer calls
+    int64_t q_rows[3] = {0, 0, 0};
+    cudaEvent_t q_done = nullptr;           // orders device-buffer calls issued on different streams over q_ws[2]
     bool st_in_smem = false;  // CTA kernel keeps St in shared memory
     size_t cta_smem = 0;
     int num_sms = 148;
@@ -1204,15 +1222,138 @@ constexpr int kTpsBigThreads = 384;  // TMEM-resident-q variant: one 12-warp CTA
 // is bound by the 3-register-operand FFMA rate, not by latency -- so the variant is opt-in (kernel_hint 4) only
 constexpr int kCtaThreads = 128;
 constexpr int kWpsWarps = 4;
-constexpr int64_t kTcCrossover = 2 * 148 * 128;   // two waves of the tensor-core kernel (128 samples per SM)
+// the tensor-core kernel takes over from two full waves (128 samples per SM): 37 888 samples on a 148-SM B200
+inline int64_t tc_crossover(const nlml_tucker_plan* pl) { return 2 * (int64_t)pl->num_sms * 128; }
 constexpr int64_t kWpsCrossover = 8192;  // below this the warp-per-sample kernel finishes sooner (profiles/)
 using TpsDefault = TpsCfg<5, 3, 3, 3, kTpsThreads, kTpsSamples>;
 using TpsBig = TpsCfg<5, 3, 3, 3, kTpsBigThreads, 1, true>;
 size_t wps_smem_bytes(int F) { return sizeof(float) * kWpsWarps * ((F + 3) / 4 * 4 + 64); }
 
+// ---- run-time-rank tensor-core kernel: per-plan configuration (TMEM columns, shared-memory ring, block size) ----
+constexpr int kGenSmemMax = 232448;   // 227 KB of dynamic shared memory per CTA
+bool choose_gen_config(int ri, int ry, int rp, int rr, tgen::GenCfg& best) {
+    if (rr > 8 || ri > tgen::kMaxRank || ry > tgen::kMaxRank || rp > tgen::kMaxRank) return false;
+    tgen::GenCfg b{};
+    b.ri = ri; b.ry = ry; b.rp = rp; b.rr = rr; b.R = ri * ry * rp * rr;
+    b.rrmax = rr <= 5 ? 5 : 8;
+    b.nA = tri(ri); b.KA = (b.nA + 7) / 8 * 8; b.NA16 = (b.nA + 15) / 16 * 16;
+    b.nC = tri(rp); b.nBC = tri(ry) * tri(rp);
+    b.nDp = (tri(b.rrmax) + 7) / 8 * 8;
+    b.NP = 3 + ri;
+    b.t_p = 0; b.t_gx = b.NP; b.t_gl = 2 * b.NP; b.t_cy = 3 * b.NP; b.t_dcy = b.t_cy + ry; b.t_cp = b.t_dcy + ry;
+    b.t_dcp = b.t_cp + rp; b.t_rows = b.t_dcp + rp;
+    const int tab_bytes = b.t_rows * tgen::kSamples * 4, bar_bytes = 1024;
+    double best_score = -1.0;
+    for (int BCP = 1; BCP <= 32; ++BCP) {
+        const int NB = (BCP * b.nDp + 15) / 16 * 16;   // MMA N granularity; pad columns hold zeros in the tiles and the operand
+        if (NB > 256) continue;
+        const int nblocks = (b.nBC + BCP - 1) / BCP;
+        for (int tbufs = 2; tbufs >= 1; --tbufs)
+            for (int gbufs = 2; gbufs >= 1; --gbufs) {
+                if (gbufs * b.NA16 + 2 * b.KA + tbufs * NB > 512) continue;
+                for (int ybufs = 2; ybufs >= 1; --ybufs) {
+                    const int tt = NB * b.KA * 8, gt = b.NA16 * NB * 8, ypr = ybufs * NB * tgen::kSamples * 8;
+                    const int avail = kGenSmemMax - 1024 - ypr - tab_bytes - bar_bytes;
+                    if (avail < tt + gt) continue;
+                    const bool resident = nblocks <= tgen::kMaxSlots && (long long)nblocks * (tt + gt) <= avail;
+                    const int slots = resident ? nblocks : std::min(4, avail / (tt + gt));
+                    const double waste = (double)nblocks * NB / ((double)b.nBC * tri(rr)) - 1.0;   // padded columns issued per useful one
+                    const double score = (resident ? 100.0 : 10.0 * std::min(slots, 3)) + 6.0 * ybufs + 4.0 * tbufs + 3.0 * gbufs +
+                                         (NB >= 64 ? 8.0 : NB >= 48 ? 6.0 : NB >= 32 ? 4.0 : 0.0) - 20.0 * waste;
+                    if (score <= best_score) continue;
+                    best_score = score;
+                    best = b;
+                    best.BCP = BCP; best.NB = NB; best.nblocks = nblocks;
+                    best.tbufs = tbufs; best.gbufs = gbufs; best.ybufs = ybufs;
+                    best.tslots = best.gslots = slots; best.resident = resident ? 1 : 0;
+                    best.tt_bytes = tt; best.gt_bytes = gt;
+                    best.col_g = 0; best.col_a = gbufs * b.NA16; best.col_t = best.col_a + 2 * b.KA;
+                    best.off_tring = 0;
+                    best.off_gring = slots * tt;
+                    best.off_ypr = best.off_gring + slots * gt;
+                    best.off_tab = best.off_ypr + ypr;
+                    best.off_bar = best.off_tab + tab_bytes;
+                    best.smem_bytes = best.off_bar + bar_bytes;
+                }
+            }
+    }
+    return best_score >= 0.0;
+}
+
+template <int RRMAX, int NA16MAX>
+int launch_gen_instance(const tgen::GenArgs& a, unsigned grid, cudaStream_t st, bool set_attr) {
+    auto kern = tgen::tucker_fit_gen_kernel<RRMAX, NA16MAX>;
+    if (set_attr) {
+        NLML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.c.smem_bytes));
+        return 0;
+    }
+    kern<<<grid, tgen::kThreads, a.c.smem_bytes, st>>>(a);
+    return 0;
+}
+int dispatch_gen(const tgen::GenArgs& a, unsigned grid, cudaStream_t st, bool set_attr) {
+    const bool small_a = a.c.NA16 <= 48;
+    if (a.c.rrmax == 5) return small_a ? launch_gen_instance<5, 48>(a, grid, st, set_attr) : launch_gen_instance<5, 144>(a, grid, st, set_attr);
+    return small_a ? launch_gen_instance<8, 48>(a, grid, st, set_attr) : launch_gen_instance<8, 144>(a, grid, st, set_attr);
+}
+
+// samples per pass of the generic kernel: whole waves of 128-sample CTAs, q slabs of at most ~1.5 GB
+int64_t gen_chunk(const nlml_tucker_plan* pl) {
+    const int64_t wave = (int64_t)pl->num_sms * tgen::kSamples;
+    const int64_t waves = std::max<int64_t>(1, (int64_t)(1.5e9 / ((double)pl->R * 4.0 * (double)wave)));
+    return std::min<int64_t>(waves, 8) * wave;
+}
+
+int launch_gen(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int iters, float lr, float clip, float* P,
+               int64_t ldp, int ws_slot, cudaStream_t st) {
+    const int64_t chunk = gen_chunk(pl);
+    const int64_t want = std::min<int64_t>(chunk, ceil_div(N, tgen::kSamples) * tgen::kSamples);
+    if (pl->q_rows[ws_slot] < want) {
+        if (pl->q_rows[ws_slot]) NLML_CUDA(cudaDeviceSynchronize());
+        pl->q_rows[ws_slot] = 0;
+        cudaFree(pl->q_ws[ws_slot]);
+        pl->q_ws[ws_slot] = nullptr;
+        NLML_CUDA(cudaMalloc(&pl->q_ws[ws_slot], sizeof(float) * (size_t)want * pl->R));
+        pl->q_rows[ws_slot] = want;
+    }
+    if (ws_slot == 2) {   // device-buffer calls may come from different streams: they share one q workspace
+        if (!pl->q_done) NLML_CUDA(cudaEventCreateWithFlags(&pl->q_done, cudaEventDisableTiming));
+        else NLML_CUDA(cudaStreamWaitEvent(st, pl->q_done, 0));
+    }
+    tgen::GenArgs a{};
+    a.q = pl->q_ws[ws_slot];
+    a.tiles = pl->gen_tiles;
+    a.ldp = ldp;
+    a.T = iters; a.lr = lr; a.clip = clip;
+    a.c = pl->gen;
+    std::memcpy(a.rows_y, pl->base.rows_y, sizeof(a.rows_y));
+    std::memcpy(a.rows_p, pl->base.rows_p, sizeof(a.rows_p));
+    std::memcpy(a.rows_r, pl->base.rows_r, sizeof(a.rows_r));
+    for (int64_t s0 = 0; s0 < N; s0 += chunk) {
+        const int64_t n = std::min<int64_t>(chunk, N - s0);
+        const float* x = X + s0 * ldx;
+        const int vec_ok = (pl->F % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+        const unsigned ctas = (unsigned)ceil_div(n, tgen::kSamples);
+        tgen::tucker_project_kernel<<<dim3(ctas, (unsigned)ceil_div(pl->R, 64)), 256, 0, st>>>(x, n, ldx, pl->W2, pl->R, pl->F, vec_ok, pl->q_ws[ws_slot]);
+        a.P = P + s0 * ldp;
+        a.N = n;
+        if (int rc = dispatch_gen(a, ctas, st, false)) return rc;
+        NLML_CUDA(cudaGetLastError());
+        pl->launches += 2;
+    }
+    if (ws_slot == 2) NLML_CUDA(cudaEventRecord(pl->q_done, st));
+    return 0;
+}
+
 int launch_fit(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int iters, float lr, float clip,
-               float* P, int64_t ldp, int hint, cudaStream_t st) {
+               float* P, int64_t ldp, int hint, cudaStream_t st, int ws_slot = 2) {
     if (N == 0) return 0;
+    // run-time-rank tensor-core kernel: asked for, or the default for every rank set without compiled kernels
+    if (hint == 6 && !pl->gen_ok)
+        return set_error(NLML_E_UNSUPPORTED, "the run-time-rank tensor-core kernel serves roll ranks <= 8 and other ranks <= %d", tgen::kMaxRank);
+    if (hint == 2 && !pl->cta_ok)
+        return set_error(NLML_E_UNSUPPORTED, "core too large for the CTA-per-sample kernel's shared-memory working set");
+    if (hint == 6 || (hint == 0 && !pl->fast && pl->gen_ok && (N >= 32 || !pl->cta_ok)))
+        return launch_gen(pl, X, N, ldx, iters, lr, clip, P, ldp, ws_slot, st);
     TuckerArgs a = pl->base;
     a.X = X;
     a.N = N;
@@ -1223,13 +1364,17 @@ int launch_fit(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int
     a.lr = lr;
     a.clip = clip;
     a.vec_ok = (pl->F % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
-    if (const char* e = std::getenv("NLML_TUCKER_DBG")) a.dbg = std::atoi(e);
+#ifdef NLML_TC_DBG
+    if (const char* e = std::getenv("NLML_TUCKER_DBG")) a.dbg = std::atoi(e);   // development build only
+#endif
     // crossover: below ~one thread-per-sample wave the 3000-step chain is latency bound and the
     // CTA-per-sample kernel finishes sooner
     // large batches: the tensor-core iteration kernel (2.6 M poses/s) beats the FP32 thread-per-sample kernel (0.92 M)
-    const bool use_tc = pl->fast && (hint == 5 || (hint == 0 && N >= kTcCrossover));
+    const bool use_tc = pl->fast && (hint == 5 || (hint == 0 && N >= tc_crossover(pl)));
     const bool use_tps = pl->fast && !use_tc && (hint == 1 || hint == 4 || (hint == 0 && N >= kWpsCrossover));
     const bool use_wps = pl->fast && !use_tc && (hint == 3 || (hint == 0 && N < kWpsCrossover));
+    if (!pl->fast && !pl->cta_ok)
+        return set_error(NLML_E_UNSUPPORTED, "core too large for the CTA-per-sample kernel's shared-memory working set");
     if ((hint == 1 || hint == 3 || hint == 4 || hint == 5) && !pl->fast)
         return set_error(NLML_E_UNSUPPORTED, "thread/warp-per-sample kernels are built for ranks (5,3,3,3) only");
     if (use_tc) {
@@ -1284,17 +1429,21 @@ int host_pipeline(nlml_tucker_plan* pl, const float* X_host, int64_t N, int64_t 
     const int np = 3 + pl->ri;
     if (!pl->streams[0]) {
         pl->chunk = (int64_t)pl->num_sms * TcFitCfg::THREADS * 8;   // 8 waves of the tensor-core kernel per chunk
+        if (!pl->fast && pl->gen_ok) pl->chunk = gen_chunk(pl);
         for (int i = 0; i < 2; ++i) NLML_CUDA(cudaStreamCreateWithFlags(&pl->streams[i], cudaStreamNonBlocking));
     }
     // staging grows to the largest chunk seen (single-sample calls through TD_Tester.Test stay small)
     const int64_t want = std::min<int64_t>(pl->chunk, ceil_div(std::max<int64_t>(N, 1), 128) * 128);
     if (pl->host_rows < want) {
         if (pl->host_rows) NLML_CUDA(cudaDeviceSynchronize());
+        pl->host_rows = 0;   // nothing below is usable until every allocation has succeeded
         for (int i = 0; i < 2; ++i) {
             cudaFree(pl->x_dev[i]);
             cudaFree(pl->p_dev[i]);
             if (pl->p_stage[i]) cudaFreeHost(pl->p_stage[i]);
             pl->x_dev[i] = pl->p_dev[i] = pl->p_stage[i] = nullptr;
+        }
+        for (int i = 0; i < 2; ++i) {
             NLML_CUDA(cudaMalloc(&pl->x_dev[i], sizeof(float) * (size_t)want * pl->F));
             NLML_CUDA(cudaMalloc(&pl->p_dev[i], sizeof(float) * (size_t)want * np));
             NLML_CUDA(cudaMallocHost(&pl->p_stage[i], sizeof(float) * (size_t)want * np));
@@ -1329,7 +1478,7 @@ int host_pipeline(nlml_tucker_plan* pl, const float* X_host, int64_t N, int64_t 
         else
             NLML_CUDA(cudaMemcpy2DAsync(pl->x_dev[slot], sizeof(float) * pl->F, X_host + s0 * ldx, sizeof(float) * ldx,
                                         sizeof(float) * pl->F, (size_t)n, cudaMemcpyHostToDevice, st));
-        if (int rc = launch(pl->x_dev[slot], n, pl->p_dev[slot], st)) return rc;
+        if (int rc = launch(pl->x_dev[slot], n, pl->p_dev[slot], st, slot)) return rc;
         NLML_CUDA(cudaMemcpyAsync(pl->p_stage[slot], pl->p_dev[slot], sizeof(float) * np * n, cudaMemcpyDeviceToHost, st));
         pending[slot].s0 = s0;
         pending[slot].n = n;
@@ -1369,8 +1518,14 @@ extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, i
     pl->NAP = (pl->nA + 3) / 4 * 4;
     pl->nBCD = tri(r_y) * tri(r_p) * tri(r_r);
     pl->nBCDp = (pl->nBCD + 31) / 32 * 32;
-    if (pl->nBCD > kMaxBCD) {
-        return set_error(NLML_E_UNSUPPORTED, "angle-mode ranks (%d,%d,%d) give %d folded entries per identity pair; limit %d",
+    pl->gen_ok = choose_gen_config(r_id, r_y, r_p, r_r, pl->gen);
+    if (pl->gen_ok) {
+        const double tile_bytes = (double)pl->gen.nblocks * ((double)pl->gen.tt_bytes + pl->gen.gt_bytes);
+        if (tile_bytes > 3.0e9) pl->gen_ok = false;
+    }
+    if (pl->nBCD > kMaxBCD && !pl->gen_ok) {
+        return set_error(NLML_E_UNSUPPORTED, "angle-mode ranks (%d,%d,%d) give %d folded entries per identity pair; limit %d "
+                         "(the tensor-core kernel for larger cores needs a roll rank <= 8)",
                          r_y, r_p, r_r, tri(r_y) * tri(r_p) * tri(r_r), kMaxBCD);
     }
     cudaDeviceProp prop;
@@ -1392,7 +1547,12 @@ extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, i
     NLML_CUDA(cudaMemset(pl->St, 0, sizeof(float) * (size_t)pl->nA * pl->nBCDp));
     {
         const int n = pl->R * pl->R;
-        gram_kernel<<<(n + 127) / 128, 128>>>(pl->W2, pl->R, F, M);
+        if (pl->R > 512) {
+            const unsigned nb = (unsigned)ceil_div(pl->R, 64);
+            tgen::gram_tiled_kernel<<<dim3(nb, nb), 256>>>(pl->W2, pl->R, F, M);
+        } else {
+            gram_kernel<<<(n + 127) / 128, 128>>>(pl->W2, pl->R, F, M);
+        }
         const int m = pl->nA * pl->nBCD;
         fold_kernel<<<(m + 127) / 128, 128>>>(M, r_id, r_y, r_p, r_r, pl->NAP, pl->nBCDp, pl->S, pl->St);
         NLML_CUDA(cudaGetLastError());
@@ -1425,12 +1585,26 @@ extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, i
         const size_t with_st = sizeof(float) * cta_layout(F, pl->R, pl->nBCD, pl->nA, pl->nBCDp, true).total;
         pl->st_in_smem = with_st <= 96 * 1024;
         pl->cta_smem = sizeof(float) * cta_layout(F, pl->R, pl->nBCD, pl->nA, pl->nBCDp, pl->st_in_smem).total;
-        if (pl->cta_smem > 220 * 1024) {
-            nlml_tucker_plan_destroy(pl);
+        pl->cta_ok = pl->nBCD <= kMaxBCD && pl->cta_smem <= 220 * 1024;
+        if (!pl->cta_ok && !pl->gen_ok)   // (PlanOwner frees the plan)
             return set_error(NLML_E_UNSUPPORTED, "core too large for the CTA kernel's shared-memory working set");
-        }
-        NLML_CUDA(cudaFuncSetAttribute(tucker_fit_cta_kernel<kCtaThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)pl->cta_smem));
+        if (pl->cta_ok)
+            NLML_CUDA(cudaFuncSetAttribute(tucker_fit_cta_kernel<kCtaThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)pl->cta_smem));
+    }
+    if (pl->gen_ok) {
+        // tile images of S for the run-time-rank tensor-core kernel (hi/lo TF32 planes in the UMMA operand layout)
+        const size_t bytes = (size_t)pl->gen.nblocks * ((size_t)pl->gen.tt_bytes + pl->gen.gt_bytes);
+        NLML_CUDA(cudaMalloc(&pl->gen_tiles, bytes));
+        const long long elems = (long long)pl->gen.nblocks * ((long long)pl->gen.NB * pl->gen.KA + (long long)pl->gen.NA16 * pl->gen.NB);
+        const unsigned grid = (unsigned)std::min<long long>((elems + 255) / 256, (long long)pl->num_sms * 32);
+        tgen::build_tiles_kernel<<<grid, 256>>>(pl->S, pl->NAP, pl->gen, pl->gen_tiles);
+        NLML_CUDA(cudaGetLastError());
+        NLML_CUDA(cudaDeviceSynchronize());
+        pl->launches += 1;
+        tgen::GenArgs ga{};
+        ga.c = pl->gen;
+        if (int rc = dispatch_gen(ga, 1, nullptr, true)) return rc;
     }
     owner.p = nullptr;
     *plan_out = pl;
@@ -1449,6 +1623,9 @@ extern "C" void nlml_tucker_plan_destroy(nlml_tucker_plan* pl) {
     cudaFree(pl->W2);
     cudaFree(pl->S);
     cudaFree(pl->St);
+    cudaFree(pl->gen_tiles);
+    for (int i = 0; i < 3; ++i) cudaFree(pl->q_ws[i]);
+    if (pl->q_done) cudaEventDestroy(pl->q_done);
     delete pl;
 }
 
@@ -1459,7 +1636,7 @@ extern "C" int nlml_tucker_fit_f32(nlml_tucker_plan* pl, const float* X_dev, int
     if (N < 0 || ldx < pl->F || ldp < 3 + pl->ri || iters < 0)
         return set_error(NLML_E_INVALID, "bad sizes: N=%lld ldx=%lld (F=%d) ldp=%lld (need >= %d) iters=%d",
                          (long long)N, (long long)ldx, pl->F, (long long)ldp, 3 + pl->ri, iters);
-    if (kernel_hint < 0 || kernel_hint > 5) return set_error(NLML_E_INVALID, "kernel_hint must be 0..5");
+    if (kernel_hint < 0 || kernel_hint > 6) return set_error(NLML_E_INVALID, "kernel_hint must be 0..6");
     DeviceGuard guard(pl->device);
     return launch_fit(pl, X_dev, N, ldx, iters, lr, clip, P_out_dev, ldp, kernel_hint, (cudaStream_t)stream);
 }
@@ -1471,9 +1648,9 @@ extern "C" int nlml_tucker_fit_host_f32(nlml_tucker_plan* pl, const float* X_hos
     DeviceGuard guard(pl->device);
     const int np = 3 + pl->ri;
     // every chunk runs the kernel the whole batch would get (the first chunks of the ramp are below the cross-over)
-    const int hint = (pl->fast && N >= kTcCrossover) ? 5 : 0;
-    return host_pipeline(pl, X_host, N, ldx, P_out_host, ldp, [&](const float* x, int64_t n, float* p, cudaStream_t st) {
-        return launch_fit(pl, x, n, pl->F, iters, lr, clip, p, np, hint, st);
+    const int hint = (pl->fast && N >= tc_crossover(pl)) ? 5 : 0;
+    return host_pipeline(pl, X_host, N, ldx, P_out_host, ldp, [&](const float* x, int64_t n, float* p, cudaStream_t st, int slot) {
+        return launch_fit(pl, x, n, pl->F, iters, lr, clip, p, np, hint, st, slot);
     });
 }
 
@@ -1494,7 +1671,7 @@ extern "C" int nlml_tucker_solve_host_f32(nlml_tucker_plan* pl, const float* X_h
     if (!pl->fast) return set_error(NLML_E_UNSUPPORTED, "the converged solve is built for ranks (5,3,3,3) only");
     DeviceGuard guard(pl->device);
     const int np = 3 + pl->ri;
-    return host_pipeline(pl, X_host, N, ldx, P_out_host, ldp, [&](const float* x, int64_t n, float* p, cudaStream_t st) {
+    return host_pipeline(pl, X_host, N, ldx, P_out_host, ldp, [&](const float* x, int64_t n, float* p, cudaStream_t st, int) {
         return launch_solve(pl, x, n, pl->F, max_evals, p, np, nullptr, st);
     });
 }
@@ -1503,9 +1680,12 @@ extern "C" int64_t nlml_tucker_launch_count(const nlml_tucker_plan* pl) { return
 
 // test hook: D[128][N] = A[128][K] * B[N][K]^T through the 3xTF32 tcgen05 building block of tucker_tc.cuh
 extern "C" int nlml_debug_tf32_gemm(const float* A_dev, const float* B_dev, int K, int N, float* D_dev) {
-    if (!A_dev || !B_dev || !D_dev) return set_error(NLML_E_INVALID, "null pointer argument");
+    return nlml_debug_tf32_gemm_mode(A_dev, B_dev, K, N, D_dev, 0);
+}
+extern "C" int nlml_debug_tf32_gemm_mode(const float* A_dev, const float* B_dev, int K, int N, float* D_dev, int mode) {
+    if (!A_dev || !B_dev || !D_dev || mode < 0 || mode > 1) return set_error(NLML_E_INVALID, "null pointer argument or bad mode");
     if (K < 8 || K % 8 || K > 64 || N < 16 || N % 16 || N > 256) return set_error(NLML_E_INVALID, "K must be 8..64 (multiple of 8), N 16..256 (multiple of 16)");
-    ttc::TcCheckArgs a{A_dev, B_dev, D_dev, K, N};
+    ttc::TcCheckArgs a{A_dev, B_dev, D_dev, K, N, mode};
     const size_t smem = 2 * ttc::op_bytes(128, K) + 2 * ttc::op_bytes(N, K) + 64;
     NLML_CUDA(cudaFuncSetAttribute(ttc::tc_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ttc::tc_check_kernel<<<1, 128, smem>>>(a);

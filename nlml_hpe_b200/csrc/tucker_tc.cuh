@@ -39,6 +39,22 @@ __device__ __forceinline__ uint64_t make_desc_noswz(uint32_t tile_addr, int K, i
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// the same with the B operand MN-major ("transposed"): bit 16
+__host__ __device__ constexpr uint32_t make_idesc_tf32_bt(int M, int N) { return make_idesc_tf32(M, N) | (1u << 16); }
+// B operand read from the K-major image of its TRANSPOSE: the tile was stored as rows = k (Kt of them), contiguous
+// dimension = n (N of them), i.e. element (n, k) at op_offset(k, n, N).  As an MN-major operand (canonical no-swizzle
+// form ((4,1,m),(8,k)):((1,4,SBO),(16 B,LBO))): 4 consecutive n are contiguous, 8 consecutive k are 16 B apart,
+// SBO = 128 B (next 4 n), LBO = (N/4)*128 B (next 8 k).  Descriptor for the K-slice [k0, k0+8).
+__device__ __forceinline__ uint64_t make_desc_noswz_bt(uint32_t tile_addr, int N, int k0) {
+    const uint32_t lbo = (uint32_t)((N / 4) * 128);
+    const uint32_t addr = tile_addr + (uint32_t)(k0 / 8) * lbo;
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(128 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -110,6 +126,20 @@ __device__ __forceinline__ void issue_gemm_3xtf32(uint32_t tmem_d, uint32_t a_hi
     }
 }
 
+// the same with the B tile stored as the K-major image of its transpose (one copy of a tile then serves two GEMMs:
+// as the K-major B operand of one and the MN-major B operand of the other)
+__device__ __forceinline__ void issue_gemm_3xtf32_bt(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                                     int K, int N, bool first) {
+    const uint32_t idesc = make_idesc_tf32_bt(128, N);
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        const uint64_t dah = make_desc_noswz(a_hi, K, k0), dal = make_desc_noswz(a_lo, K, k0);
+        const uint64_t dbh = make_desc_noswz_bt(b_hi, N, k0), dbl = make_desc_noswz_bt(b_lo, N, k0);
+        umma_tf32(tmem_d, dal, dbh, idesc, !(first && k0 == 0));
+        umma_tf32(tmem_d, dah, dbl, idesc, 1);
+        umma_tf32(tmem_d, dah, dbh, idesc, 1);
+    }
+}
+
 // 3xTF32 GEMM with the A operand in tensor memory: hi part in columns [a_tmem, a_tmem + K), lo part in the next K.
 __device__ __forceinline__ void issue_gemm_3xtf32_ta(uint32_t tmem_d, uint32_t a_tmem, uint32_t b_hi, uint32_t b_lo, int K, int N,
                                                      bool first) {
@@ -128,6 +158,7 @@ struct TcCheckArgs {
     const float* B;   // [N][K]
     float* D;         // [128][N]
     int K, N;
+    int mode;         // 0: B stored K-major.  1: B stored as the K-major image of its transpose, read as an MN-major operand
 };
 
 __global__ void __launch_bounds__(128) tc_check_kernel(const __grid_constant__ TcCheckArgs a) {
@@ -160,8 +191,9 @@ __global__ void __launch_bounds__(128) tc_check_kernel(const __grid_constant__ T
         const int n = idx / K, k = idx % K;
         float hi, lo;
         split_tf32(a.B[idx], hi, lo);
-        *reinterpret_cast<float*>(b_hi + op_offset(n, k, K)) = hi;
-        *reinterpret_cast<float*>(b_lo + op_offset(n, k, K)) = lo;
+        const int off = a.mode == 1 ? op_offset(k, n, N) : op_offset(n, k, K);
+        *reinterpret_cast<float*>(b_hi + off) = hi;
+        *reinterpret_cast<float*>(b_lo + off) = lo;
     }
     fence_async_smem();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -169,7 +201,8 @@ __global__ void __launch_bounds__(128) tc_check_kernel(const __grid_constant__ T
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *slot;
     if (tid == 0) {
-        issue_gemm_3xtf32(tmem, smem_u32(a_hi), smem_u32(a_lo), smem_u32(b_hi), smem_u32(b_lo), K, N, true);
+        if (a.mode == 1) issue_gemm_3xtf32_bt(tmem, smem_u32(a_hi), smem_u32(a_lo), smem_u32(b_hi), smem_u32(b_lo), K, N, true);
+        else issue_gemm_3xtf32(tmem, smem_u32(a_hi), smem_u32(a_lo), smem_u32(b_hi), smem_u32(b_lo), K, N, true);
         umma_commit_to(bar);
     }
     mbar_wait(bar, 0);

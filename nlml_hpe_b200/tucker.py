@@ -15,7 +15,7 @@ import torch
 from . import _lib
 
 KERNEL_HINTS = {"auto": 0, "thread_per_sample": 1, "cta_per_sample": 2, "warp_per_sample": 3,
-                "thread_per_sample_tmem": 4, "tensor_core": 5}
+                "thread_per_sample_tmem": 4, "tensor_core": 5, "tensor_core_generic": 6}
 
 
 def _device_index(device):

@@ -121,3 +121,10 @@ def test_plan_cache_key_follows_the_constants(art, rows):
     assert TD_Tester._content_key(W, r2, None) != k0
     assert TD_Tester._content_key(W, r, "cuda:1") != k0
     assert TD_Tester._content_key(W.reshape(5, 3, 3, 1, 3 * 1404), r, None) != k0      # same bytes, other ranks
+    # the per-object fast path: the same array object is hashed once, and an in-place change of it is noticed
+    assert TD_Tester._content_key(W, r, None) == k0
+    keep = W[2, 1, 1, 1, 5]
+    W[2, 1, 1, 1, 5] = np.nextafter(keep, np.float32(np.inf))
+    assert TD_Tester._content_key(W, r, None) != k0
+    W[2, 1, 1, 1, 5] = keep
+    assert TD_Tester._content_key(W, r, None) == k0

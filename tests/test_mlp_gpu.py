@@ -113,7 +113,7 @@ def test_random_weights_and_inputs(cuda_lib):
     X = torch.randn(513, 1404)
     out = model.predict(X.cuda()).cpu().numpy()
     ref = mlp_oracle.forward(*sds, X.numpy())
-    assert np.abs(out - ref).max() < 2e-5
+    assert np.abs(out - ref).max() < 1.7e-5   # 1e-3 degrees (BASELINE.json north_star) in radians
 
 
 def test_full_size_properties_1M(model, art, rows):
