@@ -241,6 +241,126 @@ def cpu_baseline_mlp(art, cores, n=16384, reps=3):
                       "oracle.mlp_oracle.forward = restatement of NLML_HPE_Model_Builder.py:115-126"}
 
 
+ENLARGED = [  # BASELINE.json configs[4]: enlarged synthetic cores (higher rank), full feature count, T = 3000
+    {"ranks": (8, 5, 5, 5), "waves": 4, "steps": 2, "cpu_iters": 3000},
+    {"ranks": (16, 8, 8, 8), "waves": 1, "steps": 1, "cpu_iters": 100},
+]
+
+
+def tri(r):
+    return r * (r + 1) // 2
+
+
+def enlarged_problem(ranks, seed=11):
+    from nlml_hpe_b200 import synthetic
+    G = synthetic.synthetic_core(ranks, F, seed=seed, std=1.0)
+    rws = [synthetic.synthetic_cos_params(r, 21 + i) for i, r in enumerate(ranks[1:])]
+    return G, rws
+
+
+def cpu_baseline_enlarged(ranks, cores, iters):
+    """oracle port of TD_Tester.optimize_with_sgd on the enlarged core, one sample per worker process (1 thread each),
+    `iters` iterations timed and scaled to T = 3000 (every iteration costs the same: two einsums over the core)."""
+    from concurrent.futures import ProcessPoolExecutor
+    from nlml_hpe_b200 import synthetic
+    G, rws = enlarged_problem(ranks)
+    n = min(cores, 16)
+    X = synthetic.make_features(n, G, *rws, U_id=None, seed=1234)
+    with ProcessPoolExecutor(max_workers=n, initializer=_pin_worker, initargs=(n,)) as pool:
+        list(pool.map(_cpu_warm_worker, range(n)))
+        t0 = time.perf_counter()
+        list(pool.map(_cpu_tucker_worker_iters, [(G, X[i], rws, iters) for i in range(n)]))
+        dt = time.perf_counter() - t0
+    per_pose = dt * T_ITERS / iters
+    return {"value": n / per_pose, "unit": "poses/s", "cores": n, "kind": "port",
+            "s_per_sample_per_core": per_pose,
+            "sample": f"{n} samples (one per pinned worker process, 1 thread each), {iters} of T={T_ITERS} iterations timed "
+                      f"({dt:.1f} s) and scaled; oracle.tucker_oracle.sgd_reference_form on the ranks {ranks} core"}
+
+
+def _cpu_tucker_worker_iters(args):
+    import torch
+    torch.set_num_threads(1)
+    from oracle import tucker_oracle
+    W, x, rows, iters = args
+    return tucker_oracle.sgd_reference_form(W, x, *rows, lr=LR, iters=iters, clip=CLIP)
+
+
+_PIN_COUNTER = None
+
+
+def _pin_worker(n_workers):
+    """ProcessPoolExecutor initializer: pin each worker to its own CPU (one worker per core, no migration), so the two
+    CPU legs of a run agree (1.70 vs 3.72 poses/s for the same leg minutes apart, unpinned)."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        import multiprocessing as mp
+        ident = mp.current_process()._identity
+        k = (ident[0] - 1) if ident else 0
+        os.sched_setaffinity(0, {cpus[(k * max(1, len(cpus) // max(1, n_workers))) % len(cpus)]})
+    except Exception:
+        pass
+
+
+def bench_enlarged(spec, fitter_cls, torch, dist, world, rank, dev, num_sms, tf32_peak, peaks, with_cpu):
+    """One enlarged-core record: device-resident value, host-buffer e2e, tensor roofline (useful and issued), CPU port."""
+    from nlml_hpe_b200 import synthetic
+    ranks = spec["ranks"]
+    G, rws = enlarged_problem(ranks)
+    n = spec["waves"] * num_sms * 128
+    t0 = time.perf_counter()
+    fit = fitter_cls(G, *rws, device=dev)
+    torch.cuda.synchronize()
+    plan_s = time.perf_counter() - t0
+    X = synthetic.make_features_torch(n, G, *rws, U_id=None, seed=77 + rank, device=dev, chunk=8192)
+    Xh = torch.empty((n, F), dtype=torch.float32, pin_memory=True)
+    Xh.copy_(X)
+    np_ = 3 + ranks[0]
+    P = torch.empty((n, np_), dtype=torch.float32, device=dev)
+    Ph = np.empty((n, np_), dtype=np.float32)
+    fit.fit(X, 3, LR, CLIP, out=P)                       # warm-up: first launch, q workspace
+    fit.fit_host(Xh.numpy()[: 2 * 128], 3, LR, CLIP)
+    l0 = fit.launches
+    ms, _ = time_steps(lambda: fit.fit(X, T_ITERS, LR, CLIP, out=P), spec["steps"], 0, torch, dist, world)
+    launches = fit.launches - l0
+    ms /= spec["steps"]
+    ms_e = time_host_steps(lambda: fit.fit_host(Xh.numpy(), T_ITERS, LR, CLIP, out=Ph), 1, 0, torch, dist, world)
+    fit.close()
+    del X, Xh, P
+    torch.cuda.empty_cache()
+    ri, ry, rp, rr = ranks
+    nA, nBCD, R = tri(ri), tri(ry) * tri(rp) * tri(rr), ri * ry * rp * rr
+    useful = T_ITERS * 2 * (2 * nA * nBCD)                       # the two contractions with the folded Gram tensor, per pose
+    # issued: padded columns x (KA + NA16) x 3 passes (the kernel's configuration is re-derived as in choose_gen_config)
+    rrmax = 5 if rr <= 5 else 8
+    ndp = (tri(rrmax) + 7) // 8 * 8
+    KA, NA16 = (nA + 7) // 8 * 8, (nA + 15) // 16 * 16
+    issued_lo = T_ITERS * 2 * 3 * (tri(ry) * tri(rp) * ndp) * (KA + NA16)
+    per_gpu = n / (ms * 1e-3)
+    rec = {
+        "ranks": list(ranks), "R": R, "F": F, "T": T_ITERS,
+        "metric": "poses/sec (Tucker-fit, enlarged core, run-time-rank tensor-core kernel)",
+        "value": n * world / (ms * 1e-3), "unit": "poses/s", "ms_per_step": ms, "steps": spec["steps"], "dtype": "f32",
+        "config": {"workload": f"BASELINE.json configs[4]: synthetic core ranks {ranks} (W {R}x{F} f32 = {R * F * 4 / 1e6:.1f} MB, folded Gram tensor "
+                               f"{nA}x{nBCD} = {nA * nBCD * 4 / 1e6:.1f} MB), {n} synthetic feature vectors per GPU, T={T_ITERS}",
+                   "samples_per_gpu": n, "plan_create_s": plan_s},
+        "e2e": {"value": n * world / (ms_e * 1e-3), "unit": "poses/s", "h2d_bytes_per_step": n * F * 4, "d2h_bytes_per_step": n * np_ * 4,
+                "steps": 1, "api": "nlml_tucker_fit_host_f32 (pinned host X -> host P)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": tf32_peak, "peak_source": "measured live: nlml_measure_tf32_tflops (dense TF32 tcgen05 probe)",
+                     "achieved": per_gpu * useful / 1e12, "frac": per_gpu * useful / 1e12 / tf32_peak,
+                     "issued_frac": per_gpu * issued_lo / 1e12 / tf32_peak, "mma_passes": 3, "traffic": None,
+                     "kernel": "tucker_fit_gen_kernel",
+                     "note": f"useful = T x 2 x (2 x {nA} x {nBCD}) flop per pose (both contractions with the folded Gram tensor); "
+                             "issued counts the 3xTF32 passes and the padding of the pair / roll-pair axes"},
+        "roofline_hbm": {"bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"], "achieved": per_gpu * (F * 4 + np_ * 4) / 1e9,
+                         "frac": per_gpu * (F * 4 + np_ * 4) / 1e9 / peaks["hbm_gbs"]},
+    }
+    if with_cpu:
+        rec["cpu_baseline"] = cpu_baseline_enlarged(ranks, os.cpu_count() or 1, spec["cpu_iters"])
+    return rec
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -282,6 +402,10 @@ def run_b200(args):
     _lib.check(lib.nlml_measure_fp32_tflops(local, ctypes.byref(fp32_peak)))
     _lib.check(lib.nlml_measure_fp32_tflops_3reg(local, ctypes.byref(fp32_peak_3reg)))
     fp32_peak, fp32_peak_3reg = fp32_peak.value, fp32_peak_3reg.value
+    tf32_peak = ctypes.c_double()
+    _lib.check(lib.nlml_measure_tf32_tflops(local, ctypes.byref(tf32_peak)))
+    tf32_peak = tf32_peak.value
+    num_sms = torch.cuda.get_device_properties(dev).multi_processor_count
 
     result = {}
     with ClockSampler(local) as clocks:
@@ -316,6 +440,14 @@ def run_b200(args):
         ms_me = time_host_steps(lambda: model.predict_host(X_host.numpy()), e2e_steps, 1, torch, dist, world)
         mlp_e2e_ms = ms_me / e2e_steps
     clk2 = clocks2.summary()
+
+    enlarged = []
+    if not args.no_enlarged:
+        del model
+        torch.cuda.empty_cache()
+        for spec in ENLARGED:
+            enlarged.append(bench_enlarged(spec, TuckerFitter, torch, dist, world, rank, dev, num_sms, tf32_peak, peaks,
+                                           with_cpu=(world == 1 and rank == 0 and not args.no_cpu_baseline)))
 
     if rank != 0:
         if world > 1:
@@ -399,7 +531,9 @@ def run_b200(args):
                              "unit": "GB/s", "frac": per_gpu_m * MLP_BYTES_PER_POSE / 1e9 / peaks["hbm_gbs"]},
             "clocks": {"sm_mhz": clk2["sm_mhz"], "sm_max_mhz": clk2["sm_max_mhz"], "reasons": clk2["reasons"]},
         },
+        "enlarged": enlarged,
         "fp32_fma_peak_tflops_measured": fp32_peak, "fp32_fma_3reg_peak_tflops_measured": fp32_peak_3reg,
+        "tf32_tensor_peak_tflops_measured": tf32_peak,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_tucker(art, rows, cores)
@@ -455,6 +589,7 @@ def main():
     ap.add_argument("--samples", type=int, default=1_000_000, help="feature vectors per GPU per step")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-enlarged", action="store_true", help="skip the enlarged-core records (BASELINE.json configs[4])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

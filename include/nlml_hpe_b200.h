@@ -150,6 +150,10 @@ int nlml_measure_fp32_tflops(int device, double* tflops_out);
  * that bounds an FMA stream whose multiplier and addend both change, like the fit kernel's inner loop. */
 int nlml_measure_fp32_tflops_3reg(int device, double* tflops_out);
 
+/* Dense TF32 tensor-core rate (TFLOP/s): back-to-back tcgen05.mma.kind::tf32 128x256x8 from shared-memory operands on
+ * every SM.  The denominator of the Tucker-fit kernels' tensor roofline (bench.py measures it live). */
+int nlml_measure_tf32_tflops(int device, double* tflops_out);
+
 /* Test hook (current device): D[128][N] = A[128][K] * B[N][K]^T through the 3xTF32 tcgen05 building block used by
  * the tensor-core Tucker iteration.  K in 8..64 (multiple of 8), N in 16..256 (multiple of 16).  Synchronous. */
 int nlml_debug_tf32_gemm(const float* A_dev, const float* B_dev, int K, int N, float* D_dev);

@@ -19,7 +19,7 @@ EXPORTS = [
     "nlml_tucker_fit_host_f32", "nlml_tucker_solve_f32", "nlml_tucker_solve_host_f32", "nlml_tucker_launch_count",
     "nlml_mlp_plan_create", "nlml_mlp_plan_destroy", "nlml_mlp_forward_f32",
     "nlml_mlp_forward_host_f32", "nlml_mlp_forward_landmarks_f32", "nlml_mlp_forward_landmarks_host_f32", "nlml_pose_postprocess_f64", "nlml_mlp_latent_f32", "nlml_mlp_launch_count", "nlml_mlp_set_path",
-    "nlml_measure_fp32_tflops", "nlml_measure_fp32_tflops_3reg", "nlml_debug_tf32_gemm", "nlml_debug_tf32_gemm_mode",
+    "nlml_measure_fp32_tflops", "nlml_measure_fp32_tflops_3reg", "nlml_measure_tf32_tflops", "nlml_debug_tf32_gemm", "nlml_debug_tf32_gemm_mode",
 ]
 
 _lib = None
@@ -65,6 +65,7 @@ def load():
     lib.nlml_mlp_set_path.argtypes = [vp, i32]
     lib.nlml_measure_fp32_tflops.argtypes = [i32, c_double_p]
     lib.nlml_measure_fp32_tflops_3reg.argtypes = [i32, c_double_p]
+    lib.nlml_measure_tf32_tflops.argtypes = [i32, c_double_p]
     lib.nlml_debug_tf32_gemm.argtypes = [vp, vp, i32, i32, vp]
     lib.nlml_debug_tf32_gemm_mode.argtypes = [vp, vp, i32, i32, vp, i32]
     _lib = lib

@@ -1174,6 +1174,50 @@ __global__ void __launch_bounds__(256) ffma_3reg_kernel(float* out, const float*
     out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+// back-to-back tcgen05.mma.kind::tf32 (M = 128, N = 256, K = 8, operands in shared memory, two TMEM accumulators):
+// measures the dense TF32 tensor rate of the device, the denominator of the Tucker kernels' tensor roofline
+__global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters) {
+    extern __shared__ __align__(1024) uint8_t psm[];
+    constexpr int K = 64;
+    uint8_t* a_t = psm;                                  // [128][64]
+    uint8_t* b_t = psm + ttc::op_bytes(128, K);           // [256][64]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(b_t + ttc::op_bytes(256, K));
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    for (int i = tid; i < (ttc::op_bytes(128, K) + ttc::op_bytes(256, K)) / 4; i += 128) reinterpret_cast<float*>(psm)[i] = 1.0f + 1e-3f * (float)(i & 63);
+    if (tid == 0) {
+        ttc::mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc_cols(slot, 512);
+    ttc::fence_async_smem();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *slot;
+    if (warp == 0) {
+        const uint32_t idesc = ttc::make_idesc_tf32(128, 256);
+        for (int it = 0; it < iters; ++it) {
+            uint64_t da = ttc::make_desc_noswz(ttc::smem_u32(a_t), K, 0), db = ttc::make_desc_noswz(ttc::smem_u32(b_t), K, 0);
+#pragma unroll
+            for (int k = 0; k < K / 8; ++k) {
+                asm volatile(
+                    "{\n\t.reg .pred p, e;\n\t"
+                    "elect.sync _|e, 0xffffffff;\n\t"
+                    "setp.ne.b32 p, %4, 0;\n\t"
+                    "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                    ::"r"(tmem + (uint32_t)((k & 1) * 256)), "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)(it > 0 || k > 1)) : "memory");
+                da += 16; db += 16;
+            }
+        }
+        ttc::umma_commit_elect(bar);
+    }
+    ttc::mbar_wait(bar, 0);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_free_cols(tmem, 512);
+}
+
 }  // namespace nlml
 
 // =============================================================================================
@@ -1244,30 +1288,45 @@ bool choose_gen_config(int ri, int ry, int rp, int rr, tgen::GenCfg& best) {
     b.t_dcp = b.t_cp + rp; b.t_rows = b.t_dcp + rp;
     const int tab_bytes = b.t_rows * tgen::kSamples * 4, bar_bytes = 1024;
     double best_score = -1.0;
+#ifdef NLML_GEN_TUNE
+    // development build only (-DNLML_GEN_TUNE): pin parts of the configuration from the environment for sweeps
+    auto pin = [](const char* name) { const char* e = std::getenv(name); return e ? std::atoi(e) : 0; };
+    const int pin_bcp = pin("NLML_GEN_BCP"), pin_tb = pin("NLML_GEN_TB"), pin_gb = pin("NLML_GEN_GB"), pin_yb = pin("NLML_GEN_YB"),
+              pin_slots = pin("NLML_GEN_SLOTS"), pin_ytm = pin("NLML_GEN_YTM");   // YTM: 1 = shared memory, 2 = tensor memory
+#else
+    constexpr int pin_bcp = 0, pin_tb = 0, pin_gb = 0, pin_yb = 0, pin_slots = 0, pin_ytm = 0;
+#endif
     for (int BCP = 1; BCP <= 32; ++BCP) {
+        if (pin_bcp && BCP != pin_bcp) continue;
         const int NB = (BCP * b.nDp + 15) / 16 * 16;   // MMA N granularity; pad columns hold zeros in the tiles and the operand
         if (NB > 256) continue;
         const int nblocks = (b.nBC + BCP - 1) / BCP;
+        for (int ytm = 1; ytm >= 0; --ytm)   // the YPR operand in tensor memory (preferred: shared-memory bandwidth is the scarce resource) or in shared memory
         for (int tbufs = 2; tbufs >= 1; --tbufs)
             for (int gbufs = 2; gbufs >= 1; --gbufs) {
-                if (gbufs * b.NA16 + 2 * b.KA + tbufs * NB > 512) continue;
+                if ((pin_tb && tbufs != pin_tb) || (pin_gb && gbufs != pin_gb)) continue;
                 for (int ybufs = 2; ybufs >= 1; --ybufs) {
-                    const int tt = NB * b.KA * 8, gt = b.NA16 * NB * 8, ypr = ybufs * NB * tgen::kSamples * 8;
+                    const int cols = gbufs * b.NA16 + 2 * b.KA + tbufs * NB + (ytm ? ybufs * 2 * NB : 0);
+                    if (cols > 512) continue;
+                    const int tt = NB * b.KA * 8, gt = b.NA16 * NB * 8, ypr = ytm ? 0 : ybufs * NB * tgen::kSamples * 8;
                     const int avail = kGenSmemMax - 1024 - ypr - tab_bytes - bar_bytes;
                     if (avail < tt + gt) continue;
-                    const bool resident = nblocks <= tgen::kMaxSlots && (long long)nblocks * (tt + gt) <= avail;
-                    const int slots = resident ? nblocks : std::min(4, avail / (tt + gt));
+                    if (pin_yb && ybufs != pin_yb) continue;
+                    if (pin_ytm && ytm != pin_ytm - 1) continue;
+                    const bool resident = !pin_slots && nblocks <= tgen::kMaxSlots && (long long)nblocks * (tt + gt) <= avail;
+                    int slots = resident ? nblocks : std::min(4, avail / (tt + gt));
+                    if (pin_slots) slots = std::min(slots, pin_slots);
                     const double waste = (double)nblocks * NB / ((double)b.nBC * tri(rr)) - 1.0;   // padded columns issued per useful one
-                    const double score = (resident ? 100.0 : 10.0 * std::min(slots, 3)) + 6.0 * ybufs + 4.0 * tbufs + 3.0 * gbufs +
-                                         (NB >= 64 ? 8.0 : NB >= 48 ? 6.0 : NB >= 32 ? 4.0 : 0.0) - 20.0 * waste;
+                    const double score = (resident ? 40.0 : 10.0 * std::min(slots, 3)) + 6.0 * ybufs + 4.0 * tbufs + 3.0 * gbufs + 30.0 * ytm +
+                                         0.25 * std::min(NB, 128) - 20.0 * waste;
                     if (score <= best_score) continue;
                     best_score = score;
                     best = b;
                     best.BCP = BCP; best.NB = NB; best.nblocks = nblocks;
-                    best.tbufs = tbufs; best.gbufs = gbufs; best.ybufs = ybufs;
+                    best.tbufs = tbufs; best.gbufs = gbufs; best.ybufs = ybufs; best.ypr_tmem = ytm;
                     best.tslots = best.gslots = slots; best.resident = resident ? 1 : 0;
                     best.tt_bytes = tt; best.gt_bytes = gt;
-                    best.col_g = 0; best.col_a = gbufs * b.NA16; best.col_t = best.col_a + 2 * b.KA;
+                    best.col_g = 0; best.col_a = gbufs * b.NA16; best.col_t = best.col_a + 2 * b.KA; best.col_y = best.col_t + tbufs * NB;
                     best.off_tring = 0;
                     best.off_gring = slots * tt;
                     best.off_ypr = best.off_gring + slots * gt;
@@ -1676,6 +1735,14 @@ extern "C" int nlml_tucker_solve_host_f32(nlml_tucker_plan* pl, const float* X_h
     });
 }
 
+#ifdef NLML_GEN_TIMING
+extern "C" int nlml_debug_gen_timing(float* host_out /*[64]*/) {   // development build only
+    NLML_CUDA(cudaDeviceSynchronize());
+    NLML_CUDA(cudaMemcpyFromSymbol(host_out, tgen::g_gen_timing, sizeof(float) * 64));
+    return 0;
+}
+#endif
+
 extern "C" int64_t nlml_tucker_launch_count(const nlml_tucker_plan* pl) { return pl ? pl->launches : 0; }
 
 // test hook: D[128][N] = A[128][K] * B[N][K]^T through the 3xTF32 tcgen05 building block of tucker_tc.cuh
@@ -1691,6 +1758,36 @@ extern "C" int nlml_debug_tf32_gemm_mode(const float* A_dev, const float* B_dev,
     ttc::tc_check_kernel<<<1, 128, smem>>>(a);
     NLML_CUDA(cudaGetLastError());
     NLML_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+
+extern "C" int nlml_measure_tf32_tflops(int device, double* tflops_out) {
+    if (!tflops_out) return set_error(NLML_E_INVALID, "null pointer argument");
+    if (int rc = check_device(device)) return rc;
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    NLML_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount, iters = 2048;
+    const size_t smem = ttc::op_bytes(128, 64) + ttc::op_bytes(256, 64) + 64;
+    NLML_CUDA(cudaFuncSetAttribute(tf32_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1;
+    NLML_CUDA(cudaEventCreate(&e0));
+    NLML_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        NLML_CUDA(cudaEventRecord(e0));
+        tf32_peak_kernel<<<blocks, 128, smem>>>(iters);
+        NLML_CUDA(cudaEventRecord(e1));
+        NLML_CUDA(cudaEventSynchronize(e1));
+        NLML_CUDA(cudaGetLastError());
+        float ms = 0.f;
+        NLML_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 128 * 256 * 8 * 8.0 * (double)iters * blocks;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops_out = best;
     return 0;
 }
 

@@ -42,7 +42,9 @@ struct GenCfg {
     int nC, nBC;             // pitch pairs, (yaw pair, pitch pair) combinations
     int nDp;                 // roll pairs of the rrmax triangle padded to 8 = columns per (b,c) pair
     int BCP, NB, nblocks;    // (b,c) pairs per block, columns per block (multiple of 16), blocks per iteration
-    int tbufs, gbufs, ybufs; // TMEM buffers of D_T and D_G, shared-memory buffers of the YPR operand
+    int tbufs, gbufs, ybufs; // TMEM buffers of D_T and D_G, buffers of the YPR operand
+    int ypr_tmem;            // the YPR operand lives in tensor memory (hi | lo columns) instead of shared memory
+    int col_y;               // its first TMEM column
     int tslots, gslots;      // ring slots of T tiles / G tiles
     int resident;            // every tile has its own slot and is loaded once
     int tt_bytes, gt_bytes;  // bytes of one T tile / G tile (hi plane + lo plane)
@@ -91,6 +93,18 @@ __device__ __forceinline__ void tc_before() { asm volatile("tcgen05.fence::befor
 __device__ __forceinline__ void tc_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
+#ifdef NLML_GEN_TIMING
+// development build only: per-phase cycle counts of one lane per role of CTA 0 (scripts/time_gen.py)
+__device__ float g_gen_timing[64];
+#define GT_DECL float gt_acc[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; uint32_t gt_prev = (uint32_t)clock();
+#define GT(i) { const uint32_t gt_now = (uint32_t)clock(); gt_acc[i] += (float)(gt_now - gt_prev); gt_prev = gt_now; }
+#define GT_OUT(role) if (blockIdx.x == 0 && lane == 0 && (warp & 3) == 1) { for (int i = 0; i < 10; ++i) g_gen_timing[(role) * 16 + i] = gt_acc[i] / (float)a.T; }
+#else
+#define GT_DECL
+#define GT(i)
+#define GT_OUT(role)
+#endif
+
 // roll features (static class RRMAX): c_l, dc_l for l < rr (0 beyond), and the monomials RR_d = c_i c_j with their
 // derivative along the roll angle, d = pair_index(i, j, RRMAX), padded with zeros to NDP
 template <int RRMAX, int NDP>
@@ -118,6 +132,19 @@ __device__ __forceinline__ void roll_features(float w, const float* rows_r, int 
             dRR[pair_index(i, j, RRMAX)] = fmaf(dcr[i], cr[j], cr[i] * dcr[j]);
         }
 }
+
+// position in a ring of n buffers guarded by mbarriers: index and phase parity, advanced without divisions
+struct Ring {
+    int idx, n;
+    uint32_t phase;
+    __device__ __forceinline__ Ring(int n_) : idx(0), n(n_), phase(0) {}
+    __device__ __forceinline__ void next() {
+        if (++idx == n) {
+            idx = 0;
+            phase ^= 1u;
+        }
+    }
+};
 
 // walk over the (b,c) pairs in storage order: b = (bi <= bj) over the yaw rank, c = (ci <= cj) over the pitch rank, c fastest
 struct PairWalk {
@@ -165,7 +192,9 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
     uint64_t* uu_ready = aempty + 2;           // UU operand of this iteration is in tensor memory
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(uu_ready + 1);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, group = warp >> 2;
+    // the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the MMA warp's descriptor
+    // arithmetic in the uniform datapath (without it every tcgen05.mma is preceded by a register->uniform broadcast loop)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31, group = warp >> 2;
     const int row = tid & 127;
     const long long s0 = (long long)blockIdx.x * kSamples;
     const int nblocks = c.nblocks, NB = c.NB, KA = c.KA, NA16 = c.NA16;
@@ -187,7 +216,8 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
     // p = 0 (TD_Tester.py:130) and the gradient exchange rows
     for (int i = tid; i < c.t_rows * kSamples; i += kThreads) tab[i] = 0.f;
     // the YPR operand's pad columns (NB is rounded up to the MMA's N granularity) are never written again: zero them once
-    for (int i = tid; i < c.ybufs * 2 * NB * kSamples; i += kThreads) reinterpret_cast<float*>(gsm + c.off_ypr)[i] = 0.f;
+    if (!c.ypr_tmem)
+        for (int i = tid; i < c.ybufs * 2 * NB * kSamples; i += kThreads) reinterpret_cast<float*>(gsm + c.off_ypr)[i] = 0.f;
     ttc::fence_async_smem();
     tc_before();
     __syncthreads();
@@ -209,60 +239,71 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
                     bulk_load(gsm + c.off_gring + (size_t)j * gt, a.tiles + j * stride + tt, gt, &fullG[j]);
                 }
             } else {
-                long long kb = 0;
+                Ring ts(c.tslots), gs(c.gslots);
                 for (int it = 0; it < a.T; ++it)
-                    for (int j = 0; j < nblocks; ++j, ++kb) {
-                        const int ts = (int)(kb % c.tslots), gs = (int)(kb % c.gslots);
-                        ttc::mbar_wait(&emptyT[ts], (uint32_t)((kb / c.tslots) & 1) ^ 1u);
-                        mbar_expect_tx(&fullT[ts], tt);
-                        bulk_load(gsm + c.off_tring + (size_t)ts * tt, a.tiles + j * stride, tt, &fullT[ts]);
-                        ttc::mbar_wait(&emptyG[gs], (uint32_t)((kb / c.gslots) & 1) ^ 1u);
-                        mbar_expect_tx(&fullG[gs], gt);
-                        bulk_load(gsm + c.off_gring + (size_t)gs * gt, a.tiles + j * stride + tt, gt, &fullG[gs]);
+                    for (int j = 0; j < nblocks; ++j, ts.next(), gs.next()) {
+                        ttc::mbar_wait(&emptyT[ts.idx], ts.phase ^ 1u);
+                        mbar_expect_tx(&fullT[ts.idx], tt);
+                        bulk_load(gsm + c.off_tring + (size_t)ts.idx * tt, a.tiles + j * stride, tt, &fullT[ts.idx]);
+                        ttc::mbar_wait(&emptyG[gs.idx], gs.phase ^ 1u);
+                        mbar_expect_tx(&fullG[gs.idx], gt);
+                        bulk_load(gsm + c.off_gring + (size_t)gs.idx * gt, a.tiles + j * stride + tt, gt, &fullG[gs.idx]);
                     }
             }
-        } else if (warp == 1 && lane == 0) {
-            // ===== MMA issuer =====
+        } else if (warp == 1) {
+            // ===== MMA issuer: the whole warp runs the loop with warp-uniform values (descriptor arithmetic in the uniform
+            // datapath); lane 0 issues the MMAs and commits =====
             const uint32_t ypr_plane = (uint32_t)NB * kSamples * 4;   // one plane of one YPR operand buffer
-            long long kb = 0;
+            Ring ts(c.resident ? nblocks : c.tslots), gs(c.resident ? nblocks : c.gslots), tb(c.tbufs), gb(c.gbufs), yb(c.ybufs);
+            GT_DECL
             for (int it = 0; it < a.T; ++it) {
                 ttc::mbar_wait(uu_ready, (uint32_t)(it & 1));
-                for (int j = 0; j < nblocks; ++j, ++kb) {
-                    const int ts = c.resident ? j : (int)(kb % c.tslots), gs = c.resident ? j : (int)(kb % c.gslots);
-                    const int tb = (int)(kb % c.tbufs), gb = (int)(kb % c.gbufs), yb = (int)(kb % c.ybufs);
-                    // GEMM-T: D_T[tb] = UU (tensor memory) x T tile
-                    if (!c.resident) ttc::mbar_wait(&fullT[ts], (uint32_t)((kb / c.tslots) & 1));
-                    else if (it == 0) ttc::mbar_wait(&fullT[ts], 0);
-                    ttc::mbar_wait(&tempty[tb], (uint32_t)((kb / c.tbufs) & 1) ^ 1u);
+                GT(0)   // wait for the UU operand
+                for (int j = 0; j < nblocks; ++j, ts.next(), gs.next(), tb.next(), gb.next(), yb.next()) {
+                    // GEMM-T: D_T[tb] = UU (tensor memory) x T tile        (resident tiles: ts.idx == j, loaded once)
+                    if (!c.resident || it == 0) ttc::mbar_wait(&fullT[ts.idx], c.resident ? 0u : ts.phase);
+                    GT(1)   // wait T tile
+                    ttc::mbar_wait(&tempty[tb.idx], tb.phase ^ 1u);
+                    GT(2)   // wait D_T buffer
                     tc_after();
                     {
-                        const uint32_t t_hi = ttc::smem_u32(gsm + c.off_tring + (size_t)ts * c.tt_bytes);
-                        ttc::issue_gemm_3xtf32_ta(tmem + c.col_t + tb * NB, tmem + c.col_a, t_hi, t_hi + c.tt_bytes / 2, KA, NB, true);
+                        const uint32_t t_hi = ttc::smem_u32(gsm + c.off_tring) + (uint32_t)ts.idx * (uint32_t)c.tt_bytes;
+                        ttc::gemm3_ts(tmem + c.col_t + tb.idx * NB, tmem + c.col_a, t_hi, t_hi + c.tt_bytes / 2, KA, NB);
                     }
-                    ttc::umma_commit_to(&tfull[tb]);
-                    if (!c.resident) ttc::umma_commit_to(&emptyT[ts]);
+                    ttc::umma_commit_elect(&tfull[tb.idx]);
+                    if (!c.resident) ttc::umma_commit_elect(&emptyT[ts.idx]);
+                    GT(3)   // issue GEMM-T
                     // GEMM-G: D_G[gb] = YPR block (shared memory) x G tile
-                    if (!c.resident) ttc::mbar_wait(&fullG[gs], (uint32_t)((kb / c.gslots) & 1));
-                    else if (it == 0) ttc::mbar_wait(&fullG[gs], 0);
-                    ttc::mbar_wait(&afull[yb], (uint32_t)((kb / c.ybufs) & 1));
-                    ttc::mbar_wait(&gempty[gb], (uint32_t)((kb / c.gbufs) & 1) ^ 1u);
+                    if (!c.resident || it == 0) ttc::mbar_wait(&fullG[gs.idx], c.resident ? 0u : gs.phase);
+                    GT(4)   // wait G tile
+                    ttc::mbar_wait(&afull[yb.idx], yb.phase);
+                    GT(5)   // wait YPR operand
+                    ttc::mbar_wait(&gempty[gb.idx], gb.phase ^ 1u);
+                    GT(6)   // wait D_G buffer
                     tc_after();
                     {
-                        const uint32_t g_hi = ttc::smem_u32(gsm + c.off_gring + (size_t)gs * c.gt_bytes);
-                        const uint32_t y_hi = ttc::smem_u32(gsm + c.off_ypr + (size_t)yb * 2 * ypr_plane);
-                        ttc::issue_gemm_3xtf32(tmem + c.col_g + gb * NA16, y_hi, y_hi + ypr_plane, g_hi, g_hi + c.gt_bytes / 2, NB, NA16, true);
+                        const uint32_t g_hi = ttc::smem_u32(gsm + c.off_gring) + (uint32_t)gs.idx * (uint32_t)c.gt_bytes;
+                        if (c.ypr_tmem) {
+                            ttc::gemm3_ts(tmem + c.col_g + gb.idx * NA16, tmem + c.col_y + yb.idx * 2 * NB, g_hi, g_hi + c.gt_bytes / 2, NB, NA16);
+                        } else {
+                            const uint32_t y_hi = ttc::smem_u32(gsm + c.off_ypr) + (uint32_t)yb.idx * 2u * ypr_plane;
+                            ttc::gemm3_ss(tmem + c.col_g + gb.idx * NA16, y_hi, y_hi + ypr_plane, g_hi, g_hi + c.gt_bytes / 2, NB, NA16);
+                        }
                     }
-                    ttc::umma_commit_to(&gfull[gb]);
-                    ttc::umma_commit_to(&aempty[yb]);
-                    if (!c.resident) ttc::umma_commit_to(&emptyG[gs]);
+                    ttc::umma_commit_elect(&gfull[gb.idx]);
+                    ttc::umma_commit_elect(&aempty[yb.idx]);
+                    if (!c.resident) ttc::umma_commit_elect(&emptyG[gs.idx]);
+                    GT(7)   // issue GEMM-G
                 }
             }
+            GT_OUT(0)
         }
     } else if (group == 1) {
         // ===== T readers =====
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsT));
         float* my = tab + row;   // this sample's column of the table: element r at my[r * 128]
-        long long kb = 0;
+        Ring tb(c.tbufs);
+        GT_DECL
         for (int it = 0; it < a.T; ++it) {
             // features: roll in registers, yaw into the table; UU operand into tensor memory
             // (p of this iteration is final: barrier 3 below closes the previous iteration's step)
@@ -289,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
                             v = my[(c.t_p + 3 + i) * kSamples] * my[(c.t_p + 3 + j) * kSamples];
                             if (++j == c.ri) { ++i; j = i; }
                         }
-                        ttc::split_tf32_fast(v, hi[x], lo[x]);
+                        ttc::split_tf32_bits(v, hi[x], lo[x]);
                     }
                     tmem_st8(lane_addr + c.col_a + k0, hi);
                     tmem_st8(lane_addr + c.col_a + KA + k0, lo);
@@ -299,7 +340,9 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
                 __syncwarp();
                 if (lane == 0) mbar_arrive(uu_ready);
             }
+            GT(0)   // features + UU
             named_sync(1, 384);   // features published (yaw here, pitch by the G formers)
+            GT(1)
 
             // D_T read-back: fold every (b,c) pair's NDP columns into the three angle gradients
             PairWalk pw;
@@ -308,11 +351,11 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
             float dYY = 2.0f * my[c.t_cy * kSamples] * my[c.t_dcy * kSamples];
             float gy = 0.f, gp = 0.f, gr = 0.f, gy_cur = 0.f;
             int pair = 0;
-            for (int j = 0; j < nblocks; ++j, ++kb) {
-                const int tb = (int)(kb % c.tbufs);
-                ttc::mbar_wait(&tfull[tb], (uint32_t)((kb / c.tbufs) & 1));
+            for (int j = 0; j < nblocks; ++j, tb.next()) {
+                ttc::mbar_wait(&tfull[tb.idx], tb.phase);
+                GT(2)   // wait D_T
                 tc_after();
-                const uint32_t tbase = lane_addr + c.col_t + tb * NB;
+                const uint32_t tbase = lane_addr + c.col_t + tb.idx * NB;
                 // one pair = NDP columns; the next pair's tcgen05.ld is in flight while this one is folded
                 auto fold = [&](const uint32_t (&t)[NDP]) {
                     const float cpi = my[(c.t_cp + pw.ci) * kSamples], cpj = my[(c.t_cp + pw.cj) * kSamples];
@@ -361,12 +404,14 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
                 pair += np;
                 tc_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[tb]);
+                if (lane == 0) mbar_arrive(&tempty[tb.idx]);
+                GT(3)   // fold
             }
             my[(c.t_gx + 0) * kSamples] = gy;
             my[(c.t_gx + 1) * kSamples] = gp;
             my[(c.t_gx + 2) * kSamples] = gr;
             named_sync(2, 384);   // gradient parts published (d/du by the G formers, linear term by group 3)
+            GT(4)
 
             // g = quadratic part - linear part; joint L2 clip (TD_Tester.py:150); p -= lr * g (:153-154)
             float ss = 0.f;
@@ -379,8 +424,10 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
             coef = coef < 1.0f ? coef : 1.0f;
             for (int i = 0; i < c.NP; ++i)
                 my[(c.t_p + i) * kSamples] = __fsub_rn(my[(c.t_p + i) * kSamples], __fmul_rn(a.lr, __fmul_rn(my[(c.t_gx + i) * kSamples], coef)));
+            GT(5)   // clip + step
             named_sync(3, 384);   // p stepped: the other groups may read it
         }
+        GT_OUT(1)
         if (s0 + row < a.N) {
             float* out = a.P + (s0 + row) * a.ldp;
             for (int i = 0; i < c.NP; ++i) out[i] = my[(c.t_p + i) * kSamples];
@@ -390,7 +437,8 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsG));
         float* my = tab + row;
         const uint32_t ypr_plane = (uint32_t)NB * kSamples * 4;
-        long long kb = 0;
+        Ring yb(c.ybufs), gb(c.gbufs);
+        GT_DECL
         for (int it = 0; it < a.T; ++it) {
             float cr[RRMAX], dcr[RRMAX], RRv[NDP], dRR[NDP];
             roll_features<RRMAX, NDP>(my[(c.t_p + 2) * kSamples], a.rows_r, c.rr, cr, dcr, RRv, dRR);
@@ -414,12 +462,22 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
             float YY = my[c.t_cy * kSamples] * my[c.t_cy * kSamples];
             int pair = 0;
             // write block jf of the YPR operand (rows = samples, K = the block's columns, UMMA no-swizzle layout)
-            auto form = [&](int jf, long long kf) {
-                const int yb = (int)(kf % c.ybufs);
-                ttc::mbar_wait(&aempty[yb], (uint32_t)((kf / c.ybufs) & 1) ^ 1u);
-                uint8_t* yhi = gsm + c.off_ypr + (size_t)yb * 2 * ypr_plane;
+            auto form = [&]() {
+                GT(0)
+                ttc::mbar_wait(&aempty[yb.idx], yb.phase ^ 1u);
+                GT(1)   // wait operand buffer
+                uint8_t* yhi = gsm + c.off_ypr + (size_t)yb.idx * 2 * ypr_plane;
                 uint8_t* ylo = yhi + ypr_plane;
                 const int rbase = (row / 8) * ((NB / 4) * 128) + (row % 8) * 16;   // ttc::op_offset(row, k, NB) = rbase + (k/4)*128 + (k%4)*4
+                const uint32_t ybase = lane_addr + c.col_y + yb.idx * 2 * NB;       // tensor-memory form: hi columns, then NB lo columns
+                if (c.ypr_tmem) {
+                    // the pad columns [BCP * NDP, NB) of this buffer: zero (they multiply zero tile entries, but must be finite)
+                    const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    for (int k0 = c.BCP * NDP; k0 < NB; k0 += 8) {
+                        tmem_st8(ybase + k0, z);
+                        tmem_st8(ybase + NB + k0, z);
+                    }
+                }
                 for (int pl = 0; pl < c.BCP; ++pl) {
                     float yp = 0.f;
                     if (pair < c.nBC) {
@@ -428,29 +486,48 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
                         if (pw.next(c.ry, c.rp) && pw.bi < c.ry)
                             YY = my[(c.t_cy + pw.bi) * kSamples] * my[(c.t_cy + pw.bj) * kSamples];
                     }
+                    if (c.ypr_tmem) {
 #pragma unroll
-                    for (int d4 = 0; d4 < NDP / 4; ++d4) {
-                        float h[4], l[4];
+                        for (int d8 = 0; d8 < NDP / 8; ++d8) {
+                            float h[8], l[8];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) ttc::split_tf32_fast(yp * RRv[4 * d4 + e], h[e], l[e]);
-                        const int off = rbase + ((pl * NDP) / 4 + d4) * 128;
-                        *reinterpret_cast<float4*>(yhi + off) = make_float4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<float4*>(ylo + off) = make_float4(l[0], l[1], l[2], l[3]);
+                            for (int e = 0; e < 8; ++e) ttc::split_tf32_bits(yp * RRv[8 * d8 + e], h[e], l[e]);
+                            tmem_st8(ybase + pl * NDP + 8 * d8, h);
+                            tmem_st8(ybase + NB + pl * NDP + 8 * d8, l);
+                        }
+                    } else {
+#pragma unroll
+                        for (int d4 = 0; d4 < NDP / 4; ++d4) {
+                            float h[4], l[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) ttc::split_tf32_bits(yp * RRv[4 * d4 + e], h[e], l[e]);
+                            const int off = rbase + ((pl * NDP) / 4 + d4) * 128;
+                            *reinterpret_cast<float4*>(yhi + off) = make_float4(h[0], h[1], h[2], h[3]);
+                            *reinterpret_cast<float4*>(ylo + off) = make_float4(l[0], l[1], l[2], l[3]);
+                        }
                     }
                 }
-                (void)jf;
-                ttc::fence_async_smem();
+                GT(2)   // form
+                if (c.ypr_tmem) {
+                    tmem_store_wait();
+                    tc_before();
+                } else {
+                    ttc::fence_async_smem();
+                }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&afull[yb]);
+                if (lane == 0) mbar_arrive(&afull[yb.idx]);
+                yb.next();
+                GT(3)   // fence + arrive
             };
-            form(0, kb);
-            for (int j = 0; j < nblocks; ++j, ++kb) {
-                if (j + 1 < nblocks) form(j + 1, kb + 1);
+            form();
+            for (int j = 0; j < nblocks; ++j, gb.next()) {
+                if (j + 1 < nblocks) form();
                 // promote this block's partial D_G into the FP32 accumulators (round-to-nearest adds)
-                const int gb = (int)(kb % c.gbufs);
-                ttc::mbar_wait(&gfull[gb], (uint32_t)((kb / c.gbufs) & 1));
+                GT(0)
+                ttc::mbar_wait(&gfull[gb.idx], gb.phase);
+                GT(4)   // wait D_G
                 tc_after();
-                const uint32_t gbase = lane_addr + c.col_g + gb * NA16;
+                const uint32_t gbase = lane_addr + c.col_g + gb.idx * NA16;
 #pragma unroll
                 for (int x0 = 0; x0 < NA16MAX / 8; x0 += 4) {
                     if (8 * x0 < NA16) {
@@ -469,7 +546,8 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
                 }
                 tc_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&gempty[gb]);
+                if (lane == 0) mbar_arrive(&gempty[gb.idx]);
+                GT(5)   // promote
             }
             // d/du_m of sum_A GU_A UU_A: for the pair A = (i,j): i == j -> 2 GU u_i, else GU u_j to i and GU u_i to j
             for (int i = 0; i < c.ri; ++i) my[(c.t_gx + 3 + i) * kSamples] = 0.f;
@@ -489,14 +567,18 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
                     }
                 }
             }
+            GT(6)   // d/du
             named_sync(2, 384);
             named_sync(3, 384);
+            GT(7)
         }
+        GT_OUT(2)
     } else {
         // ===== linear term: F1 = -sum q[ijkl] u_i cy_j cp_k cr_l and its derivatives =====
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsL));
         float* my = tab + row;
         const float* __restrict__ q = a.q + (size_t)blockIdx.x * c.R * kSamples + row;
+        GT_DECL
         for (int it = 0; it < a.T; ++it) {
             float cr[RRMAX], dcr[RRMAX];
 #pragma unroll
@@ -512,6 +594,7 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
                 }
             }
             named_sync(1, 384);
+            GT(0)
             float ly = 0.f, lp = 0.f, lr_ = 0.f;
             const float* qi = q;
             for (int i = 0; i < c.ri; ++i) {
@@ -549,9 +632,11 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
             my[(c.t_gl + 0) * kSamples] = ly;
             my[(c.t_gl + 1) * kSamples] = lp;
             my[(c.t_gl + 2) * kSamples] = lr_;
+            GT(1)   // linear term
             named_sync(2, 384);
             named_sync(3, 384);
         }
+        GT_OUT(3)
     }
     tc_before();
     __syncthreads();

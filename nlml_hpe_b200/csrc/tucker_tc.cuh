@@ -152,6 +152,70 @@ __device__ __forceinline__ void issue_gemm_3xtf32_ta(uint32_t tmem_d, uint32_t a
     }
 }
 
+// Round-to-nearest (ties away) TF32 split without cvt.rna (which sm_100a emulates with four instructions incl. an
+// infinity test): add half an ulp of TF32 to the bit pattern, clear the 13 dropped bits; lo = v - hi is exact.
+__device__ __forceinline__ void split_tf32_bits(float v, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+    lo = v - hi;
+}
+
+// ---- issue loops for the run-time-rank kernel (tucker_gen.cuh): the descriptors are built once per GEMM and advanced by
+// one add per k-step (the K-slice [k0, k0+8) starts 256 B further: +16 in the descriptor's address field), the three MMAs
+// of a k-step share one asm block.  Meant to be executed by a whole warp with warp-uniform arguments (descriptor
+// arithmetic stays in the uniform datapath); only the elected lane issues.
+__device__ __forceinline__ void mma3_ss(uint32_t d, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.b32 q, %5, %5;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %3, %5, p;\n\t"   // lo * hi (small terms first)
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %4, %5, q;\n\t"   // hi * lo
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %3, %5, q;\n\t}"  // hi * hi
+        ::"r"(d), "l"(ah), "l"(al), "l"(bh), "l"(bl), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void mma3_ts(uint32_t d, uint32_t ah, uint32_t al, uint64_t bh, uint64_t bl, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.b32 q, %5, %5;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %3, %5, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %4, %5, q;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %3, %5, q;\n\t}"
+        ::"r"(d), "r"(ah), "r"(al), "l"(bh), "l"(bl), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// commit by the elected lane of a converged warp
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar)) : "memory");
+}
+// D = A * B^T (fresh accumulator), A and B tiles in shared memory (no-swizzle K-major), K multiple of 8.
+// Executed by a CONVERGED warp with warp-uniform arguments.
+__device__ __forceinline__ void gemm3_ss(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int K, int N) {
+    const uint32_t idesc = make_idesc_tf32(128, N);
+    uint64_t ah = make_desc_noswz(a_hi, K, 0), al = make_desc_noswz(a_lo, K, 0);
+    uint64_t bh = make_desc_noswz(b_hi, K, 0), bl = make_desc_noswz(b_lo, K, 0);
+    for (int k = 0; k < K; k += 8) {
+        mma3_ss(d, ah, al, bh, bl, idesc, k > 0 ? 1u : 0u);
+        ah += 16; al += 16; bh += 16; bl += 16;
+    }
+}
+// the same with the A operand in tensor memory (hi in columns [a, a+K), lo in [a+K, a+2K))
+__device__ __forceinline__ void gemm3_ts(uint32_t d, uint32_t a_tmem, uint32_t b_hi, uint32_t b_lo, int K, int N) {
+    const uint32_t idesc = make_idesc_tf32(128, N);
+    uint64_t bh = make_desc_noswz(b_hi, K, 0), bl = make_desc_noswz(b_lo, K, 0);
+    for (int k = 0; k < K; k += 8) {
+        mma3_ts(d, a_tmem + k, a_tmem + K + k, bh, bl, idesc, k > 0 ? 1u : 0u);
+        bh += 16; bl += 16;
+    }
+}
+
 // ---- stand-alone check kernel: one CTA, D[128][N] = A[128][K] * B[N][K]^T --------------------------------
 struct TcCheckArgs {
     const float* A;   // [128][K]
