@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes
 import warnings
+from typing import List, Tuple
 
 import numpy as np
 import torch
@@ -47,10 +48,12 @@ class _Plan:
     """Device-resident packed weights for one (encoder, 3 heads) set."""
 
     def __init__(self, linears, device_index):
+        """linears: 21 nn.Linear modules, or 21 (weight, bias) tensor pairs, in the C ABI's order."""
         lib = _lib.load()
         assert len(linears) == 21
-        ws = [np.ascontiguousarray(l.weight.detach().cpu().numpy(), dtype=np.float32) for l in linears]
-        bs = [np.ascontiguousarray(l.bias.detach().cpu().numpy(), dtype=np.float32) for l in linears]
+        pairs = [(l.weight, l.bias) if isinstance(l, nn.Linear) else l for l in linears]
+        ws = [np.ascontiguousarray(w.detach().cpu().numpy(), dtype=np.float32) for w, _ in pairs]
+        bs = [np.ascontiguousarray(b.detach().cpu().numpy(), dtype=np.float32) for _, b in pairs]
         wp = (ctypes.c_void_p * 21)(*[w.ctypes.data for w in ws])
         bp = (ctypes.c_void_p * 21)(*[b.ctypes.data for b in bs])
         outs = (ctypes.c_int * 21)(*[w.shape[0] for w in ws])
@@ -240,6 +243,91 @@ class CombinedAnglePredictionModel(nn.Module):
 
 
 # ---------------------------------------------------------------------------------------------
+# TorchScript form.  The reference SAVES torch.jit.script(combined_model) (:222-223) and its callers LOAD it with
+# torch.jit.load("models/combined_model_scripted.pth", map_location=device).to(device).eval() (NLML_HPE_Test.py:217-219;
+# generatePose_on_video.py:289).  To stay a drop-in at that boundary the archive written here is a real TorchScript
+# module with the reference's parameter names whose forward is ONE custom operator, nlml_hpe_b200::combined_forward,
+# implemented by the CUDA chain behind the C ABI.  The operator is registered when this package is imported, so a
+# caller adds `import nlml_hpe_b200` and keeps its torch.jit.load line unchanged.
+# ---------------------------------------------------------------------------------------------
+_OPS = torch.library.Library("nlml_hpe_b200", "DEF")
+_OPS.define("combined_forward(Tensor x, Tensor[] weights, Tensor[] biases) -> Tensor")
+_OP_PLANS = {}   # (weights identity, device) -> _Plan
+
+
+def _combined_forward_op(x, weights, biases):
+    """x float32 [B,input_size] (CUDA: asynchronous device path; CPU: pipelined host path onto the current CUDA device)
+    -> [B,3] (yaw, pitch, roll) radians on x's device.  21 weights / biases in the C ABI's order."""
+    if len(weights) != 21 or len(biases) != 21:
+        raise ValueError("combined_forward takes the 21 Linear layers of the encoder and the three heads")
+    dev = x.device.index if x.is_cuda else _device_index(None)
+    key = (tuple((w.data_ptr(), w._version) for w in weights) + tuple((b.data_ptr(), b._version) for b in biases), dev)
+    plan = _OP_PLANS.get(key)
+    if plan is None:
+        if len(_OP_PLANS) >= 4:
+            _OP_PLANS.pop(next(iter(_OP_PLANS))).close()
+        plan = _OP_PLANS[key] = _Plan(list(zip(weights, biases)), dev)
+    x = _check_x(x.detach(), plan.input_size)
+    if x.is_cuda:
+        out = torch.empty((x.shape[0], 3), dtype=torch.float32, device=x.device)
+        ldx = x.stride(0) if x.shape[0] > 1 else x.shape[1]
+        _lib.check(plan.lib.nlml_mlp_forward_f32(plan.h, x.data_ptr(), x.shape[0], ldx, out.data_ptr(),
+                                                 torch.cuda.current_stream(x.device).cuda_stream))
+        return out
+    xh = np.ascontiguousarray(x.numpy())
+    out = np.empty((xh.shape[0], 3), dtype=np.float32)
+    _lib.check(plan.lib.nlml_mlp_forward_host_f32(plan.h, xh.ctypes.data, xh.shape[0], xh.shape[1], out.ctypes.data))
+    return torch.from_numpy(out)
+
+
+_OPS.impl("combined_forward", _combined_forward_op, "CompositeExplicitAutograd")
+
+
+class _ParamStack(nn.Module):
+    """Holds a Sequential under the attribute name the reference uses ('encoder' / 'model') so the scripted
+    module's state_dict keys are the reference's; never evaluated with torch math."""
+
+    def __init__(self, attr, seq):
+        super().__init__()
+        setattr(self, attr, seq)
+
+
+class ScriptedCombinedAnglePredictionModel(nn.Module):
+    """TorchScript-able twin of CombinedAnglePredictionModel: forward(x) -> (yaw[B,1], pitch[B,1], roll[B,1]) radians
+    (:115-126) through torch.ops.nlml_hpe_b200.combined_forward."""
+
+    def __init__(self, combined):
+        super().__init__()
+        self.encoder = _ParamStack("encoder", combined.encoder.encoder)
+        self.yaw_network = _ParamStack("model", combined.yaw_network.model)
+        self.pitch_network = _ParamStack("model", combined.pitch_network.model)
+        self.roll_network = _ParamStack("model", combined.roll_network.model)
+
+    def forward(self, input_landmarks: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        e = self.encoder.encoder
+        y = self.yaw_network.model
+        p = self.pitch_network.model
+        r = self.roll_network.model
+        ws: List[torch.Tensor] = [e[0].weight, e[2].weight, e[4].weight, e[6].weight, e[8].weight, e[10].weight,
+                                  y[0].weight, y[2].weight, y[4].weight, y[6].weight, y[8].weight,
+                                  p[0].weight, p[2].weight, p[4].weight, p[6].weight, p[8].weight,
+                                  r[0].weight, r[2].weight, r[4].weight, r[6].weight, r[8].weight]
+        bs: List[torch.Tensor] = [e[0].bias, e[2].bias, e[4].bias, e[6].bias, e[8].bias, e[10].bias,
+                                  y[0].bias, y[2].bias, y[4].bias, y[6].bias, y[8].bias,
+                                  p[0].bias, p[2].bias, p[4].bias, p[6].bias, p[8].bias,
+                                  r[0].bias, r[2].bias, r[4].bias, r[6].bias, r[8].bias]
+        out = torch.ops.nlml_hpe_b200.combined_forward(input_landmarks, ws, bs)
+        return out[:, 0:1], out[:, 1:2], out[:, 2:3]
+
+
+def script_combined_model(combined):
+    """torch.jit.script form of a CombinedAnglePredictionModel (what model_builder saves, :222-223)."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return torch.jit.script(ScriptedCombinedAnglePredictionModel(combined).eval())
+
+
+# ---------------------------------------------------------------------------------------------
 # weight loading (the contract of model_builder(), :168-224)
 # ---------------------------------------------------------------------------------------------
 def build_combined_model(encoder_sd, yaw_sd, pitch_sd, roll_sd, input_size=None, matrix_dims=None):
@@ -278,9 +366,10 @@ def load_combined_model(path="models/combined_model_scripted.pth", map_location=
 
 
 def model_builder(out_path="models/combined_model_scripted.pth"):
-    """Same inputs as the reference's model_builder (:168-224): configs/config_EncoderTrainer.yaml,
-    outputs/features/*.npz, models/{Encoder,yaw_network,pitch_network,roll_network}.pth.  Writes a plain
-    state_dict checkpoint (a ctypes-backed module cannot be TorchScript-ed) that load_combined_model reads."""
+    """Same inputs and output as the reference's model_builder (:168-224): configs/config_EncoderTrainer.yaml,
+    outputs/features/*.npz, models/{Encoder,yaw_network,pitch_network,roll_network}.pth -> a TorchScript archive at
+    models/combined_model_scripted.pth (:222-223) that torch.jit.load opens (NLML_HPE_Test.py:217) once this package has
+    been imported; its forward is the CUDA chain (nlml_hpe_b200::combined_forward).  Returns the eager model."""
     warnings.filterwarnings("ignore")
     config = load_config("configs/config_EncoderTrainer.yaml")
     input_size = config["input_size"]
@@ -292,7 +381,7 @@ def model_builder(out_path="models/combined_model_scripted.pth"):
     for sd, w in zip(sds[1:], head_in):
         assert sd["model.0.weight"].shape[1] == w
     model = build_combined_model(*sds, input_size=input_size, matrix_dims=matrix_dims)
-    torch.save(model.state_dict(), out_path)
+    script_combined_model(model).save(out_path)
     print("model is built")
     return model
 

@@ -7,3 +7,7 @@ Host code is Python; compute is hand-written CUDA reached through the C ABI in
 include/nlml_hpe_b200.h (libnlml_hpe_b200.so, built in-tree).  No CPU fallback.
 """
 __version__ = "0.1.0"
+
+# importing the package registers the TorchScript operator nlml_hpe_b200::combined_forward, which the archive written by
+# NLML_HPE_Model_Builder.model_builder() calls (so `import nlml_hpe_b200` + the reference's torch.jit.load line suffice)
+from . import NLML_HPE_Model_Builder as _model_builder  # noqa: E402,F401

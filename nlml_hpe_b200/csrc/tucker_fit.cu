@@ -35,6 +35,7 @@ struct TuckerArgs {
     const float* W2;  // [R][F]
     const float* S;   // [nBCD][NAP]   thread-per-sample layout
     const float* St;  // [nA][nBCDp]   CTA-per-sample layout
+    const uint8_t* tc_ops;   // tensor-core kernel: shared-memory image of the two B operands (S in both GEMM views, hi/lo)
     float* P;
     long long ldp;
     int F, T;
@@ -791,6 +792,35 @@ struct TcFitCfg {
     static constexpr int COL_T = 0, COL_V = 224, COL_Q = 320, COL_A1 = 456;   // A1: the T GEMM's A operand (UU hi | lo, 2 x 16 columns)
 };
 
+// shared-memory image of the tensor-core kernel's constant B operands, built once per plan:
+//   B1[n = bcd][k = A]            = S[A,b,c,d]      (T GEMM, 224 x 16)
+//   BV[n = A*6 + b][k = c*6 + d]  = S[A,b,c,d]      (V GEMM,  96 x 40)
+// each as a hi plane followed by a lo plane (3xTF32 split), UMMA no-swizzle K-major layout
+__global__ void build_tc_operands_kernel(const float* __restrict__ S, uint8_t* __restrict__ img) {
+    using C = TcFitCfg;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int idx = tid; idx < C::N1 * C::K1; idx += nth) {
+        const int n = idx / C::K1, k = idx % C::K1;
+        const float v = (n < C::nBCD && k < C::nA) ? S[n * 16 + k] : 0.f;
+        float hi, lo;
+        ttc::split_tf32(v, hi, lo);
+        *reinterpret_cast<float*>(img + C::OFF_B1 + ttc::op_offset(n, k, C::K1)) = hi;
+        *reinterpret_cast<float*>(img + C::OFF_B1 + C::B1_BYTES + ttc::op_offset(n, k, C::K1)) = lo;
+    }
+    for (int idx = tid; idx < C::NV * C::KV; idx += nth) {
+        const int n = idx / C::KV, k = idx % C::KV;
+        float v = 0.f;
+        if (n < C::nA * C::nB && k < C::nC * C::nD) {
+            const int aa = n / C::nB, b = n % C::nB;
+            v = S[(b * 36 + k) * 16 + aa];
+        }
+        float hi, lo;
+        ttc::split_tf32(v, hi, lo);
+        *reinterpret_cast<float*>(img + C::OFF_BV + ttc::op_offset(n, k, C::KV)) = hi;
+        *reinterpret_cast<float*>(img + C::OFF_BV + C::BV_BYTES + ttc::op_offset(n, k, C::KV)) = lo;
+    }
+}
+
 // Half of T (3 of the 6 b's = 108 columns) -> partial GR[6], GP[6] and the 3 GY of those b's
 template <int B0>
 __device__ __forceinline__ void tc_reduce_t(uint32_t taddr, const float (&YY)[6], const float (&PP)[6], const float (&RRv)[8],
@@ -858,8 +888,11 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
     float* gx = reinterpret_cast<float*>(tsm + C::OFF_GX);
 
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int row = tid & 127, role = tid >> 7;
+    // the warp index through a shuffle: provably warp-uniform, so the two MMA-issuing warps keep their descriptor arithmetic
+    // in the uniform datapath (a plain `tid == 0` issue wraps every tcgen05.mma in a register->uniform broadcast loop,
+    // ~100 cycles per MMA on the iteration's critical path)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int row = tid & 127, role = warp >> 2;
     const long long s0 = (long long)blockIdx.x * C::THREADS;
     const bool vec_ok = a.vec_ok != 0;
     const int F = a.F;
@@ -867,37 +900,18 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
     if (tid == 0) {
         ttc::mbar_init(bar, 1);       // T GEMM done
         ttc::mbar_init(bar + 1, 1);   // V GEMM done
+        ttc::mbar_init(bar + 3, 1);   // B operands landed (TMA)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc_cols(tmem_slot, C::TMEM_COLS);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // (phase A's barriers publish the allocation)
 
-    // ---- constant B operands: the folded Gram tensor in both GEMM views, split hi/lo ----
-    //   B1[n = bcd][k = A]          = S[A,b,c,d]
-    //   BV[n = A*6 + b][k = c*6 + d] = S[A,b,c,d]
-    for (int idx = tid; idx < C::N1 * C::K1; idx += 256) {
-        const int n = idx / C::K1, k = idx % C::K1;
-        const float v = (n < C::nBCD && k < C::nA) ? __ldg(a.S + n * 16 + k) : 0.f;
-        float hi, lo;
-        ttc::split_tf32(v, hi, lo);
-        *reinterpret_cast<float*>(b1_hi + ttc::op_offset(n, k, C::K1)) = hi;
-        *reinterpret_cast<float*>(b1_lo + ttc::op_offset(n, k, C::K1)) = lo;
+    // ---- constant B operands: the folded Gram tensor in both GEMM views (hi/lo TF32 planes in the UMMA layout), staged
+    // once per CTA by ONE 1-D TMA bulk copy of the image build_tc_operands_kernel prepared at plan creation ----
+    if (tid == 0) {
+        tgen::mbar_expect_tx(bar + 3, (uint32_t)C::OFF_AV);
+        tgen::bulk_load(tsm + C::OFF_B1, a.tc_ops, (uint32_t)C::OFF_AV, bar + 3);
     }
-    for (int idx = tid; idx < C::NV * C::KV; idx += 256) {
-        const int n = idx / C::KV, k = idx % C::KV;
-        float v = 0.f;
-        if (n < C::nA * C::nB && k < C::nC * C::nD) {
-            const int aa = n / C::nB, b = n % C::nB;
-            v = __ldg(a.S + (b * 36 + k) * 16 + aa);
-        }
-        float hi, lo;
-        ttc::split_tf32(v, hi, lo);
-        *reinterpret_cast<float*>(bv_hi + ttc::op_offset(n, k, C::KV)) = hi;
-        *reinterpret_cast<float*>(bv_lo + ttc::op_offset(n, k, C::KV)) = lo;
-    }
-
-    ttc::fence_async_smem();   // every thread's share of the B operand writes -> visible to the tensor core's async proxy
-                               // (phase A's barriers order it before the first MMA)
     // ---- phase A: q[r] = sum_f W2[r][f] * x[f]; the two threads of a sample take half of the rows r each ----
     {
         constexpr int RH = C::RPAD / 2;   // 68 rows per role
@@ -950,6 +964,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         tmem_store4(qdst + 64, acc + 64);
         tmem_store_wait();
     }
+    ttc::mbar_wait(bar + 3, 0);   // the B operands are in shared memory (async proxy writes: visible to the MMAs)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -989,15 +1004,15 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             sym_products<5>(u, UU);
             UU[15] = 0.f;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) ttc::split_tf32_fast(UU[k], hl[k], hl[16 + k]);
+            for (int k = 0; k < 16; ++k) ttc::split_tf32_bits(UU[k], hl[k], hl[16 + k]);
             tmem_store32(lane_addr + C::COL_A1, hl);
             tmem_store_wait();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (tid == 0 && NLML_DBG_MMA) {
+            if (warp == 0 && NLML_DBG_MMA) {   // the whole warp, converged; the elected lane issues
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                ttc::issue_gemm_3xtf32_ta(tmem + C::COL_T, tmem + C::COL_A1, ttc::smem_u32(b1_hi), ttc::smem_u32(b1_lo), C::K1, C::N1, true);
-                ttc::umma_commit_to(bar);
+                ttc::gemm3_ts(tmem + C::COL_T, tmem + C::COL_A1, ttc::smem_u32(b1_hi), ttc::smem_u32(b1_lo), C::K1, C::N1);
+                ttc::umma_commit_elect(bar);
             }
         }
         NLML_TSTAMP(0);   // role 0: UU publish + T GEMM issue
@@ -1017,7 +1032,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
                 for (int e = 0; e < 4; ++e) {
                     const int kk = 4 * k4 + e;
                     const float v = kk < 36 ? PP[kk / 6] * RRv[kk % 6] : 0.f;
-                    ttc::split_tf32_fast(v, h[e], l[e]);
+                    ttc::split_tf32_bits(v, h[e], l[e]);
                 }
                 *reinterpret_cast<float4*>(av_hi + ttc::op_offset(row, 4 * k4, C::KV)) = make_float4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<float4*>(av_lo + ttc::op_offset(row, 4 * k4, C::KV)) = make_float4(l[0], l[1], l[2], l[3]);
@@ -1025,11 +1040,11 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             ttc::fence_async_smem();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync 2, 128;" ::: "memory");
-            if (tid == 160 && NLML_DBG_MMA) {   // warp 5: not on the sub-partition of the T GEMM's issuer (warp 0)
+            if (warp == 5 && NLML_DBG_MMA) {   // warp 5: not on the sub-partition of the T GEMM's issuer (warp 0)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                ttc::issue_gemm_3xtf32(tmem + C::COL_V, ttc::smem_u32(av_hi), ttc::smem_u32(av_lo), ttc::smem_u32(bv_hi),
-                                       ttc::smem_u32(bv_lo), C::KV, C::NV, true);
-                ttc::umma_commit_to(bar + 1);
+                ttc::gemm3_ss(tmem + C::COL_V, ttc::smem_u32(av_hi), ttc::smem_u32(av_lo), ttc::smem_u32(bv_hi),
+                              ttc::smem_u32(bv_lo), C::KV, C::NV);
+                ttc::umma_commit_elect(bar + 1);
             }
         }
         NLML_TSTAMP(1);   // pitch/roll features (+ role 1: PP(x)RR publish + V GEMM issue)
@@ -1237,6 +1252,7 @@ struct nlml_tucker_plan {
     bool cta_ok = false;      // CTA-per-sample kernel usable (its working set fits shared memory)
     bool gen_ok = false;      // run-time-rank tensor-core kernel usable (tucker_gen.cuh)
     tgen::GenCfg gen{};
+    uint8_t* tc_ops = nullptr;              // (5,3,3,3) tensor-core kernel: image of its two constant B operands
     uint8_t* gen_tiles = nullptr;           // tile images of S (hi/lo, UMMA layout), streamed by TMA
     float* q_ws[3] = {nullptr, nullptr, nullptr};   // q = W2 x slabs: [0],[1] host-pipeline slots, [2] device-buffer calls
     int64_t q_rows[3] = {0, 0, 0};
@@ -1635,6 +1651,12 @@ extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, i
         NLML_CUDA(cudaFuncSetAttribute(tucker_fit_tps_kernel<5, 3, 3, 3, kTpsBigThreads, 1, 1, true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpsBig::SMEM_BYTES));
         NLML_CUDA(cudaFuncSetAttribute(tucker_fit_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcFitCfg::SMEM_BYTES));
+        NLML_CUDA(cudaMalloc(&pl->tc_ops, TcFitCfg::OFF_AV));
+        build_tc_operands_kernel<<<32, 256>>>(pl->S, pl->tc_ops);
+        NLML_CUDA(cudaGetLastError());
+        NLML_CUDA(cudaDeviceSynchronize());
+        pl->launches += 1;
+        a.tc_ops = pl->tc_ops;
         if (wps_smem_bytes(F) > 200 * 1024) pl->fast = false;
         else
             NLML_CUDA(cudaFuncSetAttribute(tucker_fit_wps_kernel<5, 3, 3, 3, kWpsWarps>,
@@ -1683,6 +1705,7 @@ extern "C" void nlml_tucker_plan_destroy(nlml_tucker_plan* pl) {
     cudaFree(pl->S);
     cudaFree(pl->St);
     cudaFree(pl->gen_tiles);
+    cudaFree(pl->tc_ops);
     for (int i = 0; i < 3; ++i) cudaFree(pl->q_ws[i]);
     if (pl->q_done) cudaEventDestroy(pl->q_done);
     delete pl;

@@ -27,6 +27,12 @@ def tucker_golden():
 
 
 @pytest.fixture(scope="session")
+def powell_golden():
+    """96 outputs of the reference's Test() = scipy Powell (tests/golden/make_golden_powell.py)."""
+    return dict(np.load(os.path.join(GOLDEN, "powell_golden.npz")))
+
+
+@pytest.fixture(scope="session")
 def mlp_golden():
     return dict(np.load(os.path.join(GOLDEN, "mlp_golden.npz")))
 
@@ -76,3 +82,54 @@ def hostcheck():
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-mfma", "-ffp-contract=off", "-shared", "-fPIC", "-o", out, src])
     return ctypes.CDLL(out)
+
+
+ENCODER_YAML = """yaw_bins:
+  min_bin: -50
+  max_bin:  51
+  interval: 10
+
+pitch_bins:
+  min_bin: -40
+  max_bin:  41
+  interval: 10
+
+roll_bins:
+  min_bin: -30
+  max_bin:  31
+  interval: 10
+
+input_size: 1404   # number of inputs of the encoder
+batch_size: 256
+"""
+
+# the shipped file's defect is reproduced on purpose: `val_set_path = "..."` ('=' instead of ':', config_NLML_HPE_Test.yaml:29)
+TEST_YAML = """yaw_intervals:
+  - [-51, -33.33]
+  - [33.33, 51]
+
+val_set : "facescape" # facescape / biwi / AFLW2000
+# val_set_path: "C:\\\\somewhere\\\\BIWI.npz"
+val_set_path = "E:/Mahdi/Databases/some_valset_(+y+p+r)_rotation_convention(jpg)" 
+"""
+
+
+@pytest.fixture()
+def ref_layout(tmp_path, art, state_dicts, monkeypatch):
+    """A working directory laid out like a checkout of the reference: configs/*.yaml, outputs/features/*.npz,
+    models/*.pth (shipped heads + the synthetic stand-in for the missing Encoder.pth).  The entry points read
+    CWD-relative paths (TD_Inference.py:40,49; NLML_HPE_Model_Builder.py:174-216; NLML_HPE_Test.py:188,200,217)."""
+    import torch
+    (tmp_path / "configs").mkdir()
+    (tmp_path / "configs" / "config_EncoderTrainer.yaml").write_text(ENCODER_YAML)
+    (tmp_path / "configs" / "config_NLML_HPE_Test.yaml").write_text(TEST_YAML)
+    feat = tmp_path / "outputs" / "features"
+    feat.mkdir(parents=True)
+    np.savez(feat / "Trained_data.npz", W=art["W"], CoreTensor=np.zeros((1,), np.float32),
+             optimized_yaw=art["optimized_yaw"], optimized_pitch=art["optimized_pitch"], optimized_roll=art["optimized_roll"])
+    np.savez(feat / "Factor_Matrices.npz", U_id=art["U_id"], U_yaw=art["U_yaw"], U_pitch=art["U_pitch"], U_roll=art["U_roll"])
+    (tmp_path / "models").mkdir()
+    for name, sd in zip(("Encoder", "yaw_network", "pitch_network", "roll_network"), state_dicts):
+        torch.save({k: torch.as_tensor(np.asarray(v)) for k, v in sd.items()}, tmp_path / "models" / f"{name}.pth")
+    monkeypatch.chdir(tmp_path)
+    return tmp_path

@@ -159,6 +159,7 @@ def test_reference_entry_points(art, rows, X1k, tucker_golden, cuda_lib):
     # default: converged fit, as the reference's Test (scipy Powell, TD_Tester.py:191-199); same basin as Powell
     y, pi, r, u = TD_Tester.Test(art["W"], torch.from_numpy(X1k[0]), 5, *rows, None, None, None, None)
     pw = tucker_golden["powell_shipped_deg"][0]
+    # converged fit vs scipy Powell: same basin, lower loss, angles up to several degrees apart (test_solve_vs_reference_powell_96)
     assert u is None and isinstance(y, float) and max(abs(y - pw[0]), abs(pi - pw[1]), abs(r - pw[2])) < 5.0
 
 
@@ -301,19 +302,27 @@ def test_solve_matches_f64_oracle(fitter, art, rows, X1k):
     assert np.abs(newton[:, :3]).max() * DEG < 5e-2 and np.quantile(np.abs(newton[:, :3]).max(1), 0.95) * DEG < TOL_DEG
 
 
-def test_solve_reaches_powell_basin_at_lower_loss(fitter, art, rows, X1k, tucker_golden):
-    """Against the reference's own Test() (scipy Powell) on 8 samples: same basin, loss not higher."""
-    pw = tucker_golden["powell_shipped_deg"]
-    P = fitter.solve(_gpu(X1k[:8])).cpu().numpy()
-    assert np.abs(P[:, :3] * DEG - pw).max() < 5.0          # Powell stops at xtol = ftol = 1e-4, well before the optimum
-    # loss at our optimum vs loss at Powell's angles with the identity re-solved exactly (its u is not in the golden)
-    L_ours = _loss64(P, art, X1k[:8], rows)
-    Pp = P.copy().astype(np.float64)
-    Pp[:, :3] = pw / DEG
-    for _ in range(3):   # u is a linear least-squares problem for fixed angles: Newton in u converges in one step
-        _, G, H = tucker_oracle.newton_terms(Pp, art["W"], X1k[:8], *rows)
-        Pp[:, 3:] -= np.linalg.solve(H[:, 3:, 3:], G[:, 3:, None])[:, :, 0]
-    assert (L_ours <= _loss64(Pp, art, X1k[:8], rows) + 1e-7).all()
+def test_solve_vs_reference_powell_96(fitter, art, rows, X1k, powell_golden):
+    """What the drop-in's Test() returns against what the reference's Test() returns (scipy Powell, TD_Tester.py:191-199),
+    on 96 outputs of the REAL reference (tests/golden/powell_golden.npz).  The deviation is explicit, not hidden:
+    * the objective value (the reference's own `objective`, float64) at our result is never above Powell's;
+    * Powell stops at xtol = ftol = 1e-4 in a flat valley, so its angles sit up to several degrees short of the
+      minimum: measured gap median 0.28, 90th percentile 2.8, maximum 8.7 degrees (same basin: the loss differs by
+      < 1 %).  TD_Tester.TEST_SOLVER = "sgd" selects the fixed-iteration block with the bit-level parity contract."""
+    idx = powell_golden["idx"]
+    X = X1k[idx]
+    P, evals = fitter.solve(_gpu(X), return_evals=True)
+    P, evals = P.cpu().numpy(), evals.cpu().numpy()
+    assert (evals < 64).all()                                # every sample converged before the evaluation cap
+    L_ours = _loss64(P, art, X, rows)
+    L_powell = _loss64(powell_golden["p"], art, X, rows)
+    assert np.abs(L_powell - powell_golden["loss"]).max() < 1e-8   # the fixture's loss is the reference's own value
+    assert (L_ours <= L_powell + 1e-7).all()
+    assert ((L_powell - L_ours) / L_powell).max() < 0.02           # same basin: < 2 % apart in loss
+    gap = np.abs(P[:, :3].astype(np.float64) * DEG - powell_golden["deg"]).max(1)
+    q50, q90, qmax = np.quantile(gap, [0.5, 0.9, 1.0])
+    print(f"angle gap to scipy Powell over {len(idx)} samples: median {q50:.3f}, 90 % {q90:.3f}, max {qmax:.3f} degrees")
+    assert q50 < 0.6 and q90 < 4.0 and qmax < 12.0
 
 
 def test_solve_edges_and_host_path(fitter, art, rows, X1k, tucker_golden):
