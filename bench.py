@@ -37,7 +37,8 @@ TUCKER_FLOP_PER_POSE_REFERENCE = T_ITERS * 2 * 2 * 135 * F                      
 # one Newton evaluation: per S row (216) 15 FMA for T + 4x15 FMA for GU/HY/HP/HR + 20 for the scalar sums,
 # linear term 5*3*(6*9) FMA + assembly
 SOLVE_FLOP_PER_EVAL = 2 * (216 * (15 + 60 + 20) + 5 * 3 * 54 + 400)
-TUCKER_TC_FLOP_PER_POSE = T_ITERS * 2 * 3 * (224 * 16 + 96 * 40)
+TUCKER_TC_FLOP_PER_POSE = T_ITERS * 2 * 3 * (224 * 16 + 96 * 40)      # ISSUED: 3xTF32 passes and padding included
+TUCKER_TC_USEFUL_FLOP_PER_POSE = T_ITERS * 2 * (2 * 15 * 216)          # USEFUL: the two contractions with the folded Gram tensor
 TUCKER_BYTES_PER_POSE = F * 4 + 8 * 4
 # DRAM traffic of tucker_fit_tc_kernel per sample, from the committed `ncu --set full` capture (profiles/r01_tucker_tc_ncu.txt:
 # dram__bytes_read 218.43 MB + dram__bytes_write 5.36 MB for a 37 888-sample launch); scaled to the bench launch
@@ -172,14 +173,15 @@ def cpu_baseline_tucker(art, rows, cores, seconds_cap=40.0):
     worker process with 1 torch thread each, `cores` workers, T=3000."""
     from concurrent.futures import ProcessPoolExecutor
     from nlml_hpe_b200 import synthetic
+    cores = physical_cores(cores)
     X = synthetic.make_features(cores, art["W"], *rows, U_id=art["U_id"], seed=1234)
-    with ProcessPoolExecutor(max_workers=cores) as pool:
+    with ProcessPoolExecutor(max_workers=cores, initializer=_pin_worker, initargs=(cores,)) as pool:
         list(pool.map(_cpu_warm_worker, range(cores)))          # interpreter + torch import stay outside the timing
         t0 = time.perf_counter()
         list(pool.map(_cpu_tucker_worker, [(art["W"], X[i], rows) for i in range(cores)]))
         dt = time.perf_counter() - t0
-    return {"value": cores / dt, "unit": "poses/s", "cores": cores, "kind": "port",
-            "sample": f"{cores} samples (one per worker process, 1 thread each), T={T_ITERS}, "
+    return {"value": cores / dt, "unit": "poses/s", "cores": cores, "kind": "port", "s_per_sample_per_core": dt, "seconds": dt,
+            "sample": f"{cores} samples (one per worker process pinned to its own physical core, 1 thread each), T={T_ITERS}, "
                       f"oracle.tucker_oracle.sgd_reference_form = autograd restatement of TD_Tester.py:127-159; {dt:.1f} s"}
 
 
@@ -188,14 +190,28 @@ def cpu_baseline_powell(art, rows, cores):
     restatement of TD_Tester.py:162-199), one sample per worker process."""
     from concurrent.futures import ProcessPoolExecutor
     from nlml_hpe_b200 import synthetic
+    cores = physical_cores(cores)
     X = synthetic.make_features(cores, art["W"], *rows, U_id=art["U_id"], seed=1234)
-    with ProcessPoolExecutor(max_workers=cores) as pool:
+    with ProcessPoolExecutor(max_workers=cores, initializer=_pin_worker, initargs=(cores,)) as pool:
         list(pool.map(_cpu_warm_worker, range(cores)))
         t0 = time.perf_counter()
         list(pool.map(_cpu_powell_worker, [(art["W"], X[i], rows) for i in range(cores)]))
         dt = time.perf_counter() - t0
     return {"value": cores / dt, "unit": "poses/s", "cores": cores, "kind": "port",
             "sample": f"{cores} samples (one per worker process), scipy Powell as TD_Tester.Test (TD_Tester.py:191-199); {dt:.1f} s"}
+
+
+def physical_cores(logical):
+    """One worker per PHYSICAL core (hyper-thread siblings share an FP unit: oversubscribing them made the two CPU legs of
+    round 1 disagree by 2x).  Falls back to the logical count when /sys is not readable."""
+    try:
+        seen = set()
+        for cpu in sorted(os.sched_getaffinity(0)):
+            with open(f"/sys/devices/system/cpu/cpu{cpu}/topology/thread_siblings_list") as f:
+                seen.add(f.read().strip())
+        return max(1, min(logical, len(seen)))
+    except Exception:
+        return logical
 
 
 def _cpu_powell_worker(args):
@@ -293,11 +309,21 @@ def _pin_worker(n_workers):
     """ProcessPoolExecutor initializer: pin each worker to its own CPU (one worker per core, no migration), so the two
     CPU legs of a run agree (1.70 vs 3.72 poses/s for the same leg minutes apart, unpinned)."""
     try:
-        cpus = sorted(os.sched_getaffinity(0))
         import multiprocessing as mp
+        firsts = []
+        seen = set()
+        for cpu in sorted(os.sched_getaffinity(0)):
+            try:
+                with open(f"/sys/devices/system/cpu/cpu{cpu}/topology/thread_siblings_list") as f:
+                    sib = f.read().strip()
+            except Exception:
+                sib = str(cpu)
+            if sib not in seen:
+                seen.add(sib)
+                firsts.append(cpu)            # first hardware thread of every physical core
         ident = mp.current_process()._identity
         k = (ident[0] - 1) if ident else 0
-        os.sched_setaffinity(0, {cpus[(k * max(1, len(cpus) // max(1, n_workers))) % len(cpus)]})
+        os.sched_setaffinity(0, {firsts[k % len(firsts)]})
     except Exception:
         pass
 
@@ -361,6 +387,86 @@ def bench_enlarged(spec, fitter_cls, torch, dist, world, rank, dev, num_sms, tf3
     return rec
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin this rank's host threads to the CPUs nvidia-smi reports as local to its GPU (`nvidia-smi topo -m`, CPU Affinity
+    column) BEFORE any pinned host buffer is allocated, so staging memory is first-touched on the GPU's NUMA node."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        header = None
+        for line in out.splitlines():
+            cols = [c.strip() for c in line.split("\t") if c.strip()]
+            if not cols:
+                continue
+            if header is None and any("CPU Affinity" in c for c in cols):
+                header = cols
+                continue
+            if header is not None and cols[0] == f"GPU{local_rank}":
+                idx = [i for i, c in enumerate(header) if "CPU Affinity" in c][0] + 1   # data rows start with the row label
+                spec = cols[idx]
+                cpus = set()
+                for part in spec.split(","):
+                    lo, _, hi = part.partition("-")
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+                cpus &= set(os.sched_getaffinity(0))
+                if cpus:
+                    os.sched_setaffinity(0, cpus)
+                    return {"cpus": spec, "bound": True}
+        return {"bound": False, "why": "no CPU Affinity entry for this GPU"}
+    except Exception as e:   # noqa: BLE001
+        return {"bound": False, "why": str(e)[:80]}
+
+
+def h2d_probe(torch, dist, world, dev, seconds=0.6, chunk_bytes=850_000_000):
+    """Concurrent host->device bandwidth of the box: every rank streams a pinned buffer to its GPU with plain
+    cudaMemcpyAsync (one copy per chunk, as the host-buffer entry points do) at the same time; per-rank GB/s by CUDA
+    events, aggregate = sum over ranks.  The ceiling the PCIe-bound end-to-end paths can reach at this GPU count."""
+    n = chunk_bytes // 4
+    host = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    host.fill_(1.0)
+    devb = torch.empty(n, dtype=torch.float32, device=dev)
+    devb.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 0
+    t0 = time.perf_counter()
+    e0.record()
+    while time.perf_counter() - t0 < seconds:
+        devb.copy_(host, non_blocking=True)
+        reps += 1
+    e1.record()
+    torch.cuda.synchronize()
+    gbs = reps * n * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    t = torch.tensor([gbs], device=dev, dtype=torch.float64)
+    lo = t.clone()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    del host, devb
+    return {"aggregate_gbs": t.item(), "min_rank_gbs": lo.item(), "ranks": world, "chunk_bytes": n * 4,
+            "how": "pinned -> device cudaMemcpyAsync, all ranks at once, CUDA events"}
+
+
+def strong_record(fn_device, make_slice, n_total, width, torch, dist, world, rank, dev, steps, warmup):
+    """One batch of n_total rows cut by sample index across the ranks (sharding.shard_bounds), run through
+    sharding.run_sharded and gathered with sharding.gather_rows (one NCCL all_gather of the ragged shards at the end):
+    barrier + synchronize on both sides, CUDA events, max over ranks.  Returns (rows per second, ms per step)."""
+    from nlml_hpe_b200 import sharding
+    lo, hi = sharding.shard_bounds(n_total, world, rank)
+    Xs = make_slice(lo, hi)
+    out = {}
+
+    def step():
+        out["y"] = sharding.run_sharded(fn_device, lambda a, b: Xs, n_total)
+    ms, _ = time_steps(step, steps, warmup, torch, dist, world)
+    y = out["y"]
+    assert y.shape[0] == n_total and y.shape[1] == width
+    ok = bool(torch.isfinite(y).all().item())
+    del Xs
+    return n_total / (ms / steps * 1e-3), ms / steps, ok
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -375,6 +481,8 @@ def run_b200(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: nlml_hpe_b200 has no CPU fallback")
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa(local) if not args.no_numa_bind else {"bound": False, "why": "--no-numa-bind"}
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -441,10 +549,39 @@ def run_b200(args):
         mlp_e2e_ms = ms_me / e2e_steps
     clk2 = clocks2.summary()
 
+    # the same end-to-end calls fed PAGEABLE host memory (what the reference hands over: plain numpy arrays)
+    n_pg = min(n, 262144)
+    X_page = np.array(X_host.numpy()[:n_pg], copy=True)
+    ms_pg_t = time_host_steps(lambda: fitter.fit_host(X_page, T_ITERS, LR, CLIP, out=P_host[:n_pg]), 1, 1, torch, dist, world)
+    ms_pg_m = time_host_steps(lambda: model.predict_host(X_page), 2, 1, torch, dist, world) / 2
+    del X_page
+
+    # concurrent host->device bandwidth at this GPU count (the ceiling of the PCIe-bound end-to-end paths)
+    probe = h2d_probe(torch, dist, world, dev)
+
+    # strong scaling: ONE n-row batch cut by sample index across the ranks, gathered at the end (NCCL all_gather)
+    strong = {}
+    if not args.no_strong:
+        def make_slice(lo, hi):
+            return synthetic.make_features_torch(hi - lo, art["W"], *rows, U_id=art["U_id"], seed=4242 + rank, device=dev)
+        st_steps = max(1, min(steps, 3))
+        v, ms_s, ok = strong_record(lambda x: fitter.fit(x, T_ITERS, LR, CLIP), make_slice, n, 8, torch, dist, world, rank, dev, st_steps, 1)
+        strong["tucker"] = {"value": v, "unit": "poses/s", "ms_per_step": ms_s, "rows_total": n, "finite": ok}
+        v, ms_s, ok = strong_record(lambda x: model.predict(x), make_slice, n, 3, torch, dist, world, rank, dev, st_steps, 1)
+        strong["mlp"] = {"value": v, "unit": "poses/s", "ms_per_step": ms_s, "rows_total": n, "finite": ok}
+        v, ms_s, ok = strong_record(lambda x: fitter.solve(x), make_slice, n, 8, torch, dist, world, rank, dev, st_steps, 1)
+        strong["converged"] = {"value": v, "unit": "poses/s", "ms_per_step": ms_s, "rows_total": n, "finite": ok}
+        strong["scaling"] = "strong"
+        strong["how"] = (f"one batch of {n} rows cut with sharding.shard_bounds over {world} rank(s), each rank runs its slice "
+                         "(device-resident), sharding.gather_rows all-gathers the ragged [rows, k] results over NCCL; "
+                         "barrier + synchronize on both sides, CUDA events, max over ranks; efficiency = value(N) / (N x value(1))")
+
     enlarged = []
     if not args.no_enlarged:
         del model
         torch.cuda.empty_cache()
+        if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)
         for spec in ENLARGED:
             enlarged.append(bench_enlarged(spec, TuckerFitter, torch, dist, world, rank, dev, num_sms, tf32_peak, peaks,
                                            with_cpu=(world == 1 and rank == 0 and not args.no_cpu_baseline)))
@@ -472,16 +609,19 @@ def run_b200(args):
                 "d2h_bytes_per_step": n * 8 * 4, "steps": e2e_steps,
                 "api": "nlml_tucker_fit_host_f32 (TuckerFitter.fit_host), pinned host X -> host P"},
         "gpu_launches": int(t_launches),
-        "roofline": {"bound": "tensor", "achieved": per_gpu_t * TUCKER_TC_FLOP_PER_POSE / 1e12,
-                     "peak": peaks["bf16_tflops_sustained"] / 2, "unit": "TFLOP/s",
-                     "frac": per_gpu_t * TUCKER_TC_FLOP_PER_POSE / 1e12 / (peaks["bf16_tflops_sustained"] / 2),
+        "roofline": {"bound": "tensor", "achieved": per_gpu_t * TUCKER_TC_USEFUL_FLOP_PER_POSE / 1e12,
+                     "peak": tf32_peak, "unit": "TFLOP/s",
+                     "frac": per_gpu_t * TUCKER_TC_USEFUL_FLOP_PER_POSE / 1e12 / tf32_peak,
+                     "issued_frac": per_gpu_t * TUCKER_TC_FLOP_PER_POSE / 1e12 / tf32_peak, "mma_passes": 3,
                      "traffic": TUCKER_TC_NCU_DRAM_BYTES_PER_POSE * n,
                      "traffic_note": "bytes per launch = ncu dram__bytes_read+write of a 37 888-sample launch (profiles/r01_tucker_tc_ncu.txt), "
                                      f"{TUCKER_TC_NCU_DRAM_BYTES_PER_POSE:.0f} B/sample against {TUCKER_BYTES_PER_POSE} algorithmic, x samples per launch",
                      "kernel": "tucker_fit_tc_kernel",
-                     "peak_source": peaks["source"] + " (TF32 dense = half of the measured sustained bf16 rate)",
-                     "note": "issued TF32 tensor work: per sample-iteration two 3xTF32 GEMM rows (128x224x16 and 128x96x40 per 128 "
-                             f"samples, 3 MMAs per MAC) = {TUCKER_TC_FLOP_PER_POSE / 1e6:.1f} MFLOP/pose at T=3000. The tensor pipe is NOT "
+                     "peak_source": "measured live: nlml_measure_tf32_tflops (dense TF32 tcgen05 probe, all SMs)",
+                     "note": f"frac = USEFUL flops ({TUCKER_TC_USEFUL_FLOP_PER_POSE / 1e6:.1f} MFLOP/pose: T x 2 x (2 x 15 x 216), the two contractions "
+                             "with the folded Gram tensor) / measured TF32 peak -- the same convention as mlp.roofline.frac; issued_frac counts "
+                             "the 3xTF32 passes and the operand padding (per sample-iteration two GEMM rows, 128x224x16 and 128x96x40 per 128 "
+                             f"samples, 3 MMAs per MAC = {TUCKER_TC_FLOP_PER_POSE / 1e6:.1f} MFLOP/pose). The tensor pipe is NOT "
                              "the binding unit of this kernel (ncu: tensor pipe ~31 % active): each iteration is a serial chain "
                              "features -> operand rows -> GEMMs -> tcgen05.ld -> gradient -> step, and the kernel is bound by that "
                              "chain's latency plus the FP32 work left on the CUDA cores (roofline_fp32)."},
@@ -532,10 +672,18 @@ def run_b200(args):
             "clocks": {"sm_mhz": clk2["sm_mhz"], "sm_max_mhz": clk2["sm_max_mhz"], "reasons": clk2["reasons"]},
         },
         "enlarged": enlarged,
+        "strong": strong,
+        "h2d_probe": probe,
+        "numa": numa,
+        "e2e_pageable": {"tucker": {"value": n_pg * world / (ms_pg_t * 1e-3), "unit": "poses/s", "rows": n_pg},
+                         "mlp": {"value": n_pg * world / (ms_pg_m * 1e-3), "unit": "poses/s", "rows": n_pg},
+                         "note": "same host-buffer C-ABI calls fed pageable numpy arrays (the reference's callers hand over "
+                                 "plain numpy / torch CPU tensors); the driver stages pageable copies through its own pinned buffers"},
         "fp32_fma_peak_tflops_measured": fp32_peak, "fp32_fma_3reg_peak_tflops_measured": fp32_peak_3reg,
         "tf32_tensor_peak_tflops_measured": tf32_peak,
     }
     if world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)   # the CPU legs use every host core again
         line["cpu_baseline"] = cpu_baseline_tucker(art, rows, cores)
         line["converged"]["cpu_baseline"] = cpu_baseline_powell(art, rows, cores)
         line["mlp"]["cpu_baseline"] = cpu_baseline_mlp(art, cores)
@@ -561,17 +709,19 @@ def run_reference(args):
         if time.perf_counter() - t0 > 150:
             break
     dt = time.perf_counter() - t0
-    value = cores * len(vals) / dt
+    # samples fitted (one per pinned physical core per step) / time inside the fits (worker start-up and imports excluded,
+    # exactly as in the b200 arm's cpu_baseline leg, so the two CPU figures of a run agree)
+    value = sum(v["cores"] for v in vals) / sum(v["seconds"] for v in vals)
     base = dict(vals[-1], value=value)
     mlp = cpu_baseline_mlp(art, cores)
     line = {
         "impl": "reference",
         "metric": "poses/sec (Tucker-fit, fixed T=3000 iterations; Encoder+MLP heads under 'mlp')",
         "value": value, "unit": "poses/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": min(args.warmup, 1),
-        "ms_per_step": dt / len(vals) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": sum(v["seconds"] for v in vals) / len(vals) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"TD_Inference Tucker-fit, CPU port of the reference (TD_Tester.optimize_with_sgd), shipped W ranks {RANKS}, "
-                               f"F={F}, T={T_ITERS}; each step = {cores} samples, one per host core"},
+                               f"F={F}, T={T_ITERS}; each step = {vals[-1]['cores']} samples, one per physical host core (pinned)"},
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "mlp": {"value": mlp["value"], "unit": "poses/s", "cpu_baseline": mlp,
@@ -590,6 +740,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-enlarged", action="store_true", help="skip the enlarged-core records (BASELINE.json configs[4])")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling records")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the rank to its GPU's NUMA-local CPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -83,6 +83,30 @@ int nlml_tucker_solve_f32(nlml_tucker_plan* plan, const float* X_dev, int64_t N,
 int nlml_tucker_solve_host_f32(nlml_tucker_plan* plan, const float* X_host, int64_t N, int64_t ldx,
                                int max_evals, float* P_out_host, int64_t ldp);
 
+/* TD_Tester.Test as the reference SHIPS it (/root/reference/TD_Tester.py:162-199): scipy.optimize.minimize(method="Powell")
+ * over the float64 objective of :31-58 from p = 0.  scipy is an unpinned third-party dependency of the reference; the
+ * algorithm is restated from scipy 1.18.1 (csrc/powell_math.h: bracket, Brent, _linesearch_powell, _minimize_powell with
+ * the defaults the reference leaves in place) and the objective is evaluated in the reference's own operation order
+ * (np.einsum accumulation order, numpy's pairwise np.sum), so the result equals the reference's BIT FOR BIT, including the
+ * number of function evaluations (pinned by tests/golden/powell_golden.npz, 96 outputs of the real reference).
+ * One CTA per sample; float64-pipe bound.  P_out: DEVICE float64 [N][ldp] = result.x (radians + identity coefficients);
+ * fun_out / nfev_out: optional DEVICE [N] (result.fun, result.nfev).  Asynchronous on `stream`. */
+int nlml_tucker_powell_f64(nlml_tucker_plan* plan, const float* X_dev, int64_t N, int64_t ldx, double* P_out_dev,
+                           int64_t ldp, double* fun_out_dev, int32_t* nfev_out_dev, void* stream);
+
+/* Offline steps that produce the hot path's constants.
+ * nlml_cosine_fit_f64 = TD_Trainer.Train for one factor matrix (/root/reference/TD_Trainer.py:232-351): per column the
+ * Fourier initial guess of est_params_by_Uniform_Fourier (:125-148), then scipy Powell on the least-squares objective
+ * (:38-43, :60-93), float64, one GPU thread per column.  U_host [n_rows][n_cols] row-major (rows = angle bins), w_deg_host
+ * [n_rows] the bins in degrees; params_out_host [n_cols][4] = (a, b, c, d); optional init_out_host [n_cols][4],
+ * fun_out_host [n_cols], nfev_out_host [n_cols].  HOST pointers (the matrices are tiny).  Synchronous. */
+int nlml_cosine_fit_f64(const double* U_host, int n_rows, int n_cols, const double* w_deg_host, double* params_out_host,
+                        double* init_out_host, double* fun_out_host, int32_t* nfev_out_host, int device);
+/* nlml_core_times_features_f32 = W = core x_5 U_feat (/root/reference/TD_main.py:231-238): core_host [R][M] (R = product of
+ * the four mode ranks, M = feature rank), U_feat_host [F][M] -> W_out_host [R][F].  HOST pointers.  Synchronous. */
+int nlml_core_times_features_f32(const float* core_host, const float* U_feat_host, int64_t R, int M, int F, float* W_out_host,
+                                 int device);
+
 /* Number of kernel launches issued by this plan so far (for bench.py's gpu_launches). */
 int64_t nlml_tucker_launch_count(const nlml_tucker_plan* plan);
 

@@ -8,14 +8,15 @@ Same names, argument meaning and return conventions as /root/reference/TD_Tester
 plus the batched form the reference lacks (`optimize_with_sgd_batch`).
 
 Behavioural notes:
-* `Test` DOES NOT RETURN THE SAME ANGLES AS THE REFERENCE'S `Test`.  Like the reference's default it runs a converged
-  fit from p = 0, but where the reference calls scipy Powell (:191-199; unpinned third-party search that stops at
-  xtol = ftol = 1e-4 in a flat valley) this module runs a damped-Newton solve of the same objective on the GPU.
-  Measured on 96 outputs of the real reference (tests/golden/powell_golden.npz): the objective value at our result is
-  never above Powell's (same basin, < 1 % apart), and the angles differ by 0.28 degrees in the median, 2.8 degrees at
-  the 90th percentile, 8.7 degrees at most.  A warning is raised if the solve hits its evaluation cap.
-  `TEST_SOLVER = "sgd"` selects the fixed-iteration block the reference keeps commented out at :168-184 instead
-  (the one with the bit-level parity contract, <= 1e-2 degrees).
+* `Test` returns what the reference's `Test` returns, BIT FOR BIT: the default `TEST_SOLVER = "powell"` runs scipy's modified
+  Powell search (the reference's minimize(..., method='Powell'), :191-194) on the GPU -- algorithm restated from scipy
+  1.18.1, objective evaluated in the reference's own float64 operation order (csrc/powell_math.h) -- pinned by 96 outputs of
+  the real reference including the evaluation counts (tests/golden/powell_golden.npz).  Two faster alternatives:
+  `TEST_SOLVER = "converged"`: damped-Newton solve of the same objective (16 M poses/s batched).  It does NOT return
+  Powell's angles: the objective value at its result is never above Powell's (same basin, < 1 % apart), but Powell stops
+  at xtol = ftol = 1e-4 in a flat valley, so the angles differ by 0.28 degrees in the median, 2.8 at the 90th percentile,
+  8.7 at most over those 96 samples; a warning is raised if the solve hits its evaluation cap.
+  `TEST_SOLVER = "sgd"`: the fixed-iteration block the reference keeps commented out at :168-184 (<= 1e-2 degrees).
 * Like the reference, `Test` returns the u_id it was GIVEN (normally None), not the optimum (:291).
 * No module-global trace lists (:18-22) are kept: the call is re-entrant.
 * No progress printing (:131, :142-143).
@@ -30,7 +31,7 @@ import torch
 
 from .tucker import TuckerFitter
 
-TEST_SOLVER = "converged"   # or "sgd": what Test() runs (see the module docstring)
+TEST_SOLVER = "powell"      # "powell" (the reference's shipped default, bit for bit), "converged" or "sgd": what Test() runs
 SOLVE_MAX_EVALS = 64        # evaluation cap of the converged solve (csrc/tucker_math.h lm_default_options)
 
 _PLAN_CACHE = {}
@@ -126,6 +127,13 @@ def optimize_with_sgd(W, x, u_id, u_id_shape, params_y, params_p, params_r, lear
 
 def Test(W, x, u_id_shape, optimized_params_y, optimized_params_p, optimized_params_r, u_id, f_y, f_p, f_r):
     """Reference entry point (TD_Tester.py:162-163) -> (yaw, pitch, roll) in degrees and the given u_id."""
+    if TEST_SOLVER == "powell":
+        fit = _fitter(W, optimized_params_y, optimized_params_p, optimized_params_r)
+        if fit.ranks[0] != int(u_id_shape):
+            raise ValueError(f"u_id_shape={u_id_shape} does not match W.shape[0]={fit.ranks[0]}")
+        xg = torch.from_numpy(_as_numpy(x, np.float32).reshape(1, -1)).to(fit.device)
+        deg = np.degrees(fit.powell(xg)[0].cpu().numpy())          # np.degrees(result.x), :196
+        return deg[0], deg[1], deg[2], u_id
     if TEST_SOLVER == "sgd":
         p = optimize_with_sgd(W, x, u_id, u_id_shape, optimized_params_y, optimized_params_p, optimized_params_r).numpy()
     elif TEST_SOLVER == "converged":
@@ -139,6 +147,6 @@ def Test(W, x, u_id_shape, optimized_params_y, optimized_params_p, optimized_par
                           "step tolerance; the returned angles are the last iterate", RuntimeWarning)
         p = P[0].cpu().numpy()
     else:
-        raise ValueError(f"TEST_SOLVER must be 'converged' or 'sgd', got {TEST_SOLVER!r}")
+        raise ValueError(f"TEST_SOLVER must be 'powell', 'converged' or 'sgd', got {TEST_SOLVER!r}")
     deg = np.degrees(p.astype(np.float64))
     return deg[0], deg[1], deg[2], u_id

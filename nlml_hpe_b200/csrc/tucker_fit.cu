@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "tucker_math.h"
+#include "powell_math.h"
 
 namespace nlml {
 
@@ -1149,6 +1150,161 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
     if (warp == 0) tmem_free_cols(tmem, C::TMEM_COLS);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// TD_Tester.Test as the reference ships it: scipy Powell over the float64 objective (TD_Tester.py:31-58, :191-194),
+// reproduced BIT FOR BIT (powell_math.h).  One CTA per sample: every thread runs the same Powell / Brent control flow
+// on identical values (the search is a sequential scalar algorithm), and each objective evaluation -- 135 x 1404
+// float64 product chains, the part that costs -- is shared by the CTA's threads in exactly the reference's
+// operation order: thread t owns features t, t+128, ...; x_hat accumulates over (i,j,k,l) as np.einsum does; the sum
+// of squares follows numpy's pairwise summation (leaf blocks of <= 128 elements with eight strided accumulators, then
+// the halving tree; the leaf table and the combine program are prepared on the host for the plan's F).
+// Bound by the float64 pipe (5 dependent-free operations per (r, feature) pair).
+// ---------------------------------------------------------------------------------------------
+constexpr int kPowellThreads = 128;
+constexpr int kPowellMaxFeat = 16;     // features per thread: F <= 2048
+constexpr int kPowellMaxLeaves = 64;
+
+struct PowellArgs {
+    const float* X;
+    long long N, ldx;
+    const float* W2;
+    double* P;            // [N][ldp]
+    long long ldp;
+    double* fun;          // [N] or null
+    int* nfev;            // [N] or null
+    int ri, ry, rp, rr, F;
+    int nleaf, nprog;
+    short leaf_off[kPowellMaxLeaves], leaf_len[kPowellMaxLeaves];
+    signed char prog[2 * kPowellMaxLeaves];   // postfix combine program of the pairwise tree: k >= 0 push leaf k, -1 add
+    double rows_y[4 * kMaxModeRank], rows_p[4 * kMaxModeRank], rows_r[4 * kMaxModeRank];
+};
+
+struct PowellCoopObjective {
+    const PowellArgs& a;
+    const float* xs;      // shared: this sample's x
+    double* e;            // shared: [F] squared residuals
+    double* racc;         // shared: [nleaf][8]
+    double* leafsum;      // shared: [nleaf]
+    double* result;       // shared: [1]
+    __device__ double operator()(const double* p) const {
+        const int tid = threadIdx.x;
+        powell::TuckerFactors t;
+        powell::tucker_factors(p, a.ry, a.rp, a.rr, a.rows_y, a.rows_p, a.rows_r, t);
+        const double* u = p + 3;
+        // (x - x_hat)^2 per feature; the thread's features advance together over r (independent accumulation chains)
+        double acc[kPowellMaxFeat];
+#pragma unroll
+        for (int k = 0; k < kPowellMaxFeat; ++k) acc[k] = 0.0;
+        const float* wrow = a.W2;
+        for (int i = 0; i < a.ri; ++i)
+            for (int j = 0; j < a.ry; ++j)
+                for (int kk = 0; kk < a.rp; ++kk)
+                    for (int l = 0; l < a.rr; ++l, wrow += a.F) {
+                        const double ui = u[i], fy = t.fy[j], fp = t.fp[kk], fr = t.fr[l];
+#pragma unroll
+                        for (int k = 0; k < kPowellMaxFeat; ++k) {
+                            const int m = tid + k * kPowellThreads;
+                            if (m < a.F) {
+                                const double term = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn((double)__ldg(wrow + m), ui), fy), fp), fr);
+                                acc[k] = __dadd_rn(acc[k], term);
+                            }
+                        }
+                    }
+#pragma unroll
+        for (int k = 0; k < kPowellMaxFeat; ++k) {
+            const int m = tid + k * kPowellThreads;
+            if (m < a.F) {
+                const double d = __dsub_rn((double)xs[m], acc[k]);
+                e[m] = __dmul_rn(d, d);
+            }
+        }
+        __syncthreads();
+        // numpy pairwise sum, leaves first: accumulator j of leaf k
+        for (int w = tid; w < a.nleaf * 8; w += kPowellThreads) {
+            const int k = w >> 3, j = w & 7, off = a.leaf_off[k], n = a.leaf_len[k];
+            if (n >= 8) {
+                double r = e[off + j];
+                for (int i = 8; i < n - (n % 8); i += 8) r = __dadd_rn(r, e[off + i + j]);
+                racc[w] = r;
+            }
+        }
+        __syncthreads();
+        for (int k = tid; k < a.nleaf; k += kPowellThreads) {
+            const int off = a.leaf_off[k], n = a.leaf_len[k];
+            double res;
+            if (n < 8) {
+                res = 0.0;
+                for (int i = 0; i < n; ++i) res = __dadd_rn(res, e[off + i]);
+            } else {
+                const double* r = racc + 8 * k;
+                res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+                for (int i = n - (n % 8); i < n; ++i) res = __dadd_rn(res, e[off + i]);
+            }
+            leafsum[k] = res;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double stack[16];
+            int sp = 0;
+            for (int i = 0; i < a.nprog; ++i) {
+                const int op = a.prog[i];
+                if (op >= 0) stack[sp++] = leafsum[op];
+                else {
+                    --sp;
+                    stack[sp - 1] = __dadd_rn(stack[sp - 1], stack[sp]);
+                }
+            }
+            *result = __dmul_rn(0.5, stack[0]);
+        }
+        __syncthreads();
+        const double v = *result;
+        __syncthreads();   // everybody has read the value before the next evaluation overwrites it
+        return v;
+    }
+};
+
+__global__ void __launch_bounds__(kPowellThreads) tucker_powell_kernel(const __grid_constant__ PowellArgs a) {
+    extern __shared__ __align__(16) uint8_t psm_[];
+    double* e = reinterpret_cast<double*>(psm_);
+    double* racc = e + a.F;
+    double* leafsum = racc + 8 * kPowellMaxLeaves;
+    double* result = leafsum + kPowellMaxLeaves;
+    float* xs = reinterpret_cast<float*>(result + 2);
+    const long long s = blockIdx.x;
+    for (int f = threadIdx.x; f < a.F; f += kPowellThreads) xs[f] = __ldg(a.X + s * a.ldx + f);
+    __syncthreads();
+    PowellCoopObjective obj{a, xs, e, racc, leafsum, result};
+    const int NP = 3 + a.ri;
+    double x[powell::kMaxN], direc[powell::kMaxN * powell::kMaxN];
+    for (int i = 0; i < NP; ++i) x[i] = 0.0;   // initial_guess = zeros (TD_Tester.py:166)
+    const powell::Result res = powell::minimize(obj, NP, x, direc);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NP; ++i) a.P[s * a.ldp + i] = x[i];
+        if (a.fun) a.fun[s] = res.fun;
+        if (a.nfev) a.nfev[s] = res.nfev;
+    }
+}
+
+// TD_Trainer.Train for the columns of one factor matrix (TD_Trainer.py:232-351 -> :125-148 Fourier initial guess, :60-93
+// scipy Powell per column): one thread per column, float64, the statements of powell_math.h.
+__global__ void cosine_fit_kernel(const double* __restrict__ U, int n_rows, int n_cols, const double* __restrict__ w_rad,
+                                  double* __restrict__ init, double* __restrict__ out, double* __restrict__ fun, int* __restrict__ nfev) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_cols) return;
+    double x[powell::kMaxN], direc[16], g[4];
+    powell::fourier_init(U + j, n_cols, w_rad, n_rows, g);
+    for (int i = 0; i < 4; ++i) {
+        x[i] = g[i];
+        if (init) init[4 * j + i] = g[i];
+    }
+    powell::CosineObjective obj{U + j, w_rad, n_rows, n_cols};
+    const powell::Result res = powell::minimize(obj, 4, x, direc);
+    for (int i = 0; i < 4; ++i) out[4 * j + i] = x[i];
+    if (fun) fun[j] = res.fun;
+    if (nfev) nfev[j] = res.nfev;
+}
+
 // register-only FFMA loop: measures the sustained FP32 FMA rate used as a roofline denominator
 __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
@@ -1252,6 +1408,7 @@ struct nlml_tucker_plan {
     bool cta_ok = false;      // CTA-per-sample kernel usable (its working set fits shared memory)
     bool gen_ok = false;      // run-time-rank tensor-core kernel usable (tucker_gen.cuh)
     tgen::GenCfg gen{};
+    double rows64[3][4 * kMaxModeRank] = {};   // the cosine rows in float64, as the reference's Powell objective uses them
     uint8_t* tc_ops = nullptr;              // (5,3,3,3) tensor-core kernel: image of its two constant B operands
     uint8_t* gen_tiles = nullptr;           // tile images of S (hi/lo, UMMA layout), streamed by TMA
     float* q_ws[3] = {nullptr, nullptr, nullptr};   // q = W2 x slabs: [0],[1] host-pipeline slots, [2] device-buffer calls
@@ -1638,6 +1795,9 @@ extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, i
     TuckerArgs& a = pl->base;
     a.W2 = pl->W2; a.S = pl->S; a.St = pl->St;
     a.F = F; a.ri = r_id; a.ry = r_y; a.rp = r_p; a.rr = r_r; a.nBCDp = pl->nBCDp;
+    for (int j = 0; j < 4 * r_y; ++j) pl->rows64[0][j] = rows_y[j];
+    for (int j = 0; j < 4 * r_p; ++j) pl->rows64[1][j] = rows_p[j];
+    for (int j = 0; j < 4 * r_r; ++j) pl->rows64[2][j] = rows_r[j];
     for (int j = 0; j < 4 * r_y; ++j) a.rows_y[j] = (float)rows_y[j];  // f64 -> f32, TD_Tester.py:172-174
     for (int j = 0; j < 4 * r_p; ++j) a.rows_p[j] = (float)rows_p[j];
     for (int j = 0; j < 4 * r_r; ++j) a.rows_r[j] = (float)rows_r[j];
@@ -1765,6 +1925,113 @@ extern "C" int nlml_debug_gen_timing(float* host_out /*[64]*/) {   // developmen
     return 0;
 }
 #endif
+
+
+// numpy's pairwise-summation tree for n elements: leaves (offset, length) in order and the postfix combine program
+static void pairwise_plan(int off, int n, std::vector<short>& loff, std::vector<short>& llen, std::vector<signed char>& prog) {
+    if (n <= 128) {
+        prog.push_back((signed char)loff.size());
+        loff.push_back((short)off);
+        llen.push_back((short)n);
+        return;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    pairwise_plan(off, n2, loff, llen, prog);
+    pairwise_plan(off + n2, n - n2, loff, llen, prog);
+    prog.push_back(-1);
+}
+
+extern "C" int nlml_tucker_powell_f64(nlml_tucker_plan* pl, const float* X_dev, int64_t N, int64_t ldx, double* P_out_dev,
+                                      int64_t ldp, double* fun_out_dev, int32_t* nfev_out_dev, void* stream) {
+    if (!pl || (N > 0 && (!X_dev || !P_out_dev))) return set_error(NLML_E_INVALID, "null pointer argument");
+    if (N < 0 || ldx < pl->F || ldp < 3 + pl->ri)
+        return set_error(NLML_E_INVALID, "bad sizes: N=%lld ldx=%lld (F=%d) ldp=%lld (need >= %d)", (long long)N, (long long)ldx, pl->F,
+                         (long long)ldp, 3 + pl->ri);
+    if (pl->F > kPowellThreads * kPowellMaxFeat || pl->F > 32000)
+        return set_error(NLML_E_UNSUPPORTED, "the Powell fit serves F <= %d", kPowellThreads * kPowellMaxFeat);
+    if (N == 0) return 0;
+    DeviceGuard guard(pl->device);
+    PowellArgs a{};
+    a.X = X_dev; a.N = N; a.ldx = ldx; a.W2 = pl->W2; a.P = P_out_dev; a.ldp = ldp; a.fun = fun_out_dev; a.nfev = nfev_out_dev;
+    a.ri = pl->ri; a.ry = pl->ry; a.rp = pl->rp; a.rr = pl->rr; a.F = pl->F;
+    std::vector<short> loff, llen;
+    std::vector<signed char> prog;
+    pairwise_plan(0, pl->F, loff, llen, prog);
+    if ((int)loff.size() > kPowellMaxLeaves) return set_error(NLML_E_UNSUPPORTED, "pairwise-sum tree too large");
+    a.nleaf = (int)loff.size(); a.nprog = (int)prog.size();
+    std::memcpy(a.leaf_off, loff.data(), sizeof(short) * loff.size());
+    std::memcpy(a.leaf_len, llen.data(), sizeof(short) * llen.size());
+    std::memcpy(a.prog, prog.data(), prog.size());
+    std::memcpy(a.rows_y, pl->rows64[0], sizeof(a.rows_y));
+    std::memcpy(a.rows_p, pl->rows64[1], sizeof(a.rows_p));
+    std::memcpy(a.rows_r, pl->rows64[2], sizeof(a.rows_r));
+    const size_t smem = sizeof(double) * ((size_t)pl->F + 9 * kPowellMaxLeaves + 2) + sizeof(float) * pl->F + 16;
+    NLML_CUDA(cudaFuncSetAttribute(tucker_powell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tucker_powell_kernel<<<(unsigned)N, kPowellThreads, smem, (cudaStream_t)stream>>>(a);
+    NLML_CUDA(cudaGetLastError());
+    pl->launches += 1;
+    return 0;
+}
+
+extern "C" int nlml_cosine_fit_f64(const double* U_host, int n_rows, int n_cols, const double* w_deg_host, double* params_out_host,
+                                   double* init_out_host, double* fun_out_host, int32_t* nfev_out_host, int device) {
+    if (!U_host || !w_deg_host || !params_out_host) return set_error(NLML_E_INVALID, "null pointer argument");
+    if (n_rows < 2 || n_cols < 1) return set_error(NLML_E_INVALID, "need at least 2 bins and 1 column");
+    if (int rc = check_device(device)) return rc;
+    DeviceGuard guard(device);
+    std::vector<double> w(n_rows);
+    for (int i = 0; i < n_rows; ++i) w[i] = w_deg_host[i] * (3.141592653589793238462643383279502884 / 180.0);   // np.radians
+    struct Buf {
+        void* p = nullptr;
+        ~Buf() { cudaFree(p); }
+    } dU, dw, dinit, dout, dfun, dnfev;
+    NLML_CUDA(cudaMalloc(&dU.p, sizeof(double) * n_rows * n_cols));
+    NLML_CUDA(cudaMalloc(&dw.p, sizeof(double) * n_rows));
+    NLML_CUDA(cudaMalloc(&dinit.p, sizeof(double) * 4 * n_cols));
+    NLML_CUDA(cudaMalloc(&dout.p, sizeof(double) * 4 * n_cols));
+    NLML_CUDA(cudaMalloc(&dfun.p, sizeof(double) * n_cols));
+    NLML_CUDA(cudaMalloc(&dnfev.p, sizeof(int) * n_cols));
+    NLML_CUDA(cudaMemcpy(dU.p, U_host, sizeof(double) * n_rows * n_cols, cudaMemcpyHostToDevice));
+    NLML_CUDA(cudaMemcpy(dw.p, w.data(), sizeof(double) * n_rows, cudaMemcpyHostToDevice));
+    cosine_fit_kernel<<<(n_cols + 31) / 32, 32>>>((const double*)dU.p, n_rows, n_cols, (const double*)dw.p, (double*)dinit.p, (double*)dout.p,
+                                                   (double*)dfun.p, (int*)dnfev.p);
+    NLML_CUDA(cudaGetLastError());
+    NLML_CUDA(cudaMemcpy(params_out_host, dout.p, sizeof(double) * 4 * n_cols, cudaMemcpyDeviceToHost));
+    if (init_out_host) NLML_CUDA(cudaMemcpy(init_out_host, dinit.p, sizeof(double) * 4 * n_cols, cudaMemcpyDeviceToHost));
+    if (fun_out_host) NLML_CUDA(cudaMemcpy(fun_out_host, dfun.p, sizeof(double) * n_cols, cudaMemcpyDeviceToHost));
+    if (nfev_out_host) NLML_CUDA(cudaMemcpy(nfev_out_host, dnfev.p, sizeof(int) * n_cols, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// W = core x_5 U_feat (/root/reference/TD_main.py:231-238: tl.tensordot(core, U_feat^T, axes=(4, 0))): W2[r][f] = sum_m core2[r][m] U[f][m]
+extern "C" int nlml_core_times_features_f32(const float* core_host, const float* U_feat_host, int64_t R, int M, int F, float* W_out_host,
+                                            int device) {
+    if (!core_host || !U_feat_host || !W_out_host) return set_error(NLML_E_INVALID, "null pointer argument");
+    if (R < 1 || M < 1 || F < 1) return set_error(NLML_E_INVALID, "sizes must be positive");
+    if (int rc = check_device(device)) return rc;
+    DeviceGuard guard(device);
+    struct Buf {
+        void* p = nullptr;
+        ~Buf() { cudaFree(p); }
+    } dc, du, dq;
+    const int64_t Rp = ceil_div(R, 128) * 128;
+    NLML_CUDA(cudaMalloc(&dc.p, sizeof(float) * R * M));
+    NLML_CUDA(cudaMalloc(&du.p, sizeof(float) * (size_t)F * M));
+    NLML_CUDA(cudaMalloc(&dq.p, sizeof(float) * Rp * F));
+    NLML_CUDA(cudaMemcpy(dc.p, core_host, sizeof(float) * R * M, cudaMemcpyHostToDevice));
+    NLML_CUDA(cudaMemcpy(du.p, U_feat_host, sizeof(float) * (size_t)F * M, cudaMemcpyHostToDevice));
+    // the projection kernel computes rows(core) . rows(U_feat) in its CTA-blocked layout [R/128][F][128]
+    const int vec_ok = (M % 4 == 0);
+    tgen::tucker_project_kernel<<<dim3((unsigned)(Rp / 128), (unsigned)ceil_div(F, 64)), 256>>>((const float*)dc.p, R, M, (const float*)du.p, F, M, vec_ok,
+                                                                                               (float*)dq.p);
+    NLML_CUDA(cudaGetLastError());
+    std::vector<float> blocked((size_t)Rp * F);
+    NLML_CUDA(cudaMemcpy(blocked.data(), dq.p, sizeof(float) * Rp * F, cudaMemcpyDeviceToHost));
+    for (int64_t r = 0; r < R; ++r)
+        for (int f = 0; f < F; ++f) W_out_host[r * F + f] = blocked[((r / 128) * F + f) * 128 + r % 128];
+    return 0;
+}
 
 extern "C" int64_t nlml_tucker_launch_count(const nlml_tucker_plan* pl) { return pl ? pl->launches : 0; }
 

@@ -122,6 +122,31 @@ class TuckerFitter:
                                                    evals.data_ptr() if return_evals and n > 0 else None, stream))
         return (out, evals) if return_evals else out
 
+    def powell(self, X, return_info=False):
+        """The reference's shipped default fit, bit for bit: scipy Powell from p = 0 over TD_Tester.objective
+        (TD_Tester.py:31-58, :191-194; algorithm restated from scipy 1.18.1 in csrc/powell_math.h, objective evaluated in
+        the reference's own operation order).  X: CUDA float32 [N, >=F].  Returns a CUDA float64 tensor [N, 3+R_id] =
+        result.x (radians + identity coefficients) and, with return_info, (result.fun float64 [N], result.nfev int32 [N]).
+        One CTA per sample, float64: ~10^4 poses/s -- use solve() / fit() for throughput.  Asynchronous."""
+        if not (isinstance(X, torch.Tensor) and X.is_cuda):
+            raise TypeError("powell() takes a CUDA tensor")
+        if X.dtype != torch.float32 or X.dim() != 2 or X.shape[1] < self.F:
+            raise ValueError(f"X must be float32 [N, >={self.F}], got {X.dtype} {tuple(X.shape)}")
+        if X.device.index != self.device_index:
+            raise ValueError(f"X is on {X.device}, plan is on {self.device}")
+        if X.shape[0] > 0 and X.stride(1) != 1:
+            X = X.contiguous()
+        n = X.shape[0]
+        out = torch.empty((n, self.n_params), dtype=torch.float64, device=X.device)
+        fun = torch.empty((n,), dtype=torch.float64, device=X.device) if return_info else None
+        nfev = torch.empty((n,), dtype=torch.int32, device=X.device) if return_info else None
+        stream = torch.cuda.current_stream(X.device).cuda_stream
+        ldx = X.stride(0) if n > 1 else max(X.shape[1], self.F)
+        _lib.check(self._lib.nlml_tucker_powell_f64(self._h, X.data_ptr(), n, ldx, out.data_ptr(), self.n_params,
+                                                    fun.data_ptr() if return_info and n > 0 else None,
+                                                    nfev.data_ptr() if return_info and n > 0 else None, stream))
+        return (out, fun, nfev) if return_info else out
+
     def solve_host(self, X, max_evals=0, out=None):
         """solve() for numpy / CPU float32 [N, F] in host memory; pipelined like fit_host()."""
         if isinstance(X, torch.Tensor):

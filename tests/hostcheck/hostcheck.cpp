@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../nlml_hpe_b200/csrc/tucker_math.h"
+#include "../../nlml_hpe_b200/csrc/powell_math.h"
 
 using namespace nlml;
 
@@ -169,4 +170,66 @@ extern "C" int hostcheck_chol_solve8(const float* A /*[36]*/, const float* g /*[
     const bool ok = nlml::chol_solve<8>(a, gg, dd);
     for (int i = 0; i < 8; ++i) d[i] = dd[i];
     return ok ? 1 : 0;
+}
+
+
+// ---- scipy-Powell restatement (powell_math.h) on the CPU ------------------------------------------------------------
+// TD_Tester.Test's search: Powell from p = 0 over the float64 objective, run-time ranks.
+extern "C" int hostcheck_powell_tucker(const float* W2, int ri, int ry, int rp, int rr, int F, const double* rows_y,
+                                       const double* rows_p, const double* rows_r, const float* X, int64_t N, int64_t ldx,
+                                       double* P /*[N][3+ri]*/, double* fun /*[N]*/, int* nfev /*[N]*/, int exact_mode) {
+    const int R = ri * ry * rp * rr, nA = tri(ri), nB = tri(ry), nC = tri(rp), nD = tri(rr), NP = 3 + ri;
+    std::vector<double> M((size_t)R * R);
+    for (int r = 0; r < R; ++r)
+        for (int c = r; c < R; ++c) M[(size_t)r * R + c] = M[(size_t)c * R + r] = gram_entry(W2, F, r, c);
+    std::vector<double> S((size_t)nB * nC * nD * nA);
+    for (int b = 0; b < nB; ++b)
+        for (int c = 0; c < nC; ++c)
+            for (int d = 0; d < nD; ++d)
+                for (int a = 0; a < nA; ++a)
+                    S[(size_t)((b * nC + c) * nD + d) * nA + a] = powell::fold_entry_f64(M.data(), ri, ry, rp, rr, a, b, c, d);
+    std::vector<double> q(R), direc((size_t)NP * NP), scratch(F);
+    for (int64_t s = 0; s < N; ++s) {
+        if (exact_mode) {   // exact_mode: the reference's own evaluation order (what the CUDA kernel runs)
+            powell::TuckerObjectiveExact obj{ri, ry, rp, rr, F, W2, X + s * ldx, rows_y, rows_p, rows_r, scratch.data()};
+            double x[powell::kMaxN] = {0};
+            const powell::Result res = powell::minimize(obj, NP, x, direc.data());
+            for (int i = 0; i < NP; ++i) P[s * NP + i] = x[i];
+            fun[s] = res.fun;
+            nfev[s] = res.nfev;
+            continue;
+        }
+        double xx = 0.0;
+        for (int f = 0; f < F; ++f) xx += (double)X[s * ldx + f] * (double)X[s * ldx + f];
+        for (int r = 0; r < R; ++r) {
+            double acc = 0.0;
+            for (int f = 0; f < F; ++f) acc += (double)W2[(size_t)r * F + f] * (double)X[s * ldx + f];
+            q[r] = acc;
+        }
+        powell::TuckerObjective obj{ri, ry, rp, rr, S.data(), q.data(), 1, 0.5 * xx, rows_y, rows_p, rows_r};
+        double x[powell::kMaxN] = {0};
+        const powell::Result res = powell::minimize(obj, NP, x, direc.data());
+        for (int i = 0; i < NP; ++i) P[s * NP + i] = x[i];
+        fun[s] = res.fun;
+        nfev[s] = res.nfev;
+    }
+    return 0;
+}
+
+// TD_Trainer.Train for one factor matrix: Fourier initial guess + Powell per column.  U [n_rows][n_cols] row-major.
+extern "C" int hostcheck_cosine_fit(const double* U, int n_rows, int n_cols, const double* w_deg, double* init /*[n_cols][4]*/,
+                                    double* out /*[n_cols][4]*/, double* fun, int* nfev) {
+    std::vector<double> w(n_rows);
+    for (int i = 0; i < n_rows; ++i) w[i] = w_deg[i] * (3.141592653589793238462643383279502884 / 180.0);   // np.radians
+    for (int j = 0; j < n_cols; ++j) {
+        powell::fourier_init(U + j, n_cols, w.data(), n_rows, init + 4 * j);
+        powell::CosineObjective obj{U + j, w.data(), n_rows, n_cols};
+        double x[powell::kMaxN], direc[16];
+        for (int i = 0; i < 4; ++i) x[i] = init[4 * j + i];
+        const powell::Result res = powell::minimize(obj, 4, x, direc);
+        for (int i = 0; i < 4; ++i) out[4 * j + i] = x[i];
+        fun[j] = res.fun;
+        nfev[j] = res.nfev;
+    }
+    return 0;
 }
