@@ -94,6 +94,10 @@ int nlml_tucker_solve_host_f32(nlml_tucker_plan* plan, const float* X_host, int6
 int nlml_tucker_powell_f64(nlml_tucker_plan* plan, const float* X_dev, int64_t N, int64_t ldx, double* P_out_dev,
                            int64_t ldp, double* fun_out_dev, int32_t* nfev_out_dev, void* stream);
 
+/* Test hook: TD_Tester.objective of ONE sample x_dev [F] at npts parameter points pts_dev [npts][3 + r_id] (float64),
+ * evaluated by the Powell kernel's cooperative objective -> vals_dev [npts]. */
+int nlml_debug_powell_objective(nlml_tucker_plan* plan, const float* x_dev, const double* pts_dev, int npts, double* vals_dev);
+
 /* Offline steps that produce the hot path's constants.
  * nlml_cosine_fit_f64 = TD_Trainer.Train for one factor matrix (/root/reference/TD_Trainer.py:232-351): per column the
  * Fourier initial guess of est_params_by_Uniform_Fourier (:125-148), then scipy Powell on the least-squares objective

@@ -20,6 +20,38 @@ namespace powell {
 
 constexpr int kMaxN = 3 + 16;   // parameters: three angles + identity rank (<= 16), or 4 for a cosine row
 
+// Every arithmetic operation of the search is rounded on its own, as CPython / numpy evaluate it: nvcc would otherwise
+// contract a*b+c into a fused multiply-add (one rounding instead of two), the search would evaluate the objective at
+// slightly different points and leave the reference's path.  (The host check build is compiled with -ffp-contract=off.)
+NLML_HD double mul_(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+NLML_HD double add_(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+NLML_HD double sub_(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+NLML_HD double div_(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __ddiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+
 // Counts evaluations and enforces maxfev like scipy's _wrap_scalar_function_maxfun_validation: the call that would exceed
 // the budget is not made, `aborted` is set and every caller unwinds (scipy raises _MaxFuncCallError).
 template <class F>
@@ -47,7 +79,7 @@ struct LineFn {
     int n;
     NLML_HD double operator()(double alpha) {
         double y[kMaxN];
-        for (int i = 0; i < n; ++i) y[i] = p[i] + alpha * xi[i];
+        for (int i = 0; i < n; ++i) y[i] = add_(p[i], mul_(alpha, xi[i]));
         return cf(y);
     }
 };
@@ -78,21 +110,21 @@ NLML_HD Bracket bracket(L& func, bool& aborted_flag, const bool& aborted) {
         double t = xa; xa = xb; xb = t;
         t = fa; fa = fb; fb = t;
     }
-    double xc = xb + gold * (xb - xa);
+    double xc = add_(xb, mul_(gold, sub_(xb, xa)));
     double fc = func(xc);
     if (aborted) { aborted_flag = true; return r; }
     int iter = 0;
     while (fc < fb) {
-        const double tmp1 = (xb - xa) * (fb - fc);
-        const double tmp2 = (xb - xc) * (fb - fa);
-        const double val = tmp2 - tmp1;
-        const double denom = fabs(val) < verysmall ? 2.0 * verysmall : 2.0 * val;
-        double w = xb - ((xb - xc) * tmp2 - (xb - xa) * tmp1) / denom;
-        const double wlim = xb + grow_limit * (xc - xb);
+        const double tmp1 = mul_(sub_(xb, xa), sub_(fb, fc));
+        const double tmp2 = mul_(sub_(xb, xc), sub_(fb, fa));
+        const double val = sub_(tmp2, tmp1);
+        const double denom = fabs(val) < verysmall ? 2.0 * verysmall : mul_(2.0, val);
+        double w = sub_(xb, div_(sub_(mul_(sub_(xb, xc), tmp2), mul_(sub_(xb, xa), tmp1)), denom));
+        const double wlim = add_(xb, mul_(grow_limit, sub_(xc, xb)));
         if (iter > maxiter) break;   // scipy raises RuntimeError here; unreachable for the objectives of this library
         ++iter;
         double fw;
-        if ((w - xc) * (xb - w) > 0.0) {
+        if (mul_(sub_(w, xc), sub_(xb, w)) > 0.0) {
             fw = func(w);
             if (aborted) { aborted_flag = true; return r; }
             if (fw < fc) {
@@ -102,25 +134,25 @@ NLML_HD Bracket bracket(L& func, bool& aborted_flag, const bool& aborted) {
                 xc = w; fc = fw;
                 break;
             }
-            w = xc + gold * (xc - xb);
+            w = add_(xc, mul_(gold, sub_(xc, xb)));
             fw = func(w);
             if (aborted) { aborted_flag = true; return r; }
-        } else if ((w - wlim) * (wlim - xc) >= 0.0) {
+        } else if (mul_(sub_(w, wlim), sub_(wlim, xc)) >= 0.0) {
             w = wlim;
             fw = func(w);
             if (aborted) { aborted_flag = true; return r; }
-        } else if ((w - wlim) * (xc - w) > 0.0) {
+        } else if (mul_(sub_(w, wlim), sub_(xc, w)) > 0.0) {
             fw = func(w);
             if (aborted) { aborted_flag = true; return r; }
             if (fw < fc) {
                 xb = xc; xc = w;
-                w = xc + gold * (xc - xb);
+                w = add_(xc, mul_(gold, sub_(xc, xb)));
                 fb = fc; fc = fw;
                 fw = func(w);
                 if (aborted) { aborted_flag = true; return r; }
             }
         } else {
-            w = xc + gold * (xc - xb);
+            w = add_(xc, mul_(gold, sub_(xc, xb)));
             fw = func(w);
             if (aborted) { aborted_flag = true; return r; }
         }
@@ -165,34 +197,34 @@ NLML_HD void brent_minimize(L& func, double tol, bool& aborted_flag, const bool&
     double deltax = 0.0, rat = 0.0;
     int iter = 0;
     while (iter < maxiter) {
-        const double tol1 = tol * fabs(x) + mintol;
-        const double tol2 = 2.0 * tol1;
-        const double xmid = 0.5 * (a + b);
-        if (fabs(x - xmid) < (tol2 - 0.5 * (b - a))) break;
+        const double tol1 = add_(mul_(tol, fabs(x)), mintol);
+        const double tol2 = mul_(2.0, tol1);
+        const double xmid = mul_(0.5, add_(a, b));
+        if (fabs(sub_(x, xmid)) < sub_(tol2, mul_(0.5, sub_(b, a)))) break;
         if (fabs(deltax) <= tol1) {
-            deltax = (x >= xmid) ? a - x : b - x;   // golden section step
-            rat = cg * deltax;
+            deltax = (x >= xmid) ? sub_(a, x) : sub_(b, x);   // golden section step
+            rat = mul_(cg, deltax);
         } else {                                     // parabolic step
-            double tmp1 = (x - w) * (fx - fv);
-            double tmp2 = (x - v) * (fx - fw);
-            double p = (x - v) * tmp2 - (x - w) * tmp1;
-            tmp2 = 2.0 * (tmp2 - tmp1);
+            double tmp1 = mul_(sub_(x, w), sub_(fx, fv));
+            double tmp2 = mul_(sub_(x, v), sub_(fx, fw));
+            double p = sub_(mul_(sub_(x, v), tmp2), mul_(sub_(x, w), tmp1));
+            tmp2 = mul_(2.0, sub_(tmp2, tmp1));
             if (tmp2 > 0.0) p = -p;
             tmp2 = fabs(tmp2);
             const double dx_temp = deltax;
             deltax = rat;
-            if ((p > tmp2 * (a - x)) && (p < tmp2 * (b - x)) && (fabs(p) < fabs(0.5 * tmp2 * dx_temp))) {
-                rat = p * 1.0 / tmp2;
-                const double u = x + rat;
-                if ((u - a) < tol2 || (b - u) < tol2) rat = (xmid - x >= 0) ? tol1 : -tol1;
+            if ((p > mul_(tmp2, sub_(a, x))) && (p < mul_(tmp2, sub_(b, x))) && (fabs(p) < fabs(mul_(mul_(0.5, tmp2), dx_temp)))) {
+                rat = div_(p, tmp2);
+                const double u = add_(x, rat);
+                if (sub_(u, a) < tol2 || sub_(b, u) < tol2) rat = (sub_(xmid, x) >= 0) ? tol1 : -tol1;
             } else {
-                deltax = (x >= xmid) ? a - x : b - x;
-                rat = cg * deltax;
+                deltax = (x >= xmid) ? sub_(a, x) : sub_(b, x);
+                rat = mul_(cg, deltax);
             }
         }
         double u;
-        if (fabs(rat) < tol1) u = (rat >= 0) ? x + tol1 : x - tol1;
-        else u = x + rat;
+        if (fabs(rat) < tol1) u = (rat >= 0) ? add_(x, tol1) : sub_(x, tol1);
+        else u = add_(x, rat);
         const double fu = func(u);
         if (aborted) { aborted_flag = true; return; }
         if (fu > fx) {
@@ -224,8 +256,8 @@ NLML_HD void linesearch(CF& cf, int n, double* p, double* xi, double tol, double
     brent_minimize(lf, tol, aborted_flag, cf.aborted, alpha, fret);
     if (aborted_flag) return;
     for (int i = 0; i < n; ++i) {
-        xi[i] = alpha * xi[i];
-        p[i] = p[i] + xi[i];
+        xi[i] = mul_(alpha, xi[i]);
+        p[i] = add_(p[i], xi[i]);
     }
     fval = fret;
 }
@@ -256,32 +288,32 @@ NLML_HD Result minimize(F& f, int n, double* x, double* direc, double xtol = 1e-
             const double fx2 = fval;
             linesearch(cf, n, x, direc1, xtol * 100, fval, aborted);
             if (aborted) break;
-            if ((fx2 - fval) > delta) {
-                delta = fx2 - fval;
+            if (sub_(fx2, fval) > delta) {
+                delta = sub_(fx2, fval);
                 bigind = i;
             }
         }
         if (aborted) break;
         ++iter;
-        const double bnd = ftol * (fabs(fx) + fabs(fval)) + 1e-20;
-        if (2.0 * (fx - fval) <= bnd) break;
+        const double bnd = add_(mul_(ftol, add_(fabs(fx), fabs(fval))), 1e-20);
+        if (mul_(2.0, sub_(fx, fval)) <= bnd) break;
         if (cf.calls >= maxfun) break;
         if (iter >= maxiter) break;
         if (fx != fx && fval != fval) break;
         // the extrapolated point
         for (int i = 0; i < n; ++i) {
-            direc1[i] = x[i] - x1[i];
+            direc1[i] = sub_(x[i], x1[i]);
             x1[i] = x[i];
-            x2[i] = x[i] + direc1[i];
+            x2[i] = add_(x[i], direc1[i]);
         }
         const double fx2 = cf(x2);
         if (cf.aborted) break;
         if (fx > fx2) {
-            double t = 2.0 * (fx + fx2 - 2.0 * fval);
-            double temp = (fx - fval - delta);
-            t *= temp * temp;
-            temp = fx - fx2;
-            t -= delta * temp * temp;
+            double t = mul_(2.0, sub_(add_(fx, fx2), mul_(2.0, fval)));
+            double temp = sub_(sub_(fx, fval), delta);
+            t = mul_(t, mul_(temp, temp));
+            temp = sub_(fx, fx2);
+            t = sub_(t, mul_(mul_(delta, temp), temp));
             if (t < 0.0) {
                 linesearch(cf, n, x, direc1, xtol * 100, fval, aborted);
                 if (aborted) break;

@@ -1286,6 +1286,27 @@ __global__ void __launch_bounds__(kPowellThreads) tucker_powell_kernel(const __g
     }
 }
 
+// test hook: the cooperative objective alone, at given parameter points of ONE sample (checked bitwise against the host build)
+__global__ void __launch_bounds__(kPowellThreads) tucker_powell_objective_kernel(const __grid_constant__ PowellArgs a, const double* __restrict__ pts,
+                                                                                 int npts, double* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t psm_[];
+    double* e = reinterpret_cast<double*>(psm_);
+    double* racc = e + a.F;
+    double* leafsum = racc + 8 * kPowellMaxLeaves;
+    double* result = leafsum + kPowellMaxLeaves;
+    float* xs = reinterpret_cast<float*>(result + 2);
+    for (int f = threadIdx.x; f < a.F; f += kPowellThreads) xs[f] = __ldg(a.X + f);
+    __syncthreads();
+    PowellCoopObjective obj{a, xs, e, racc, leafsum, result};
+    const int NP = 3 + a.ri;
+    for (int i = 0; i < npts; ++i) {
+        double x[powell::kMaxN];
+        for (int k = 0; k < NP; ++k) x[k] = pts[i * NP + k];
+        const double v = obj(x);
+        if (threadIdx.x == 0) out[i] = v;
+    }
+}
+
 // TD_Trainer.Train for the columns of one factor matrix (TD_Trainer.py:232-351 -> :125-148 Fourier initial guess, :60-93
 // scipy Powell per column): one thread per column, float64, the statements of powell_math.h.
 __global__ void cosine_fit_kernel(const double* __restrict__ U, int n_rows, int n_cols, const double* __restrict__ w_rad,
@@ -1942,9 +1963,21 @@ static void pairwise_plan(int off, int n, std::vector<short>& loff, std::vector<
     prog.push_back(-1);
 }
 
+static int powell_launch(nlml_tucker_plan* pl, const float* X_dev, int64_t N, int64_t ldx, double* P_out_dev, int64_t ldp,
+                         double* fun_out_dev, int32_t* nfev_out_dev, void* stream, const double* pts, int npts, double* vals);
+
 extern "C" int nlml_tucker_powell_f64(nlml_tucker_plan* pl, const float* X_dev, int64_t N, int64_t ldx, double* P_out_dev,
                                       int64_t ldp, double* fun_out_dev, int32_t* nfev_out_dev, void* stream) {
     if (!pl || (N > 0 && (!X_dev || !P_out_dev))) return set_error(NLML_E_INVALID, "null pointer argument");
+    return powell_launch(pl, X_dev, N, ldx, P_out_dev, ldp, fun_out_dev, nfev_out_dev, stream, nullptr, 0, nullptr);
+}
+/* test hook: TD_Tester.objective (float64, the reference's operation order) of ONE sample x at npts parameter points */
+extern "C" int nlml_debug_powell_objective(nlml_tucker_plan* pl, const float* x_dev, const double* pts_dev, int npts, double* vals_dev) {
+    if (!pl || !x_dev || !pts_dev || !vals_dev || npts < 1) return set_error(NLML_E_INVALID, "null pointer argument");
+    return powell_launch(pl, x_dev, 1, pl->F, nullptr, 3 + pl->ri, nullptr, nullptr, nullptr, pts_dev, npts, vals_dev);
+}
+static int powell_launch(nlml_tucker_plan* pl, const float* X_dev, int64_t N, int64_t ldx, double* P_out_dev, int64_t ldp,
+                         double* fun_out_dev, int32_t* nfev_out_dev, void* stream, const double* pts, int npts, double* vals) {
     if (N < 0 || ldx < pl->F || ldp < 3 + pl->ri)
         return set_error(NLML_E_INVALID, "bad sizes: N=%lld ldx=%lld (F=%d) ldp=%lld (need >= %d)", (long long)N, (long long)ldx, pl->F,
                          (long long)ldp, 3 + pl->ri);
@@ -1967,6 +2000,12 @@ extern "C" int nlml_tucker_powell_f64(nlml_tucker_plan* pl, const float* X_dev, 
     std::memcpy(a.rows_p, pl->rows64[1], sizeof(a.rows_p));
     std::memcpy(a.rows_r, pl->rows64[2], sizeof(a.rows_r));
     const size_t smem = sizeof(double) * ((size_t)pl->F + 9 * kPowellMaxLeaves + 2) + sizeof(float) * pl->F + 16;
+    if (pts) {
+        NLML_CUDA(cudaFuncSetAttribute(tucker_powell_objective_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tucker_powell_objective_kernel<<<1, kPowellThreads, smem, (cudaStream_t)stream>>>(a, pts, npts, vals);
+        NLML_CUDA(cudaGetLastError());
+        return 0;
+    }
     NLML_CUDA(cudaFuncSetAttribute(tucker_powell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tucker_powell_kernel<<<(unsigned)N, kPowellThreads, smem, (cudaStream_t)stream>>>(a);
     NLML_CUDA(cudaGetLastError());

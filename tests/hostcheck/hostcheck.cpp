@@ -233,3 +233,12 @@ extern "C" int hostcheck_cosine_fit(const double* U, int n_rows, int n_cols, con
     }
     return 0;
 }
+
+// the exact objective alone, at given points of one sample
+extern "C" int hostcheck_powell_objective(const float* W2, int ri, int ry, int rp, int rr, int F, const double* rows_y, const double* rows_p,
+                                          const double* rows_r, const float* x, const double* pts, int npts, double* vals) {
+    std::vector<double> scratch(F);
+    powell::TuckerObjectiveExact obj{ri, ry, rp, rr, F, W2, x, rows_y, rows_p, rows_r, scratch.data()};
+    for (int i = 0; i < npts; ++i) vals[i] = obj(pts + (size_t)i * (3 + ri));
+    return 0;
+}

@@ -97,11 +97,9 @@ def test_powell_kernel_reproduces_the_reference_on_all_96_goldens(art, rows, X1k
     gap = np.abs(np.degrees(P[:, :3]) - powell_golden["deg"]).max(1)
     print(f"Powell kernel vs reference: {same.mean() * 100:.1f} % identical evaluation counts, {np.mean(gap == 0) * 100:.1f} % "
           f"bit-identical angles, max gap {gap.max():.3e} deg")
-    # the device's float64 cos may differ from the host's in the last bit; the objective rounds the factors to float32,
-    # which hides that except on a rounding boundary
-    assert same.mean() >= 0.95 and np.mean(gap == 0) >= 0.95
-    assert np.quantile(gap, 0.99) < 1e-2
-    assert np.array_equal(fun[same & (gap == 0)], powell_golden["loss"][same & (gap == 0)])
+    # measured on B200: 100 % / 100 % / 0.0 (the device's float64 cos may differ from numpy's in the last bit, but the
+    # objective rounds the factors to float32, which hides that except exactly on a rounding boundary)
+    assert same.all() and np.array_equal(P, powell_golden["p"]) and np.array_equal(fun, powell_golden["loss"])
 
 
 @pytest.mark.gpu
