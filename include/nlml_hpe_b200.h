@@ -94,6 +94,11 @@ int nlml_tucker_solve_host_f32(nlml_tucker_plan* plan, const float* X_host, int6
 int nlml_tucker_powell_f64(nlml_tucker_plan* plan, const float* X_dev, int64_t N, int64_t ldx, double* P_out_dev,
                            int64_t ldp, double* fun_out_dev, int32_t* nfev_out_dev, void* stream);
 
+/* Test hook: phase A of the (5,3,3,3) kernels as the tensor-core GEMM the converged solve uses from 4096 samples on
+ * (3xTF32 tcgen05, raw FP32 X tiles by TMA): q = W2 x, CTA-blocked, Q_out_dev [ceil(N/128)][136][128]
+ * (q[r] of sample s at ((s / 128) * 136 + r) * 128 + s % 128).  Synchronous. */
+int nlml_debug_project_tc(nlml_tucker_plan* plan, const float* X_dev, int64_t N, int64_t ldx, float* Q_out_dev);
+
 /* Test hook: TD_Tester.objective of ONE sample x_dev [F] at npts parameter points pts_dev [npts][3 + r_id] (float64),
  * evaluated by the Powell kernel's cooperative objective -> vals_dev [npts]. */
 int nlml_debug_powell_objective(nlml_tucker_plan* plan, const float* x_dev, const double* pts_dev, int npts, double* vals_dev);

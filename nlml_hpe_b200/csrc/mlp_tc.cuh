@@ -162,6 +162,33 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The MMA warp runs its loop CONVERGED with warp-uniform values and lets the elected lane issue (elect.sync inside the asm
+// block): descriptor arithmetic then stays in the uniform datapath.  A plain `if (lane == 0)` issue wraps every
+// tcgen05.mma in a register->uniform-register broadcast loop (~100 cycles per MMA), which made the short-K / narrow layers
+// issue-bound (their MMAs execute in 32-64 cycles).
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast_elect(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -247,7 +274,7 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
     float4* neck_whs = reinterpret_cast<float4*>(neck_b5s + 12);          // [3][128] (w0, w1, w2, bias)
     float* neck_xch = reinterpret_cast<float*>(neck_whs + 3 * kNeckHeadW);   // [2 halves][9][BM]
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int num_kb = a.Kp / BK;
     const int tiles_n = a.out / BN;
     const long long tiles_m = ((a.N + BM - 1) / BM + CL - 1) / CL;   // M-tile groups: CL consecutive M-tiles per cluster
@@ -318,7 +345,7 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
         // chains (measured: 3.6e-3 deg at the output when all K/16*3 steps of a layer went into one TMEM
         // accumulator).  So one TMEM accumulator only ever sums ONE k-block (4 k-steps x 3 passes = 12 MMAs);
         // the epilogue warps promote each partial tile into FP32 registers with round-to-nearest adds.
-        if (lane == 0) {
+        {   // the whole warp, converged; the elected lane issues (see umma_f16_elect)
             constexpr uint32_t idesc = make_idesc_f16(BM, BN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -329,22 +356,22 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                    const uint32_t st = smem_u32(stage_base + (size_t)stage * C::STAGE_BYTES);
+                    const uint32_t st = smem_u32(stage_base) + (uint32_t)stage * (uint32_t)C::STAGE_BYTES;
                     const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + C::A_BYTES);
                     const uint64_t w_hi = make_smem_desc(st + 2 * C::A_BYTES), w_lo = make_smem_desc(st + 2 * C::A_BYTES + C::W_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // 32 B per k-step inside the swizzle row
-                        umma_f16(d_tmem, a_lo + adv, w_hi + adv, idesc, !(g_first && k == 0));   // small terms first
-                        umma_f16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
-                        umma_f16(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+                        umma_f16_elect(d_tmem, a_lo + adv, w_hi + adv, idesc, !(g_first && k == 0));   // small terms first
+                        umma_f16_elect(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                        umma_f16_elect(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
                     }
                     // operand stage free once these MMAs have read it (told to every CTA that writes into it)
-                    if (CL == 1) umma_commit(&empty[stage]);
-                    else umma_commit_mcast(&empty[stage], kMask);
+                    if (CL == 1) umma_commit_elect(&empty[stage]);
+                    else umma_commit_mcast_elect(&empty[stage], kMask);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     if (g_last) {
-                        umma_commit(&tfull[acc]);     // partial tile ready for promotion
+                        umma_commit_elect(&tfull[acc]);     // partial tile ready for promotion
                         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                     }
                 }
@@ -561,6 +588,22 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, u
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_f16_2sm_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_elect(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
@@ -586,7 +629,7 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* bias_all = reinterpret_cast<float*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256);   // [warp][HALF], private per epilogue warp
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const uint32_t crank = cluster_ctarank();
     const bool leader = crank == 0;
     const int num_kb = a.Kp / BK;
@@ -636,7 +679,7 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
     } else if (warp == 1) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));   // register hand-over, see kThreads
         // ===== MMA issuer (leader CTA only; one instruction drives both SMs' tensor cores) =====
-        if (leader && lane == 0) {
+        if (leader) {   // the whole warp of the leader CTA, converged; the elected lane issues
             constexpr uint32_t idesc = make_idesc_f16(2 * BM, BN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -647,20 +690,20 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                    const uint32_t st = smem_u32(stage_base + (size_t)stage * C::STAGE_BYTES);
+                    const uint32_t st = smem_u32(stage_base) + (uint32_t)stage * (uint32_t)C::STAGE_BYTES;
                     const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + C::A_BYTES);
                     const uint64_t w_hi = make_smem_desc(st + 2 * C::A_BYTES), w_lo = make_smem_desc(st + 2 * C::A_BYTES + C::W_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
-                        umma_f16_2sm(d_tmem, a_lo + adv, w_hi + adv, idesc, !(g_first && k == 0));
-                        umma_f16_2sm(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
-                        umma_f16_2sm(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
+                        umma_f16_2sm_elect(d_tmem, a_lo + adv, w_hi + adv, idesc, !(g_first && k == 0));
+                        umma_f16_2sm_elect(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                        umma_f16_2sm_elect(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
                     }
-                    umma_commit_2sm(&empty[stage], 3);   // both CTAs' producers may refill the stage
+                    umma_commit_2sm_elect(&empty[stage], 3);   // both CTAs' producers may refill the stage
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     if (g_last) {
-                        umma_commit_2sm(&tfull[acc], 3);     // both CTAs' epilogue warps may promote their half
+                        umma_commit_2sm_elect(&tfull[acc], 3);     // both CTAs' epilogue warps may promote their half
                         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                     }
                 }

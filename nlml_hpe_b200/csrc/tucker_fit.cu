@@ -15,6 +15,8 @@
 //                          latency of the 3000-step chain matters more than throughput.
 //   tucker_fit_cta_kernel  CTA-per-sample, ranks at run time (enlarged cores, BASELINE.json config 5).
 // No kernel touches global memory between iterations.
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -37,6 +39,7 @@ struct TuckerArgs {
     const float* S;   // [nBCD][NAP]   thread-per-sample layout
     const float* St;  // [nA][nBCDp]   CTA-per-sample layout
     const uint8_t* tc_ops;   // tensor-core kernel: shared-memory image of the two B operands (S in both GEMM views, hi/lo)
+    const float* Qpre;       // q = W2 x precomputed by tucker_project_tc_kernel, CTA-blocked [N/128][RPAD][128]; null: phase A runs here
     float* P;
     long long ldp;
     int F, T;
@@ -230,8 +233,15 @@ __global__ void __launch_bounds__(THREADS, MINB) tucker_fit_tps_kernel(const __g
 
     // ---- phase A: q[r] = sum_f W2[r][f] * x[f], one pass per sample owned by this thread ----
     // (the tiles alias the q buffer of the pass in flight only: pass n stages its tiles in q slab n)
+    if constexpr (THREADS == 128 && NS == 1 && !QTMEM) {
+        if (a.Qpre) {   // projected already by the tensor-core GEMM (tucker_project_tc_kernel): coalesced copy of this CTA's slab
+            const float* slab = a.Qpre + (size_t)blockIdx.x * C::RPAD * 128;
+            for (int r = 0; r < C::R; ++r) q_s[r * THREADS + tid] = __ldg(slab + r * 128 + tid);
+        }
+    }
+    const int n_passes = (THREADS == 128 && NS == 1 && !QTMEM && a.Qpre) ? 0 : NS;
 #pragma unroll 1
-    for (int n = 0; n < NS; ++n) {
+    for (int n = 0; n < n_passes; ++n) {
     float* qn_s = QTMEM ? scr_s : q_s + n * (C::R * THREADS);   // TMEM variant: tiles live in the scratch buffer
     xs = qn_s;
     ws = qn_s + C::FC * C::XSTR;
@@ -289,6 +299,7 @@ __global__ void __launch_bounds__(THREADS, MINB) tucker_fit_tps_kernel(const __g
     }
     __syncthreads();  // S_s complete, tiles dead
     }
+    if (n_passes == 0) __syncthreads();   // S_s and the copied q slab complete
 
     if constexpr (SOLVE) {
         // ---- phase B': converged fit, data-dependent number of Newton evaluations per sample ----
@@ -1326,6 +1337,197 @@ __global__ void cosine_fit_kernel(const double* __restrict__ U, int n_rows, int 
     if (nfev) nfev[j] = res.nfev;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Phase A on the tensor cores: q = W2 x for a whole batch as a 3xTF32 tcgen05 GEMM  [N x F] x [F x 136]  (SURVEY.md
+// section 7: at 67 flop/B this projection needs tensor cores to outrun HBM; on CUDA cores it was 37 % of the converged
+// solve).  Persistent, one CTA per SM, 128 samples per tile:
+//   warp 0       TMA producer: the raw FP32 tile of X (2-D tensor map, 128 rows x 32 features, 128-byte swizzle, rows / columns
+//                beyond the batch / F zero-filled by the TMA unit) and the k-block's W2 tile image (1-D bulk copy)
+//   warp 1       MMA issuer (converged warp, elected lane): per k-block 4 k-steps x (lo*hi, hi*lo, hi*hi), FP32 TMEM accumulator
+//   warps 4-7    converters: split the landed X tile in place into hi = tf32(x) and lo = x - hi (the planes the MMAs read)
+//   warps 8-11   promotion + epilogue: tcgen05.ld every group's partial 128 x 136 tile (double-buffered in TMEM), add it into
+//                FP32 registers with round-to-nearest, store the finished tile as the CTA-blocked slab [136][128] the fit /
+//                solve kernels copy into shared memory with coalesced loads
+// ---------------------------------------------------------------------------------------------
+struct ProjCfg {
+    static constexpr int BM = 128, BK = 32, NQ = 144;           // samples per tile, features per k-block, q rows padded to 16
+    static constexpr int STAGES = 3;
+    static constexpr int GROUP = 1;                              // k-blocks summed in one TMEM accumulator (12 MMAs) before the partial
+                                                                 // tile is promoted into FP32 registers: the tensor core's accumulate
+                                                                 // truncates -- a 528-MMA chain left q 3e-5 low (0.1 degrees after the
+                                                                 // solve), 48-MMA chains 9e-7; per k-block it is FP32-grade
+    static constexpr int X_BYTES = BM * BK * 4;                  // one plane of the X tile (128-byte rows, swizzled)
+    static constexpr int W_BYTES = 2 * NQ * BK * 4;              // hi + lo planes of the W2 tile (UMMA no-swizzle image)
+    static constexpr int STAGE_BYTES = 2 * X_BYTES + W_BYTES;    // X hi (lands raw) + X lo + W
+    static constexpr int OFF_BAR = STAGES * STAGE_BYTES;
+    static constexpr size_t SMEM_BYTES = 1024 + OFF_BAR + 256;
+    static constexpr int THREADS = 384;
+};
+struct ProjArgs {
+    long long N;
+    int F, RPAD, num_kb;
+    const uint8_t* wtiles;   // [num_kb][W_BYTES]
+    float* Q;                // [tiles][RPAD][128]
+};
+__device__ __forceinline__ uint64_t proj_desc_sw128(uint32_t smem_addr) {   // K-major, 128-byte swizzle, 8-row groups 1024 B apart
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__global__ void __launch_bounds__(ProjCfg::THREADS, 1) tucker_project_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ ProjArgs a) {
+    using C = ProjCfg;
+    extern __shared__ uint8_t proj_raw[];
+    uint8_t* sm = proj_raw + ((1024u - (ttc::smem_u32(proj_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + C::OFF_BAR);
+    uint64_t* full = bars;                 // [STAGES] X tile and W tile landed
+    uint64_t* conv = bars + C::STAGES;     // [STAGES] hi / lo planes written
+    uint64_t* empty = conv + C::STAGES;    // [STAGES] consumed by the MMAs
+    uint64_t* tfull = empty + C::STAGES;   // [2] accumulator complete
+    uint64_t* tempty = tfull + 2;          // [2] accumulator stored
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+    const long long tiles = (a.N + C::BM - 1) / C::BM;
+    if (tid == 0) {
+        for (int i = 0; i < C::STAGES; ++i) { ttc::mbar_init(&full[i], 1); ttc::mbar_init(&conv[i], 4); ttc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { ttc::mbar_init(&tfull[i], 1); ttc::mbar_init(&tempty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&xmap)) : "memory");
+    }
+    if (warp == 1) tmem_alloc_cols(tmem_slot, 512);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(40));
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (long long t = blockIdx.x; t < tiles; t += gridDim.x)
+                for (int kb = 0; kb < a.num_kb; ++kb) {
+                    ttc::mbar_wait(&empty[s], ph ^ 1u);
+                    uint8_t* st = sm + (size_t)s * C::STAGE_BYTES;
+                    tgen::mbar_expect_tx(&full[s], (uint32_t)(C::X_BYTES + C::W_BYTES));
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                 ::"r"(ttc::smem_u32(st)), "l"(reinterpret_cast<uint64_t>(&xmap)), "r"(kb * C::BK), "r"((int)(t * C::BM)),
+                                   "r"(ttc::smem_u32(&full[s])) : "memory");
+                    tgen::bulk_load(st + 2 * C::X_BYTES, a.wtiles + (size_t)kb * C::W_BYTES, (uint32_t)C::W_BYTES, &full[s]);
+                    if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+                }
+        }
+    } else if (warp == 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(40));
+        const uint32_t idesc = ttc::make_idesc_tf32(128, C::NQ);
+        int s = 0; uint32_t ph = 0; int acc = 0; uint32_t aph = 0;
+        for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+            for (int kb = 0; kb < a.num_kb; ++kb) {
+                const bool g_first = kb % C::GROUP == 0, g_last = (kb % C::GROUP == C::GROUP - 1) || kb == a.num_kb - 1;
+                if (g_first) ttc::mbar_wait(&tempty[acc], aph ^ 1u);
+                ttc::mbar_wait(&conv[s], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = ttc::smem_u32(sm) + (uint32_t)s * (uint32_t)C::STAGE_BYTES;
+                const uint64_t xh = proj_desc_sw128(st), xl = proj_desc_sw128(st + C::X_BYTES);
+                uint64_t wh = ttc::make_desc_noswz(st + 2 * C::X_BYTES, C::BK, 0), wl = ttc::make_desc_noswz(st + 2 * C::X_BYTES + C::W_BYTES / 2, C::BK, 0);
+#pragma unroll
+                for (int k = 0; k < C::BK / 8; ++k) {
+                    ttc::mma3_ss(tmem + acc * C::NQ, xh + 2 * k, xl + 2 * k, wh, wl, idesc, (!g_first || k > 0) ? 1u : 0u);   // 8 floats = 32 B per k-step
+                    wh += 16; wl += 16;
+                }
+                ttc::umma_commit_elect(&empty[s]);
+                if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+                if (g_last) {
+                    ttc::umma_commit_elect(&tfull[acc]);
+                    if (++acc == 2) { acc = 0; aph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(40));   // idle warps of group 0
+    } else if (warp < 8) {
+        // converters: thread = row of the tile; a row is 128 B = 8 chunks of 16 B, chunk c of row r at position c ^ (r % 8)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(64));
+        const int r = tid - 128;
+        int s = 0; uint32_t ph = 0;
+        for (long long t = blockIdx.x; t < tiles; t += gridDim.x)
+            for (int kb = 0; kb < a.num_kb; ++kb) {
+                ttc::mbar_wait(&full[s], ph);
+                uint8_t* xh = sm + (size_t)s * C::STAGE_BYTES + r * 128;
+                uint8_t* xl = xh + C::X_BYTES;
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    // the swizzle permutes whole 16-byte chunks, so position-wise processing is enough; the threads of 8
+                    // consecutive rows take different chunk positions at a time (rows are 128 B apart: all on the same banks otherwise)
+                    const int c = cc ^ (r & 7);
+                    float4 v = *reinterpret_cast<float4*>(xh + 16 * c);
+                    float4 h, l;
+                    ttc::split_tf32_bits(v.x, h.x, l.x); ttc::split_tf32_bits(v.y, h.y, l.y);
+                    ttc::split_tf32_bits(v.z, h.z, l.z); ttc::split_tf32_bits(v.w, h.w, l.w);
+                    *reinterpret_cast<float4*>(xh + 16 * c) = h;
+                    *reinterpret_cast<float4*>(xl + 16 * c) = l;
+                }
+                ttc::fence_async_smem();
+                __syncwarp();
+                if (lane == 0) tgen::mbar_arrive(&conv[s]);
+                if (++s == C::STAGES) { s = 0; ph ^= 1u; }
+            }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(232));
+        const int row = tid - 256;
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        int acc = 0; uint32_t aph = 0;
+        for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+            float sum[C::NQ];
+#pragma unroll
+            for (int j = 0; j < C::NQ; ++j) sum[j] = 0.f;
+            for (int kb = 0; kb < a.num_kb; kb += C::GROUP) {
+                ttc::mbar_wait(&tfull[acc], aph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int c0 = 0; c0 < C::NQ; c0 += 48) {
+                    uint32_t v[48];
+#pragma unroll
+                    for (int x = 0; x < 6; ++x) tgen::tmem_ld8(lane_addr + acc * C::NQ + c0 + 8 * x, v + 8 * x);
+                    tmem_load_wait();
+#pragma unroll
+                    for (int e = 0; e < 48; ++e) sum[c0 + e] += __uint_as_float(v[e]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) tgen::mbar_arrive(&tempty[acc]);
+                if (++acc == 2) { acc = 0; aph ^= 1u; }
+            }
+            float* slab = a.Q + (size_t)t * a.RPAD * 128 + row;
+#pragma unroll
+            for (int j = 0; j < C::NQ; ++j)
+                if (j < a.RPAD) slab[(size_t)j * 128] = sum[j];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) tmem_free_cols(tmem, 512);
+}
+
+// W2 tile images for the projection GEMM: k-block kb = rows r < NQ (zero beyond R), features kb*32 .. +31 (zero beyond F),
+// hi plane then lo plane, UMMA no-swizzle K-major layout
+__global__ void build_proj_tiles_kernel(const float* __restrict__ W2, int R, int F, int num_kb, uint8_t* __restrict__ img) {
+    using C = ProjCfg;
+    const long long total = (long long)num_kb * C::NQ * C::BK;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int kb = (int)(idx / (C::NQ * C::BK)), e = (int)(idx % (C::NQ * C::BK));
+        const int r = e / C::BK, k = e % C::BK, f = kb * C::BK + k;
+        const float v = (r < R && f < F) ? W2[(long long)r * F + f] : 0.f;
+        float hi, lo;
+        ttc::split_tf32(v, hi, lo);
+        uint8_t* base = img + (size_t)kb * C::W_BYTES;
+        *reinterpret_cast<float*>(base + ttc::op_offset(r, k, C::BK)) = hi;
+        *reinterpret_cast<float*>(base + C::W_BYTES / 2 + ttc::op_offset(r, k, C::BK)) = lo;
+    }
+}
+
 // register-only FFMA loop: measures the sustained FP32 FMA rate used as a roofline denominator
 __global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
@@ -1429,6 +1631,10 @@ struct nlml_tucker_plan {
     bool cta_ok = false;      // CTA-per-sample kernel usable (its working set fits shared memory)
     bool gen_ok = false;      // run-time-rank tensor-core kernel usable (tucker_gen.cuh)
     tgen::GenCfg gen{};
+    uint8_t* proj_tiles = nullptr;          // (5,3,3,3): W2 tile images of the tensor-core projection GEMM
+    float* q_pre = nullptr;                 // its output for the batch in flight (CTA-blocked slabs), grown on demand
+    int64_t q_pre_rows = 0;
+    cudaEvent_t q_pre_done = nullptr;
     double rows64[3][4 * kMaxModeRank] = {};   // the cosine rows in float64, as the reference's Powell objective uses them
     uint8_t* tc_ops = nullptr;              // (5,3,3,3) tensor-core kernel: image of its two constant B operands
     uint8_t* gen_tiles = nullptr;           // tile images of S (hi/lo, UMMA layout), streamed by TMA
@@ -1653,6 +1859,51 @@ int launch_fit(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int
     return 0;
 }
 
+// q = W2 x for the batch through tucker_project_tc_kernel.  *Qout stays null (the consumer runs its own phase A) when X
+// cannot be described by a tensor map (row pitch or base not 16-byte aligned) or the batch is small.
+typedef CUresult (*EncodeTiledFnT)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int project_tc(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, cudaStream_t st, const float** Qout) {
+    *Qout = nullptr;
+    if (!pl->fast || !pl->proj_tiles || N < 4096 || (ldx % 4) != 0 || (reinterpret_cast<uintptr_t>(X) & 15) != 0) return 0;
+    static EncodeTiledFnT encode = nullptr;
+    if (!encode) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return 0;
+        encode = reinterpret_cast<EncodeTiledFnT>(p);
+    }
+    const int64_t tiles = ceil_div(N, ProjCfg::BM);
+    if (pl->q_pre_rows < tiles * ProjCfg::BM) {
+        if (pl->q_pre_rows) NLML_CUDA(cudaDeviceSynchronize());
+        pl->q_pre_rows = 0;
+        cudaFree(pl->q_pre);
+        pl->q_pre = nullptr;
+        NLML_CUDA(cudaMalloc(&pl->q_pre, sizeof(float) * (size_t)tiles * ProjCfg::BM * 136));
+        pl->q_pre_rows = tiles * ProjCfg::BM;
+    }
+    if (!pl->q_pre_done) NLML_CUDA(cudaEventCreateWithFlags(&pl->q_pre_done, cudaEventDisableTiming));
+    else NLML_CUDA(cudaStreamWaitEvent(st, pl->q_pre_done, 0));   // one q buffer per plan: calls on other streams wait for its last reader
+    CUtensorMap xmap;
+    cuuint64_t dims[2] = {(cuuint64_t)pl->F, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)ldx * 4};
+    cuuint32_t box[2] = {(cuuint32_t)ProjCfg::BK, (cuuint32_t)ProjCfg::BM};
+    cuuint32_t estr[2] = {1, 1};
+    if (encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return 0;
+    ProjArgs pa{};
+    pa.N = N; pa.F = pl->F; pa.RPAD = 136; pa.num_kb = (pl->F + ProjCfg::BK - 1) / ProjCfg::BK;
+    pa.wtiles = pl->proj_tiles; pa.Q = pl->q_pre;
+    const unsigned grid = (unsigned)std::min<int64_t>(tiles, pl->num_sms);
+    tucker_project_tc_kernel<<<grid, ProjCfg::THREADS, ProjCfg::SMEM_BYTES, st>>>(xmap, pa);
+    NLML_CUDA(cudaGetLastError());
+    pl->launches += 1;
+    *Qout = pl->q_pre;
+    return 0;
+}
+
 // converged fit: thread-per-sample kernel, phase B' = tucker_lm_solve
 int launch_solve(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int max_evals, float* P, int64_t ldp,
                  int* evals, cudaStream_t st) {
@@ -1668,9 +1919,11 @@ int launch_solve(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, i
     a.lm = lm_default_options();
     if (max_evals > 0) a.lm.max_evals = max_evals;
     a.evals = evals;
+    if (int rc = project_tc(pl, X, N, ldx, st, &a.Qpre)) return rc;   // phase A as a tensor-core GEMM when the layout allows TMA
     auto kern = tucker_fit_tps_kernel<5, 3, 3, 3, kTpsThreads, 1, kSolveMinBlocks, false, true>;
     kern<<<(unsigned)ceil_div(N, TpsDefault::SAMPLES), kTpsThreads, TpsDefault::SMEM_BYTES, st>>>(a);
     NLML_CUDA(cudaGetLastError());
+    if (a.Qpre) NLML_CUDA(cudaEventRecord(pl->q_pre_done, st));
     pl->launches += 1;
     return 0;
 }
@@ -1838,6 +2091,15 @@ extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, i
         NLML_CUDA(cudaDeviceSynchronize());
         pl->launches += 1;
         a.tc_ops = pl->tc_ops;
+        {
+            const int num_kb = (F + ProjCfg::BK - 1) / ProjCfg::BK;
+            NLML_CUDA(cudaMalloc(&pl->proj_tiles, (size_t)num_kb * ProjCfg::W_BYTES));
+            build_proj_tiles_kernel<<<64, 256>>>(pl->W2, pl->R, F, num_kb, pl->proj_tiles);
+            NLML_CUDA(cudaGetLastError());
+            NLML_CUDA(cudaDeviceSynchronize());
+            NLML_CUDA(cudaFuncSetAttribute(tucker_project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ProjCfg::SMEM_BYTES));
+            pl->launches += 1;
+        }
         if (wps_smem_bytes(F) > 200 * 1024) pl->fast = false;
         else
             NLML_CUDA(cudaFuncSetAttribute(tucker_fit_wps_kernel<5, 3, 3, 3, kWpsWarps>,
@@ -1887,6 +2149,9 @@ extern "C" void nlml_tucker_plan_destroy(nlml_tucker_plan* pl) {
     cudaFree(pl->St);
     cudaFree(pl->gen_tiles);
     cudaFree(pl->tc_ops);
+    cudaFree(pl->proj_tiles);
+    cudaFree(pl->q_pre);
+    if (pl->q_pre_done) cudaEventDestroy(pl->q_pre_done);
     for (int i = 0; i < 3; ++i) cudaFree(pl->q_ws[i]);
     if (pl->q_done) cudaEventDestroy(pl->q_done);
     delete pl;
@@ -1970,6 +2235,17 @@ extern "C" int nlml_tucker_powell_f64(nlml_tucker_plan* pl, const float* X_dev, 
                                       int64_t ldp, double* fun_out_dev, int32_t* nfev_out_dev, void* stream) {
     if (!pl || (N > 0 && (!X_dev || !P_out_dev))) return set_error(NLML_E_INVALID, "null pointer argument");
     return powell_launch(pl, X_dev, N, ldx, P_out_dev, ldp, fun_out_dev, nfev_out_dev, stream, nullptr, 0, nullptr);
+}
+/* test hook: q = W2 x of the tensor-core projection GEMM for N >= 4096 samples, CTA-blocked: Q_out_dev [ceil(N/128)][136][128] */
+extern "C" int nlml_debug_project_tc(nlml_tucker_plan* pl, const float* X_dev, int64_t N, int64_t ldx, float* Q_out_dev) {
+    if (!pl || !X_dev || !Q_out_dev) return set_error(NLML_E_INVALID, "null pointer argument");
+    DeviceGuard guard(pl->device);
+    const float* q = nullptr;
+    if (int rc = project_tc(pl, X_dev, N, ldx, nullptr, &q)) return rc;
+    if (!q) return set_error(NLML_E_UNSUPPORTED, "the tensor-core projection needs ranks (5,3,3,3), N >= 4096 and 16-byte aligned rows");
+    NLML_CUDA(cudaEventRecord(pl->q_pre_done, nullptr));
+    NLML_CUDA(cudaMemcpy(Q_out_dev, q, sizeof(float) * (size_t)ceil_div(N, 128) * 136 * 128, cudaMemcpyDeviceToDevice));
+    return 0;
 }
 /* test hook: TD_Tester.objective (float64, the reference's operation order) of ONE sample x at npts parameter points */
 extern "C" int nlml_debug_powell_objective(nlml_tucker_plan* pl, const float* x_dev, const double* pts_dev, int npts, double* vals_dev) {

@@ -325,6 +325,35 @@ def test_solve_vs_reference_powell_96(fitter, art, rows, X1k, powell_golden):
     assert q50 < 0.6 and q90 < 4.0 and qmax < 12.0
 
 
+def test_tensor_core_projection_is_fp32_grade(fitter, art, rows, X1k, cuda_lib):
+    """Phase A as the 3xTF32 tcgen05 GEMM (the converged solve's path from 4096 samples on): q = W2 x against float64,
+    ragged batch (rows beyond N zero-filled by the TMA unit), and the solve on top of it against the in-kernel phase A."""
+    import ctypes
+    from nlml_hpe_b200 import _lib
+    n = 4096 + 77
+    X = np.concatenate([X1k] * 5)[:n]
+    X[5] = 0.0
+    X[9] *= 37.0
+    xg = _gpu(X)
+    Q = torch.zeros(((n + 127) // 128, 136, 128), dtype=torch.float32, device="cuda")
+    _lib.check(cuda_lib.nlml_debug_project_tc(fitter._h, xg.data_ptr(), n, 1404, Q.data_ptr()))
+    q = Q.cpu().numpy().transpose(0, 2, 1).reshape(-1, 136)[:n, :135]
+    ref = X.astype(np.float64) @ art["W"].reshape(135, -1).astype(np.float64).T
+    scale = np.abs(X).astype(np.float64) @ np.abs(art["W"].reshape(135, -1)).astype(np.float64).T + 1e-30   # sum |w x|: the FP32 error scale
+    err = (np.abs(q - ref) / scale).max()
+    print(f"tensor-core projection: max |q - q64| / sum|w x| = {err:.2e}")
+    assert err < 6e-7
+    assert np.abs(Q.cpu().numpy().transpose(0, 2, 1).reshape(-1, 136)[n:]).max() == 0.0      # rows beyond the batch
+    # the converged solve with either phase A: same optimum within the solver's FP32 floor
+    a = fitter.solve(xg[:3000]).cpu().numpy()
+    b = fitter.solve(xg)[:3000].cpu().numpy()
+    d = np.abs(a[:, :3] - b[:, :3]).max(1) * DEG
+    assert np.median(d) < 1e-3 and np.quantile(d, 0.99) < 2e-2 and d.max() < 0.1
+    ref64, _, _ = tucker_oracle.lm_fit(art["W"], X[:512], *rows)
+    d64 = np.abs(b[:512, :3] - ref64[:, :3]).max(1) * DEG
+    assert np.median(d64) < 1e-3 and np.quantile(d64, 0.95) < TOL_DEG and d64.max() < 5e-2
+
+
 def test_solve_edges_and_host_path(fitter, art, rows, X1k, tucker_golden):
     assert fitter.solve(_gpu(X1k[:0])).shape == (0, 8)
     one = fitter.solve(_gpu(X1k[:1])).cpu().numpy()
