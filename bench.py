@@ -43,6 +43,9 @@ TUCKER_BYTES_PER_POSE = F * 4 + 8 * 4
 # DRAM traffic of tucker_fit_tc_kernel per sample, from the committed `ncu --set full` capture (profiles/r01_tucker_tc_ncu.txt:
 # dram__bytes_read 218.43 MB + dram__bytes_write 5.36 MB for a 37 888-sample launch); scaled to the bench launch
 TUCKER_TC_NCU_DRAM_BYTES_PER_POSE = (218.431232e6 + 5.357056e6) / 37888
+# DRAM traffic of the Encoder+heads chain per sample: ncu dram__bytes_read.sum + dram__bytes_write.sum over the nine launches of
+# one 151 552-sample chunk (profiles/r02_mlp_launches.txt: 3915.8 MB read + 2593.0 MB written)
+MLP_NCU_DRAM_BYTES_PER_POSE = (3915.81312e6 + 2593.049344e6) / 151552
 MLP_FLOP_PER_POSE = 4_714_240
 MLP_BYTES_PER_POSE = F * 4 + 3 * 4
 
@@ -663,7 +666,10 @@ def run_b200(args):
                                    "note": "nlml_mlp_forward_landmarks_f32: float64 IPD normalisation fused into the operand split"},
             "roofline": {"bound": "tensor", "achieved": per_gpu_m * MLP_FLOP_PER_POSE / 1e12, "peak": peaks["bf16_tflops_sustained"],
                          "unit": "TFLOP/s", "frac": per_gpu_m * MLP_FLOP_PER_POSE / 1e12 / peaks["bf16_tflops_sustained"],
-                         "traffic": None, "peak_source": peaks["source"], "mma_passes": 3,
+                         "traffic": MLP_NCU_DRAM_BYTES_PER_POSE * n, "peak_source": peaks["source"], "mma_passes": 3,
+                         "traffic_note": "bytes per 1M-sample forward = ncu dram__bytes_read+write summed over the nine launches of one 151 552-sample "
+                                         f"chunk (profiles/r02_mlp_launches.txt): {MLP_NCU_DRAM_BYTES_PER_POSE:.0f} B/sample against {MLP_BYTES_PER_POSE} "
+                                         "algorithmic -- the FP16 hi/lo activation planes of every layer round-trip HBM (see DESIGN.md section 4)",
                          "issued_frac": 3 * per_gpu_m * MLP_FLOP_PER_POSE / 1e12 / peaks["bf16_tflops_sustained"],
                          "note": "algorithmic 4.714 MFLOP/pose against the sustained bf16 tensor peak; every MAC is three "
                                  "FP16 MMAs (hi/lo operand split needed for the 1e-3 deg budget), issued_frac counts them"},
