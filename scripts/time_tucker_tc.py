@@ -2,8 +2,8 @@
 
 Build the instrumented library and run on the GPU box:
   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -DNLML_TC_TIMING \
-       -o nlml_hpe_b200/libnlml_timing.so nlml_hpe_b200/csrc/tucker_fit.cu nlml_hpe_b200/csrc/mlp_forward.cu
-  NLML_HPE_LIB=nlml_hpe_b200/libnlml_timing.so python scripts/time_tucker_tc.py
+       -o build/dev/libnlml_timing.so nlml_hpe_b200/csrc/tucker_fit.cu nlml_hpe_b200/csrc/mlp_forward.cu
+  NLML_HPE_LIB=build/dev/libnlml_timing.so python scripts/time_tucker_tc.py
 Rows 0..7 of every CTA's output then hold the average cycles per iteration of lane 0 of warps 0..7 (warps 0-3 angle
 role, 4-7 identity role; warp w runs on SM sub-partition w % 4) in the phases marked NLML_TSTAMP(i) in tucker_fit.cu.
 """
