@@ -191,7 +191,8 @@ int nlml_measure_tf32_tflops(int device, double* tflops_out);
  * the tensor-core Tucker iteration.  K in 8..64 (multiple of 8), N in 16..256 (multiple of 16).  Synchronous. */
 int nlml_debug_tf32_gemm(const float* A_dev, const float* B_dev, int K, int N, float* D_dev);
 /* mode 0: as above.  mode 1: the B tile is stored as the K-major image of its transpose and read as an MN-major operand
- * (the form that lets one shared-memory copy of a folded-Gram tile serve both GEMMs of the run-time-rank kernel). */
+ * (the form that lets one shared-memory copy of a folded-Gram tile serve both GEMMs of the run-time-rank kernel).
+ * mode 2 / 3: the FP16 hi/lo variant (kind::f16, K multiple of 16) with the A operand in shared / tensor memory. */
 int nlml_debug_tf32_gemm_mode(const float* A_dev, const float* B_dev, int K, int N, float* D_dev, int mode);
 
 #ifdef __cplusplus

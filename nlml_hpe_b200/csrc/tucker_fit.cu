@@ -39,6 +39,8 @@ struct TuckerArgs {
     const float* S;   // [nBCD][NAP]   thread-per-sample layout
     const float* St;  // [nA][nBCDp]   CTA-per-sample layout
     const uint8_t* tc_ops;   // tensor-core kernel: shared-memory image of the two B operands (S in both GEMM views, hi/lo)
+    int s_exp;               // tensor-core kernel: its S operand image holds S * 2^s_exp
+    int pr_exp;              // ... and the PP (x) RR operand is written times 2^pr_exp (from the bound (|a|+|d|)^4 of the pitch / roll rows)
     const float* Qpre;       // q = W2 x precomputed by tucker_project_tc_kernel, CTA-blocked [N/128][RPAD][128]; null: phase A runs here
     float* P;
     long long ldp;
@@ -783,11 +785,15 @@ struct TcFitCfg {
     static constexpr int RI = 5, RY = 3, RP = 3, RR = 3, R = 135, RPAD = 136, NP = 8;
     static constexpr int nA = 15, nB = 6, nC = 6, nD = 6, nBCD = 216;
     static constexpr int THREADS = 128;               // samples per CTA (= TMEM lanes); the CTA has 2 threads per sample
-    static constexpr int K1 = 16, N1 = 224;           // T GEMM: K = A (15 -> 16), N = bcd (216 -> 224)
-    static constexpr int KV = 40, NV = 96;            // V GEMM: K = (c,D) (36 -> 40), N = (A,b) (90 -> 96)
-    static constexpr int B1_BYTES = ttc::op_bytes(N1, K1);    // 14336 per plane
-    static constexpr int BV_BYTES = ttc::op_bytes(NV, KV);    // 15360 per plane
-    static constexpr int AV_BYTES = ttc::op_bytes(128, KV);   // 20480 per plane
+    // Operands are FP16 hi/lo planes (kind::f16, K = 16 per MMA): 12 MMAs per iteration instead of the 21 of a 3xTF32 split at
+    // the same cycle cost per instruction -- the V-issuing warp, which blocks while the MMA queue drains, is the iteration's
+    // critical path -- with the same 22 operand bits.  Ranges: S carries a per-plan power-of-two scale (s_exp), UU a
+    // per-sample, per-iteration one (it grows from 0), PP (x) RR a fixed 2^kPrExp; the scales come off in the read-back.
+    static constexpr int K1 = 16, N1 = 224;           // T GEMM: K = A (15 -> 16: one k-step), N = bcd (216 -> 224)
+    static constexpr int KV = 48, NV = 96;            // V GEMM: K = (c,D) (36 -> 48: three k-steps), N = (A,b) (90 -> 96)
+    static constexpr int B1_BYTES = ttc::op16_bytes(N1, K1);    // 7168 per plane
+    static constexpr int BV_BYTES = ttc::op16_bytes(NV, KV);    // 9216 per plane
+    static constexpr int AV_BYTES = ttc::op16_bytes(128, KV);   // 12288 per plane
     static constexpr int OFF_B1 = 0;                                   // hi, lo
     static constexpr int OFF_BV = OFF_B1 + 2 * B1_BYTES;               // hi, lo
     static constexpr int OFF_AV = OFF_BV + 2 * BV_BYTES;               // hi, lo   (the T GEMM's A operand lives in tensor memory)
@@ -801,42 +807,43 @@ struct TcFitCfg {
     static constexpr int NGX = 8 + 15;                                 // 8 gradient parts + role 1's partial GR, GP, GY
     static constexpr size_t SMEM_BYTES = OFF_GX + NGX * THREADS * 4;
     static constexpr int TMEM_COLS = 512;
-    static constexpr int COL_T = 0, COL_V = 224, COL_Q = 320, COL_A1 = 456;   // A1: the T GEMM's A operand (UU hi | lo, 2 x 16 columns)
+    static constexpr int COL_T = 0, COL_V = 224, COL_Q = 320, COL_A1 = 456;   // A1: the T GEMM's A operand (UU hi | lo, 2 x 8 columns of packed halves)
 };
 
 // shared-memory image of the tensor-core kernel's constant B operands, built once per plan:
 //   B1[n = bcd][k = A]            = S[A,b,c,d]      (T GEMM, 224 x 16)
 //   BV[n = A*6 + b][k = c*6 + d]  = S[A,b,c,d]      (V GEMM,  96 x 40)
-// each as a hi plane followed by a lo plane (3xTF32 split), UMMA no-swizzle K-major layout
-__global__ void build_tc_operands_kernel(const float* __restrict__ S, uint8_t* __restrict__ img) {
+// each as a hi plane followed by a lo plane (FP16, scaled by the plan's power of two), UMMA no-swizzle K-major layout
+__global__ void build_tc_operands_kernel(const float* __restrict__ S, float s_scale, uint8_t* __restrict__ img) {
     using C = TcFitCfg;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (int idx = tid; idx < C::N1 * C::K1; idx += nth) {
         const int n = idx / C::K1, k = idx % C::K1;
-        const float v = (n < C::nBCD && k < C::nA) ? S[n * 16 + k] : 0.f;
-        float hi, lo;
-        ttc::split_tf32(v, hi, lo);
-        *reinterpret_cast<float*>(img + C::OFF_B1 + ttc::op_offset(n, k, C::K1)) = hi;
-        *reinterpret_cast<float*>(img + C::OFF_B1 + C::B1_BYTES + ttc::op_offset(n, k, C::K1)) = lo;
+        const float v = (n < C::nBCD && k < C::nA) ? S[n * 16 + k] * s_scale : 0.f;
+        __half hi, lo;
+        ttc::split_half(v, hi, lo);
+        *reinterpret_cast<__half*>(img + C::OFF_B1 + ttc::op16_offset(n, k, C::K1)) = hi;
+        *reinterpret_cast<__half*>(img + C::OFF_B1 + C::B1_BYTES + ttc::op16_offset(n, k, C::K1)) = lo;
     }
     for (int idx = tid; idx < C::NV * C::KV; idx += nth) {
         const int n = idx / C::KV, k = idx % C::KV;
         float v = 0.f;
         if (n < C::nA * C::nB && k < C::nC * C::nD) {
             const int aa = n / C::nB, b = n % C::nB;
-            v = S[(b * 36 + k) * 16 + aa];
+            v = S[(b * 36 + k) * 16 + aa] * s_scale;
         }
-        float hi, lo;
-        ttc::split_tf32(v, hi, lo);
-        *reinterpret_cast<float*>(img + C::OFF_BV + ttc::op_offset(n, k, C::KV)) = hi;
-        *reinterpret_cast<float*>(img + C::OFF_BV + C::BV_BYTES + ttc::op_offset(n, k, C::KV)) = lo;
+        __half hi, lo;
+        ttc::split_half(v, hi, lo);
+        *reinterpret_cast<__half*>(img + C::OFF_BV + ttc::op16_offset(n, k, C::KV)) = hi;
+        *reinterpret_cast<__half*>(img + C::OFF_BV + C::BV_BYTES + ttc::op16_offset(n, k, C::KV)) = lo;
     }
 }
 
 // Half of T (3 of the 6 b's = 108 columns) -> partial GR[6], GP[6] and the 3 GY of those b's
 template <int B0>
-__device__ __forceinline__ void tc_reduce_t(uint32_t taddr, const float (&YY)[6], const float (&PP)[6], const float (&RRv)[8],
-                                            float (&GR)[6], float (&GP)[6], float (&GY3)[3]) {
+// PPk / RRk: PP and RR times the inverse operand scales (the T accumulator holds T times the scales of S and UU)
+__device__ __forceinline__ void tc_reduce_t(uint32_t taddr, const float (&YY)[6], const float (&PP)[6], const float (&PPk)[6],
+                                            const float (&RRk)[8], float (&GR)[6], float (&GP)[6], float (&GY3)[3]) {
     float tr[18];   // sum_d T[b,c,d] * RR_d for the 3 b's
 #pragma unroll
     for (int i = 0; i < 18; ++i) tr[i] = 0.f;
@@ -857,8 +864,8 @@ __device__ __forceinline__ void tc_reduce_t(uint32_t taddr, const float (&YY)[6]
             if (bcd >= C0 && bcd < C0 + 108) {
                 const int b = bcd / 36, c = (bcd / 6) % 6, d = bcd % 6;
                 const float t = __uint_as_float(buf[ci & 1][x]);
-                GR[d] = fmaf(t, YY[b] * PP[c], GR[d]);
-                tr[(b - B0) * 6 + c] = fmaf(t, RRv[d], tr[(b - B0) * 6 + c]);
+                GR[d] = fmaf(t, YY[b] * PPk[c], GR[d]);
+                tr[(b - B0) * 6 + c] = fmaf(t, RRk[d], tr[(b - B0) * 6 + c]);
             }
         }
     }
@@ -990,6 +997,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
     for (int i = 0; i < C::NP; ++i) p[i] = 0.f;  // zero init, TD_Tester.py:130
     const float lr = a.lr, clip = a.clip;
     uint32_t phase = 0;
+    int uu_exp = 0;   // role 0: exponent of this iteration's UU operand scale
 #ifdef NLML_TC_TIMING
     // development build only (scripts/time_tucker_tc.py): per-phase cycle counts of one thread per role
     float tacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -1012,18 +1020,34 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         if (role == 0) {
             // the UU operand goes to TENSOR MEMORY (one 32-column store: hi | lo), not through shared memory: no operand
             // stores, no generic->async proxy fence, and the MMA reads A without touching the shared-memory ports
-            float UU[16], hl[32];
+            float UU[16], hl[16];
             sym_products<5>(u, UU);
             UU[15] = 0.f;
+            // per-sample power-of-two scale: the largest |UU| lands in [2^12, 2^13) (UU starts at 0 and grows over the fit)
+            float m = 0.f;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) ttc::split_tf32_bits(UU[k], hl[k], hl[16 + k]);
-            tmem_store32(lane_addr + C::COL_A1, hl);
+            for (int k = 0; k < 15; ++k) m = fmaxf(m, fabsf(UU[k]));
+            int eu = 12 - (((__float_as_int(m) >> 23) & 0xff) - 127);
+            eu = m > 0.f ? max(min(eu, 100), -80) : 0;
+            uu_exp = eu;
+            const float su = __int_as_float((eu + 127) << 23);
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) {   // packed pairs: element 2c in the low half of column c
+                const float v0 = UU[2 * k2] * su, v1 = UU[2 * k2 + 1] * su;
+                const __half2 h = __floats2half2_rn(v0, v1);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                hl[k2] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
+                hl[8 + k2] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&l));
+            }
+            tgen::tmem_st8(lane_addr + C::COL_A1, hl);
+            tgen::tmem_st8(lane_addr + C::COL_A1 + 8, hl + 8);
             tmem_store_wait();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (warp == 0 && NLML_DBG_MMA) {   // the whole warp, converged; the elected lane issues
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                ttc::gemm3_ts(tmem + C::COL_T, tmem + C::COL_A1, ttc::smem_u32(b1_hi), ttc::smem_u32(b1_lo), C::K1, C::N1);
+                ttc::gemm3h_ts(tmem + C::COL_T, tmem + C::COL_A1, ttc::smem_u32(b1_hi), ttc::smem_u32(b1_lo), C::K1, C::N1);
                 ttc::umma_commit_elect(bar);
             }
         }
@@ -1037,25 +1061,31 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         RRv[6] = RRv[7] = 0.f;
         // the identity threads publish the PP (x) RR operand; thread 160 launches the V GEMM (named barrier 2)
         if (role == 1) {
+            const float kPrScale = __int_as_float((127 + a.pr_exp) << 23);
 #pragma unroll
-            for (int k4 = 0; k4 < C::KV / 4; ++k4) {
-                float h[4], l[4];
+            for (int k8 = 0; k8 < C::KV / 8; ++k8) {   // one 16-byte chunk = 8 halves of this row per plane
+                uint32_t wh[4], wl[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const int kk = 4 * k4 + e;
-                    const float v = kk < 36 ? PP[kk / 6] * RRv[kk % 6] : 0.f;
-                    ttc::split_tf32_bits(v, h[e], l[e]);
+                    const int k0 = 8 * k8 + 2 * e, k1 = k0 + 1;
+                    const float v0 = k0 < 36 ? PP[k0 / 6] * RRv[k0 % 6] * kPrScale : 0.f;
+                    const float v1 = k1 < 36 ? PP[k1 / 6] * RRv[k1 % 6] * kPrScale : 0.f;
+                    const __half2 h = __floats2half2_rn(v0, v1);
+                    const float2 hf = __half22float2(h);
+                    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                    wh[e] = *reinterpret_cast<const uint32_t*>(&h);
+                    wl[e] = *reinterpret_cast<const uint32_t*>(&l);
                 }
-                *reinterpret_cast<float4*>(av_hi + ttc::op_offset(row, 4 * k4, C::KV)) = make_float4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<float4*>(av_lo + ttc::op_offset(row, 4 * k4, C::KV)) = make_float4(l[0], l[1], l[2], l[3]);
+                *reinterpret_cast<uint4*>(av_hi + ttc::op16_offset(row, 8 * k8, C::KV)) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                *reinterpret_cast<uint4*>(av_lo + ttc::op16_offset(row, 8 * k8, C::KV)) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
             }
             ttc::fence_async_smem();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync 2, 128;" ::: "memory");
             if (warp == 5 && NLML_DBG_MMA) {   // warp 5: not on the sub-partition of the T GEMM's issuer (warp 0)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                ttc::gemm3_ss(tmem + C::COL_V, ttc::smem_u32(av_hi), ttc::smem_u32(av_lo), ttc::smem_u32(bv_hi),
-                              ttc::smem_u32(bv_lo), C::KV, C::NV);
+                ttc::gemm3h_ss(tmem + C::COL_V, ttc::smem_u32(av_hi), ttc::smem_u32(av_lo), ttc::smem_u32(bv_hi),
+                               ttc::smem_u32(bv_lo), C::KV, C::NV);
                 ttc::umma_commit_elect(bar + 1);
             }
         }
@@ -1076,7 +1106,12 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         NLML_TSTAMP(2);   // yaw features + linear term
         if (role == 1) {
             // V[A,b] = sum_{c,D} PP_c RR_D S[A,b,c,D]  ->  GU[A] = sum_b YY_b V[A,b]  ->  d/du
-            float GU[15];
+            float GU[15], YYk[6];
+            {
+                const float kv = __int_as_float((127 - a.s_exp - a.pr_exp) << 23);   // 2^-(s_exp + pr_exp): the V accumulator's scale off
+#pragma unroll
+                for (int i = 0; i < 6; ++i) YYk[i] = YY[i] * kv;
+            }
 #pragma unroll
             for (int i = 0; i < 15; ++i) GU[i] = 0.f;
             if (NLML_DBG_MMA) ttc::mbar_wait(bar + 1, phase);   // V GEMM
@@ -1092,7 +1127,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
 #pragma unroll
                     for (int x = 0; x < 32; ++x) {
                         const int n = 32 * ci + x;
-                        if (n < 90) GU[n / 6] = fmaf(__uint_as_float(vb[ci & 1][x]), YY[n % 6], GU[n / 6]);
+                        if (n < 90) GU[n / 6] = fmaf(__uint_as_float(vb[ci & 1][x]), YYk[n % 6], GU[n / 6]);
                     }
                 }
             }
@@ -1102,15 +1137,21 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             for (int i = 0; i < 5; ++i) gx[(3 + i) * 128 + row] = du[i] - lin_u[i];
         } else {
             // all of T -> GR, GP, GY -> d/d(yaw, pitch, roll)
-            float GR[6], GP[6], GY[6], GR2[6], GP2[6], GY3[3];
+            float GR[6], GP[6], GY[6], GR2[6], GP2[6], GY3[3], PPk[6], RRk[8];
+            {
+                const float kt = __int_as_float((127 - a.s_exp - uu_exp) << 23);   // 2^-(s_exp + uu_exp): the T accumulator's scale off
+#pragma unroll
+                for (int i = 0; i < 6; ++i) { PPk[i] = PP[i] * kt; RRk[i] = RRv[i] * kt; }
+                RRk[6] = RRk[7] = 0.f;
+            }
             if (NLML_DBG_MMA) ttc::mbar_wait(bar, phase);       // T GEMM (launched first, long done)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             NLML_TSTAMP(3);
             if (NLML_DBG_READ) {
-                tc_reduce_t<0>(lane_addr + C::COL_T, YY, PP, RRv, GR, GP, GY3);
+                tc_reduce_t<0>(lane_addr + C::COL_T, YY, PP, PPk, RRk, GR, GP, GY3);
 #pragma unroll
                 for (int i = 0; i < 3; ++i) GY[i] = GY3[i];
-                tc_reduce_t<3>(lane_addr + C::COL_T, YY, PP, RRv, GR2, GP2, GY3);
+                tc_reduce_t<3>(lane_addr + C::COL_T, YY, PP, PPk, RRk, GR2, GP2, GY3);
 #pragma unroll
                 for (int i = 0; i < 3; ++i) GY[3 + i] = GY3[i];
 #pragma unroll
@@ -1864,9 +1905,10 @@ int launch_fit(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int
 typedef CUresult (*EncodeTiledFnT)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int project_tc(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, cudaStream_t st, const float** Qout) {
+constexpr int64_t kProjMinRows = 4096;   // below this the consumer's own phase A is as fast (one partial wave)
+int project_tc(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, cudaStream_t st, const float** Qout, int64_t min_rows = kProjMinRows) {
     *Qout = nullptr;
-    if (!pl->fast || !pl->proj_tiles || N < 4096 || (ldx % 4) != 0 || (reinterpret_cast<uintptr_t>(X) & 15) != 0) return 0;
+    if (!pl->fast || !pl->proj_tiles || N < min_rows || (ldx % 4) != 0 || (reinterpret_cast<uintptr_t>(X) & 15) != 0) return 0;
     static EncodeTiledFnT encode = nullptr;
     if (!encode) {
         void* p = nullptr;
@@ -1906,7 +1948,7 @@ int project_tc(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, cud
 
 // converged fit: thread-per-sample kernel, phase B' = tucker_lm_solve
 int launch_solve(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int max_evals, float* P, int64_t ldp,
-                 int* evals, cudaStream_t st) {
+                 int* evals, cudaStream_t st, int64_t proj_min_rows = kProjMinRows) {
     if (N == 0) return 0;
     if (!pl->fast) return set_error(NLML_E_UNSUPPORTED, "the converged solve is built for ranks (5,3,3,3) only");
     TuckerArgs a = pl->base;
@@ -1919,7 +1961,7 @@ int launch_solve(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, i
     a.lm = lm_default_options();
     if (max_evals > 0) a.lm.max_evals = max_evals;
     a.evals = evals;
-    if (int rc = project_tc(pl, X, N, ldx, st, &a.Qpre)) return rc;   // phase A as a tensor-core GEMM when the layout allows TMA
+    if (int rc = project_tc(pl, X, N, ldx, st, &a.Qpre, proj_min_rows)) return rc;   // phase A as a tensor-core GEMM when the layout allows TMA
     auto kern = tucker_fit_tps_kernel<5, 3, 3, 3, kTpsThreads, 1, kSolveMinBlocks, false, true>;
     kern<<<(unsigned)ceil_div(N, TpsDefault::SAMPLES), kTpsThreads, TpsDefault::SMEM_BYTES, st>>>(a);
     NLML_CUDA(cudaGetLastError());
@@ -2086,7 +2128,22 @@ extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, i
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpsBig::SMEM_BYTES));
         NLML_CUDA(cudaFuncSetAttribute(tucker_fit_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcFitCfg::SMEM_BYTES));
         NLML_CUDA(cudaMalloc(&pl->tc_ops, TcFitCfg::OFF_AV));
-        build_tc_operands_kernel<<<32, 256>>>(pl->S, pl->tc_ops);
+        {   // power-of-two scale of the S operand image: the largest |S| lands in [2^13, 2^14) of FP16's range
+            std::vector<float> Sh((size_t)pl->nBCD * pl->NAP);
+            NLML_CUDA(cudaMemcpy(Sh.data(), pl->S, sizeof(float) * Sh.size(), cudaMemcpyDeviceToHost));
+            float smax = 0.f;
+            for (float v : Sh) smax = std::max(smax, std::fabs(v));
+            int e = 0;
+            if (smax > 0.f && std::isfinite(smax)) e = 13 - (int)std::floor(std::log2(smax));
+            a.s_exp = std::max(-20, std::min(e, 20));
+            // |PP_c RR_D| <= (max_j |a_j| + |d_j|)^2 of the pitch rows times the same of the roll rows: keep it below 2^14
+            double bp = 0.0, br = 0.0;
+            for (int j = 0; j < r_p; ++j) bp = std::max(bp, std::fabs(rows_p[4 * j]) + std::fabs(rows_p[4 * j + 3]));
+            for (int j = 0; j < r_r; ++j) br = std::max(br, std::fabs(rows_r[4 * j]) + std::fabs(rows_r[4 * j + 3]));
+            const double bound = std::max(bp * bp * br * br, 1e-30);
+            a.pr_exp = std::max(-20, std::min(14 - (int)std::ceil(std::log2(bound)), 14));
+        }
+        build_tc_operands_kernel<<<32, 256>>>(pl->S, std::ldexp(1.0f, a.s_exp), pl->tc_ops);
         NLML_CUDA(cudaGetLastError());
         NLML_CUDA(cudaDeviceSynchronize());
         pl->launches += 1;
@@ -2199,8 +2256,10 @@ extern "C" int nlml_tucker_solve_host_f32(nlml_tucker_plan* pl, const float* X_h
     if (!pl->fast) return set_error(NLML_E_UNSUPPORTED, "the converged solve is built for ranks (5,3,3,3) only");
     DeviceGuard guard(pl->device);
     const int np = 3 + pl->ri;
+    // every chunk takes the phase A the whole batch would get (the last chunk of the ramp may be below the threshold)
+    const int64_t proj_min = N >= kProjMinRows ? 1 : kProjMinRows;
     return host_pipeline(pl, X_host, N, ldx, P_out_host, ldp, [&](const float* x, int64_t n, float* p, cudaStream_t st, int) {
-        return launch_solve(pl, x, n, pl->F, max_evals, p, np, nullptr, st);
+        return launch_solve(pl, x, n, pl->F, max_evals, p, np, nullptr, st, proj_min);
     });
 }
 
@@ -2355,7 +2414,16 @@ extern "C" int nlml_debug_tf32_gemm(const float* A_dev, const float* B_dev, int 
     return nlml_debug_tf32_gemm_mode(A_dev, B_dev, K, N, D_dev, 0);
 }
 extern "C" int nlml_debug_tf32_gemm_mode(const float* A_dev, const float* B_dev, int K, int N, float* D_dev, int mode) {
-    if (!A_dev || !B_dev || !D_dev || mode < 0 || mode > 1) return set_error(NLML_E_INVALID, "null pointer argument or bad mode");
+    if (!A_dev || !B_dev || !D_dev || mode < 0 || mode > 3) return set_error(NLML_E_INVALID, "null pointer argument or bad mode");
+    if (mode >= 2) {   // FP16 hi/lo building blocks (K multiple of 16, N <= 256)
+        if (K < 16 || K % 16 || K > 64 || N < 16 || N % 16 || N > 256) return set_error(NLML_E_INVALID, "K must be 16..64 (multiple of 16), N 16..256 (multiple of 16)");
+        const size_t smem16 = 2 * ttc::op16_bytes(128, K) + 2 * ttc::op16_bytes(N, K) + 64;
+        NLML_CUDA(cudaFuncSetAttribute(ttc::tc16_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+        ttc::tc16_check_kernel<<<1, 128, smem16>>>(A_dev, B_dev, D_dev, K, N, mode);
+        NLML_CUDA(cudaGetLastError());
+        NLML_CUDA(cudaDeviceSynchronize());
+        return 0;
+    }
     if (K < 8 || K % 8 || K > 64 || N < 16 || N % 16 || N > 256) return set_error(NLML_E_INVALID, "K must be 8..64 (multiple of 8), N 16..256 (multiple of 16)");
     ttc::TcCheckArgs a{A_dev, B_dev, D_dev, K, N, mode};
     const size_t smem = 2 * ttc::op_bytes(128, K) + 2 * ttc::op_bytes(N, K) + 64;

@@ -10,6 +10,7 @@
 // SBO = distance between 8-row groups.  We store [row group][k chunk][8 rows][16 B]: LBO = 128, SBO = (K/4) * 128.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -214,6 +215,143 @@ __device__ __forceinline__ void gemm3_ts(uint32_t d, uint32_t a_tmem, uint32_t b
         mma3_ts(d, a_tmem + k, a_tmem + K + k, bh, bl, idesc, k > 0 ? 1u : 0u);
         bh += 16; bl += 16;
     }
+}
+
+// ---- FP16 hi/lo variant of the same building blocks: kind::f16, K = 16 per MMA (half the MMA count of 3xTF32 at the same
+// cycle cost per instruction and half the operand bytes; the same 22 operand bits: hi = fp16(v), lo = fp16(v - hi)).  The
+// operands must sit in FP16's range: the callers scale them by powers of two.
+__host__ __device__ constexpr int op16_offset(int row, int k, int K) {   // K-major no-swizzle: core matrix = 8 rows x 8 halves
+    return (row / 8) * ((K / 8) * 128) + (k / 8) * 128 + (row % 8) * 16 + (k % 8) * 2;
+}
+__host__ __device__ constexpr int op16_bytes(int rows, int K) { return rows * K * 2; }
+__device__ __forceinline__ uint64_t make_desc16_noswz(uint32_t tile_addr, int K, int k0) {
+    const uint32_t addr = tile_addr + (uint32_t)((k0 / 8) * 128);
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(128 >> 4) << 16;                      // LBO: next K chunk (8 halves) of the same rows
+    d |= (uint64_t)(((K / 8) * 128) >> 4) << 32;          // SBO: next 8-row group
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_f16_f32(int M, int N) {   // D = F32, A = B = F16, both K-major
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma3h_ss(uint32_t d, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.b32 q, %5, %5;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %5, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %4, %5, q;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %5, q;\n\t}"
+        ::"r"(d), "l"(ah), "l"(al), "l"(bh), "l"(bl), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void mma3h_ts(uint32_t d, uint32_t ah, uint32_t al, uint64_t bh, uint64_t bl, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.b32 q, %5, %5;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%2], %3, %5, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %4, %5, q;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %3, %5, q;\n\t}"
+        ::"r"(d), "r"(ah), "r"(al), "l"(bh), "l"(bl), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// D = A * B^T (fresh accumulator), K multiple of 16; executed by a converged warp with warp-uniform arguments
+__device__ __forceinline__ void gemm3h_ss(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int K, int N) {
+    const uint32_t idesc = make_idesc_f16_f32(128, N);
+    uint64_t ah = make_desc16_noswz(a_hi, K, 0), al = make_desc16_noswz(a_lo, K, 0);
+    uint64_t bh = make_desc16_noswz(b_hi, K, 0), bl = make_desc16_noswz(b_lo, K, 0);
+    for (int k = 0; k < K; k += 16) {
+        mma3h_ss(d, ah, al, bh, bl, idesc, k > 0 ? 1u : 0u);
+        ah += 16; al += 16; bh += 16; bl += 16;   // 16 halves = two 128-byte chunks further
+    }
+}
+// A operand in tensor memory, two halves per 32-bit column: hi in columns [a, a + K/2), lo in [a + K/2, a + K)
+__device__ __forceinline__ void gemm3h_ts(uint32_t d, uint32_t a_tmem, uint32_t b_hi, uint32_t b_lo, int K, int N) {
+    const uint32_t idesc = make_idesc_f16_f32(128, N);
+    uint64_t bh = make_desc16_noswz(b_hi, K, 0), bl = make_desc16_noswz(b_lo, K, 0);
+    for (int k = 0; k < K; k += 16) {
+        mma3h_ts(d, a_tmem + k / 2, a_tmem + K / 2 + k / 2, bh, bl, idesc, k > 0 ? 1u : 0u);
+        bh += 16; bl += 16;
+    }
+}
+__device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+
+// check kernel of the FP16 variant: mode 2 = A in shared memory, mode 3 = A in tensor memory (packed pairs)
+__global__ void __launch_bounds__(128) tc16_check_kernel(const float* A, const float* B, float* D, int K, int N, int mode) {
+    extern __shared__ __align__(1024) uint8_t csm16[];
+    uint8_t* a_hi = csm16;
+    uint8_t* a_lo = a_hi + op16_bytes(128, K);
+    uint8_t* b_hi = a_lo + op16_bytes(128, K);
+    uint8_t* b_lo = b_hi + op16_bytes(N, K);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(b_lo + op16_bytes(N, K));
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int k = 0; k < K; ++k) {
+        __half hi, lo;
+        split_half(A[tid * K + k], hi, lo);
+        *reinterpret_cast<__half*>(a_hi + op16_offset(tid, k, K)) = hi;
+        *reinterpret_cast<__half*>(a_lo + op16_offset(tid, k, K)) = lo;
+    }
+    for (int idx = tid; idx < N * K; idx += 128) {
+        const int n = idx / K, k = idx % K;
+        __half hi, lo;
+        split_half(B[idx], hi, lo);
+        *reinterpret_cast<__half*>(b_hi + op16_offset(n, k, K)) = hi;
+        *reinterpret_cast<__half*>(b_lo + op16_offset(n, k, K)) = lo;
+    }
+    fence_async_smem();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *slot;
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t col_a = 256;
+    if (mode == 3) {   // this thread's row of A, packed (element 2c in the low half of column c)
+        for (int c = 0; c < K / 2; ++c) {
+            __half h0, l0, h1, l1;
+            split_half(A[tid * K + 2 * c], h0, l0);
+            split_half(A[tid * K + 2 * c + 1], h1, l1);
+            const uint32_t wh = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+            const uint32_t wl = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr + col_a + c), "r"(wh) : "memory");
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr + col_a + K / 2 + c), "r"(wl) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (warp == 0) {
+        if (mode == 3) gemm3h_ts(tmem, tmem + col_a, smem_u32(b_hi), smem_u32(b_lo), K, N);
+        else gemm3h_ss(tmem, smem_u32(a_hi), smem_u32(a_lo), smem_u32(b_hi), smem_u32(b_lo), K, N);
+        umma_commit_elect(bar);
+    }
+    mbar_wait(bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32];
+        tmem_load32(taddr + c0, v);
+        for (int j = 0; j < 32 && c0 + j < N; ++j) D[tid * N + c0 + j] = v[j];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
 // ---- stand-alone check kernel: one CTA, D[128][N] = A[128][K] * B[N][K]^T --------------------------------

@@ -80,24 +80,28 @@ def test_NLML_HPE_Tester_driver(ref_layout, X1k, mlp_golden, capsys, cuda_lib):
 
 
 @pytest.mark.gpu
-def test_TD_Inference_cli(ref_layout, X1k, tucker_golden, capsys, cuda_lib):
+def test_TD_Inference_cli(ref_layout, X1k, tucker_golden, capsys, cuda_lib, monkeypatch):
     """TD_Inference.inference: loads ./outputs/features/*.npz (:40-51), slices the cosine rows [0:3] (:56-57), calls
     Test, prints the three lines of :65-67."""
     np.save("x0.npy", X1k[0])
-    try:
-        TD_Tester.TEST_SOLVER = "sgd"        # the fixed-iteration block (:168-184): bit-level parity contract
-        y, p, r = TD_Inference.inference(["--features_npy", "x0.npy"])
-        out = capsys.readouterr().out.strip().splitlines()
-        ref = np.degrees(tucker_golden["sgd3000_shipped_P"][0, :3].astype(np.float64))
-        assert max(abs(y - ref[0]), abs(p - ref[1]), abs(r - ref[2])) < 1e-2
-        assert out == [f"Estimated yaw in degree = {y:.2f}", f"Estimated pitch in degree = {p:.2f}",
-                       f"Estimated roll in degree = {r:.2f}"]
-    finally:
-        TD_Tester.TEST_SOLVER = "converged"
-    y, p, r = TD_Inference.inference(["--features_npy", "x0.npy"])          # default: the converged fit
+    monkeypatch.setattr(TD_Tester, "TEST_SOLVER", "sgd")   # the fixed-iteration block (:168-184): bit-level parity contract
+    y, p, r = TD_Inference.inference(["--features_npy", "x0.npy"])
+    out = capsys.readouterr().out.strip().splitlines()
+    ref = np.degrees(tucker_golden["sgd3000_shipped_P"][0, :3].astype(np.float64))
+    assert max(abs(y - ref[0]), abs(p - ref[1]), abs(r - ref[2])) < 1e-2
+    assert out == [f"Estimated yaw in degree = {y:.2f}", f"Estimated pitch in degree = {p:.2f}",
+                   f"Estimated roll in degree = {r:.2f}"]
+    monkeypatch.setattr(TD_Tester, "TEST_SOLVER", "converged")   # the fast alternative: same basin as the reference's Powell
+    y, p, r = TD_Inference.inference(["--features_npy", "x0.npy"])
     out = capsys.readouterr().out
     assert out.count("Estimated") == 3
     pw = tucker_golden["powell_shipped_deg"][0]
-    assert max(abs(y - pw[0]), abs(p - pw[1]), abs(r - pw[2])) < 5.0       # same basin as the reference's Powell (see test_tucker_gpu)
+    assert max(abs(y - pw[0]), abs(p - pw[1]), abs(r - pw[2])) < 5.0       # see test_tucker_gpu.test_solve_vs_reference_powell_96
+    monkeypatch.setattr(TD_Tester, "TEST_SOLVER", "powell")      # the default: the reference's own search, same printed lines
+    y, p, r = TD_Inference.inference(["--features_npy", "x0.npy"])
+    out = capsys.readouterr().out.strip().splitlines()
+    assert max(abs(y - pw[0]), abs(p - pw[1]), abs(r - pw[2])) < 1e-6
+    assert out[-3:] == [f"Estimated yaw in degree = {y:.2f}", f"Estimated pitch in degree = {p:.2f}",
+                        f"Estimated roll in degree = {r:.2f}"]
     with pytest.raises(SystemExit):
         TD_Inference.inference([])                                          # argparse: one of the two inputs is required

@@ -142,7 +142,7 @@ def test_host_path_ramped_chunks(fitter, X1k):
     assert np.array_equal(fitter.solve_host(X), sdev)
 
 
-def test_reference_entry_points(art, rows, X1k, tucker_golden, cuda_lib):
+def test_reference_entry_points(art, rows, X1k, tucker_golden, cuda_lib, monkeypatch):
     """TD_Tester.optimize_with_sgd / Test with the reference's signatures and conventions."""
     from nlml_hpe_b200 import TD_Tester
     t = lambda a: torch.tensor(a, dtype=torch.float32)  # noqa: E731  (call shape of TD_Tester.py:170-177)
@@ -150,13 +150,12 @@ def test_reference_entry_points(art, rows, X1k, tucker_golden, cuda_lib):
     assert p.dtype == torch.float32 and p.shape == (8,) and not p.is_cuda
     ref = tucker_golden["sgd3000_shipped_P"][0]
     assert np.abs(p.numpy()[:3] - ref[:3]).max() * DEG < TOL_DEG
-    TD_Tester.TEST_SOLVER = "sgd"
-    try:
-        y, pi, r, u = TD_Tester.Test(art["W"], torch.from_numpy(X1k[0]), 5, *rows, None, None, None, None)
-    finally:
-        TD_Tester.TEST_SOLVER = "converged"
+    monkeypatch.setattr(TD_Tester, "TEST_SOLVER", "sgd")
+    y, pi, r, u = TD_Tester.Test(art["W"], torch.from_numpy(X1k[0]), 5, *rows, None, None, None, None)
     assert u is None and abs(y - np.degrees(ref[0])) < TOL_DEG and abs(r - np.degrees(ref[2])) < TOL_DEG
-    # default: converged fit, as the reference's Test (scipy Powell, TD_Tester.py:191-199); same basin as Powell
+    # the converged fit: where the reference's Test runs scipy Powell (TD_Tester.py:191-199); same basin as Powell
+    # (the default, "powell", is covered bit for bit in test_powell.py)
+    monkeypatch.setattr(TD_Tester, "TEST_SOLVER", "converged")
     y, pi, r, u = TD_Tester.Test(art["W"], torch.from_numpy(X1k[0]), 5, *rows, None, None, None, None)
     pw = tucker_golden["powell_shipped_deg"][0]
     # converged fit vs scipy Powell: same basin, lower loss, angles up to several degrees apart (test_solve_vs_reference_powell_96)
