@@ -207,7 +207,12 @@ struct Workspace {
 #ifndef NLML_MLP_CHUNK_WAVES
 #define NLML_MLP_CHUNK_WAVES 8       // samples per pass = waves x num_sms x 128 (4 waves 16.9 ms / 1M, 8 waves 16.5, 16 waves 16.5)
 #endif
+#ifndef NLML_MLP_DEV_LANES
+#define NLML_MLP_DEV_LANES 2         // device-buffer batches above one chunk: chunks alternate between this many internal
+#endif                               // streams (forked from / joined to the caller's), so one chunk's HBM-bound operand split
+                                     // and epilogue-bound head layers overlap the other's tensor-bound encoder layers
 namespace {
+constexpr int kDevLanes = NLML_MLP_DEV_LANES;
 constexpr int kTcGroup = NLML_MLP_TC_GROUP, kShortKGroup2 = NLML_MLP_SHORTK_GROUP2;
 constexpr bool kTcNeck = NLML_MLP_TC_NECK != 0, kTcTail = NLML_MLP_TC_TAIL != 0, kTwoCta = NLML_MLP_TWO_CTA != 0;
 }  // namespace
@@ -233,6 +238,9 @@ struct nlml_mlp_plan {
                                     // 4 waves 16.9 ms, 8 waves 16.5 ms, 16 waves 16.5 ms; workspaces 2.6 GB at 8)
     size_t f32_width[2] = {0, 0}, plane_width[2] = {0, 0};
     Workspace ws_dev;        // device-buffer entry points (ordered across caller streams by ws_dev_done)
+    Workspace ws_lane;       // second lane of the device path (batches above one chunk)
+    cudaStream_t lane[2] = {nullptr, nullptr};
+    cudaEvent_t lane_fork = nullptr, lane_join[2] = {nullptr, nullptr};
     Workspace ws_host[2];    // the host pipeline's two slots (its own internal streams); never touched by the device path
     cudaEvent_t ws_dev_done = nullptr;   // recorded after the last device-path call's kernels: a later call on ANOTHER stream
                                          // waits for it before reusing ws_dev (two unordered streams must not share the buffers)
@@ -307,7 +315,6 @@ inline int group_for(const nlml_mlp_plan* pl, int Kp) { return Kp <= kShortKGrou
 // development build only: every linear_tc2_kernel launch writes its per-warp phase cycles into the next slice of this buffer
 static float* g_mlp_timing_buf = nullptr;
 static int g_mlp_timing_slices = 0, g_mlp_timing_next = 0;
-extern "C" void nlml_debug_mlp_timing(float* dev_buf, int slices) { g_mlp_timing_buf = dev_buf; g_mlp_timing_slices = slices; g_mlp_timing_next = 0; }
 #endif
 
 // one tensor-core layer for `nz` problems of identical shape (1 = encoder layer, 3 = the heads):
@@ -534,14 +541,32 @@ int forward_device(nlml_mlp_plan* pl, const float* X, int64_t N, int64_t ldx, fl
     if (int rc = ensure_workspace(pl, pl->ws_dev, N)) return rc;
     if (!pl->ws_dev_done) NLML_CUDA(cudaEventCreateWithFlags(&pl->ws_dev_done, cudaEventDisableTiming));
     else NLML_CUDA(cudaStreamWaitEvent(st, pl->ws_dev_done, 0));   // the previous call may have run on another stream
-    for (int64_t s0 = 0; s0 < N; s0 += pl->chunk) {
-        const int64_t n = std::min<int64_t>(pl->chunk, N - s0);
-        if (int rc = forward_chunk(pl, X + s0 * ldx, n, ldx, YPR ? YPR + s0 * 3 : nullptr,
-                                   LAT ? LAT + s0 * pl->latent : nullptr, pl->ws_dev, st, pre))
-            return rc;
+    const bool lanes = kDevLanes == 2 && N > pl->chunk;
+    if (lanes) {
+        if (int rc = ensure_workspace(pl, pl->ws_lane, N - pl->chunk)) return rc;
+        if (!pl->lane_fork) {
+            for (int i = 0; i < 2; ++i) {
+                NLML_CUDA(cudaStreamCreateWithFlags(&pl->lane[i], cudaStreamNonBlocking));
+                NLML_CUDA(cudaEventCreateWithFlags(&pl->lane_join[i], cudaEventDisableTiming));
+            }
+            NLML_CUDA(cudaEventCreateWithFlags(&pl->lane_fork, cudaEventDisableTiming));
+        }
+        NLML_CUDA(cudaEventRecord(pl->lane_fork, st));
+        for (int i = 0; i < 2; ++i) NLML_CUDA(cudaStreamWaitEvent(pl->lane[i], pl->lane_fork, 0));
     }
+    int slot = 0, rc = 0;
+    for (int64_t s0 = 0; s0 < N && !rc; s0 += pl->chunk, slot ^= 1) {
+        const int64_t n = std::min<int64_t>(pl->chunk, N - s0);
+        rc = forward_chunk(pl, X + s0 * ldx, n, ldx, YPR ? YPR + s0 * 3 : nullptr, LAT ? LAT + s0 * pl->latent : nullptr,
+                           lanes && slot ? pl->ws_lane : pl->ws_dev, lanes ? pl->lane[slot] : st, pre);
+    }
+    if (lanes)   // joined on the error path too: the caller's stream must not run ahead of launched chunks
+        for (int i = 0; i < 2; ++i) {
+            NLML_CUDA(cudaEventRecord(pl->lane_join[i], pl->lane[i]));
+            NLML_CUDA(cudaStreamWaitEvent(st, pl->lane_join[i], 0));
+        }
     NLML_CUDA(cudaEventRecord(pl->ws_dev_done, st));
-    return 0;
+    return rc;
 }
 
 // W[out][in] FP32 -> power-of-two-scaled FP16 hi/lo planes [out][Kp]
@@ -687,6 +712,12 @@ extern "C" void nlml_mlp_plan_destroy(nlml_mlp_plan* pl) {
         free_workspace(pl->ws_host[i]);
     }
     free_workspace(pl->ws_dev);
+    free_workspace(pl->ws_lane);
+    for (int i = 0; i < 2; ++i) {
+        if (pl->lane[i]) cudaStreamDestroy(pl->lane[i]);
+        if (pl->lane_join[i]) cudaEventDestroy(pl->lane_join[i]);
+    }
+    if (pl->lane_fork) cudaEventDestroy(pl->lane_fork);
     if (pl->ws_dev_done) cudaEventDestroy(pl->ws_dev_done);
     delete pl;
 }
@@ -814,3 +845,7 @@ int forward_host(nlml_mlp_plan* pl, const float* X_host, int64_t N, int64_t ldx,
 }  // namespace
 
 extern "C" int64_t nlml_mlp_launch_count(const nlml_mlp_plan* pl) { return pl ? pl->launches : 0; }
+
+#ifdef NLML_MLP_TIMING
+extern "C" void nlml_debug_mlp_timing(float* dev_buf, int slices) { g_mlp_timing_buf = dev_buf; g_mlp_timing_slices = slices; g_mlp_timing_next = 0; }
+#endif

@@ -226,11 +226,20 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
     return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ float act_apply(float v, int act) {
-    if (act == 1) return fmaxf(v, 0.f);
-    if (act == 2) return tanhf(v);
+// The activation is a template parameter of everything that runs per element: with a run-time `act` every one of a
+// thread's 128 outputs carried two uniform branches (and the inlined tanh body), ~13 k cycles per tile in which the
+// epilogue warps promoted nothing and the tensor pipe of the long layers idled (29 % of encoder.0's time).
+template <int ACT>
+__device__ __forceinline__ float act_fixed(float v) {
+    if (ACT == 1) return fmaxf(v, 0.f);
+    if (ACT == 2) return tanhf(v);
     return v;
 }
+// runs BODY with `ACT` a compile-time constant equal to the run-time `act`
+#define NLML_ACT_DISPATCH(act, ...)                              \
+    if ((act) == 1) { constexpr int ACT = 1; __VA_ARGS__ }       \
+    else if ((act) == 2) { constexpr int ACT = 2; __VA_ARGS__ }  \
+    else { constexpr int ACT = 0; __VA_ARGS__ }
 
 // Two FP32 values -> packed FP16 (hi, lo) words, value 0 in the low half.  Packed conversions (one F2FP per pair, the
 // way back through HADD2.F32) instead of six scalar F2F per pair: the scalar form runs at a quarter of the ALU rate
@@ -242,6 +251,47 @@ __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uin
     const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// One thread's row of a finished tile: y = act(sum * inv_scale + bias), written as FP32 and/or as FP16 hi/lo planes.
+// `yf`, `dh`, `dl` point at this row's first column of the warp's column slice (null = not wanted).
+template <int ACT, int HALF>
+__device__ __forceinline__ void store_row(const float (&sum)[HALF], float inv_scale, const float* bias_s, float* yf, __half* dh,
+                                          __half* dl) {
+#pragma unroll
+    for (int c0 = 0; c0 < HALF; c0 += 32) {
+        float y[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + j);   // broadcast LDS.128
+            y[j] = act_fixed<ACT>(fmaf(sum[c0 + j], inv_scale, b.x));
+            y[j + 1] = act_fixed<ACT>(fmaf(sum[c0 + j + 1], inv_scale, b.y));
+            y[j + 2] = act_fixed<ACT>(fmaf(sum[c0 + j + 2], inv_scale, b.z));
+            y[j + 3] = act_fixed<ACT>(fmaf(sum[c0 + j + 3], inv_scale, b.w));
+        }
+        if (yf) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t w[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) w[e] = __float_as_uint(y[8 * j + e]);
+                st_global_v8(yf + c0 + 8 * j, w);
+            }
+        }
+        if (dh) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split_pair(y[2 * j], y[2 * j + 1], hi[j], lo[j]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint32_t wh[8], wl[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { wh[e] = hi[8 * j + e]; wl[e] = lo[8 * j + e]; }
+                st_global_v8(dh + c0 + 16 * j, wh);
+                st_global_v8(dl + c0 + 16 * j, wl);
+            }
+        }
+    }
 }
 
 // CL = CTAs per cluster (1 or 2).  With CL = 2 the two CTAs of a cluster work on M-tiles (2p, 2p+1) of the same
@@ -398,12 +448,15 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
             float* bias_s = bias_all + (warp - kFirstEpilogueWarp) * HALF;   // this warp's slice of the bias, read back as broadcasts
             float* dotw_s = dotw_all + (warp - kFirstEpilogueWarp) * HALF;
             const float* __restrict__ dot_w = a.dot_w[z];
-            __syncwarp();
-            for (int j = lane; j < HALF; j += 32) {
-                bias_s[j] = __ldg(bias + n0 + j);
-                if (dot_w) dotw_s[j] = __ldg(dot_w + n0 + j);
+            // this tile's bias (and dot weights) are fetched now and parked in shared memory after the promotion loop:
+            // the L2 latency hides behind the accumulator waits instead of stalling the start of every tile
+            float bias_r[(HALF + 31) / 32], dotw_r[(HALF + 31) / 32];
+#pragma unroll
+            for (int i = 0; i < (HALF + 31) / 32; ++i) {
+                const int j = lane + 32 * i;
+                bias_r[i] = j < HALF ? __ldg(bias + n0 + j) : 0.f;
+                dotw_r[i] = (dot_w && j < HALF) ? __ldg(dot_w + n0 + j) : 0.f;
             }
-            __syncwarp();
             float sum[HALF];
 #pragma unroll
             for (int j = 0; j < HALF; ++j) sum[j] = 0.f;
@@ -426,18 +479,26 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
                 if (lane == 0) mbar_arrive(&tempty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+            __syncwarp();   // the previous tile's reads of the slices are done (same warp, program order + this fence)
+#pragma unroll
+            for (int i = 0; i < (HALF + 31) / 32; ++i) {
+                const int j = lane + 32 * i;
+                if (j < HALF) { bias_s[j] = bias_r[i]; dotw_s[j] = dotw_r[i]; }
+            }
+            __syncwarp();
             if constexpr (BN == 64) {
                 if (a.neck) {
                     // y = tanh(.) of this warp's 32 of the 64 columns -> partial latent -> exchange -> heads' first layers
                     float lat[kNeckLatent];
 #pragma unroll
                     for (int m = 0; m < kNeckLatent; ++m) lat[m] = 0.f;
-#pragma unroll
-                    for (int j = 0; j < HALF; ++j) {
-                        const float y = act_apply(fmaf(sum[j], inv_scale, bias_s[j]), a.act);
-#pragma unroll
-                        for (int m = 0; m < kNeckLatent; ++m) lat[m] = fmaf(y, neck_w5s[m * 64 + n0 + j], lat[m]);
-                    }
+                    NLML_ACT_DISPATCH(a.act,
+                        _Pragma("unroll")
+                        for (int j = 0; j < HALF; ++j) {
+                            const float y = act_fixed<ACT>(fmaf(sum[j], inv_scale, bias_s[j]));
+                            _Pragma("unroll")
+                            for (int m = 0; m < kNeckLatent; ++m) lat[m] = fmaf(y, neck_w5s[m * 64 + n0 + j], lat[m]);
+                        })
                     const int r = quad * 32 + lane;
 #pragma unroll
                     for (int m = 0; m < kNeckLatent; ++m) neck_xch[(half * kNeckLatent + m) * BM + r] = lat[m];
@@ -478,9 +539,10 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
                 // fused final layer: this thread's share of the row's dot product, then the two column halves
                 // of a lane quadrant meet through shared memory (named barrier of the two warps)
                 float part = 0.f;
-#pragma unroll
-                for (int j = 0; j < HALF; ++j)
-                    part = fmaf(act_apply(fmaf(sum[j], inv_scale, bias_s[j]), a.act), dotw_s[j], part);
+                NLML_ACT_DISPATCH(a.act,
+                    _Pragma("unroll")
+                    for (int j = 0; j < HALF; ++j)
+                        part = fmaf(act_fixed<ACT>(fmaf(sum[j], inv_scale, bias_s[j])), dotw_s[j], part);)
                 float* slot = dot_xch + (tile_parity * BM) + quad * 32 + lane;
                 if (half == 1) *slot = part;
                 asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
@@ -488,40 +550,10 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
                 tile_parity ^= 1;
             }
             if (row < a.N && (Yf32 || Yhi)) {
-#pragma unroll
-                for (int c0 = 0; c0 < HALF; c0 += 32) {
-                    float y[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        y[j] = act_apply(fmaf(sum[c0 + j], inv_scale, bias_s[c0 + j]), a.act);
-                    if (Yf32) {
-                        float* dst = Yf32 + row * a.ldy + n0 + c0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint32_t w[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) w[e] = __float_as_uint(y[8 * j + e]);
-                            st_global_v8(dst + 8 * j, w);
-                        }
-                    }
-                    if (Yhi) {
-                        uint32_t hi[16], lo[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            split_pair(y[2 * j], y[2 * j + 1], hi[j], lo[j]);
-                        }
-                        __half* dh = Yhi + row * a.ldy + n0 + c0;
-                        __half* dl = Ylo + row * a.ldy + n0 + c0;
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            uint32_t wh[8], wl[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) { wh[e] = hi[8 * j + e]; wl[e] = lo[8 * j + e]; }
-                            st_global_v8(dh + 16 * j, wh);
-                            st_global_v8(dl + 16 * j, wl);
-                        }
-                    }
-                }
+                float* yf = Yf32 ? Yf32 + row * a.ldy + n0 : nullptr;
+                __half* dh = Yhi ? Yhi + row * a.ldy + n0 : nullptr;
+                __half* dl = Yhi ? Ylo + row * a.ldy + n0 : nullptr;
+                NLML_ACT_DISPATCH(a.act, store_row<ACT, HALF>(sum, inv_scale, bias_s, yf, dh, dl);)
             }
         }
     }
@@ -729,9 +761,9 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
             __half* __restrict__ Yhi = a.Yhi[z];
             __half* __restrict__ Ylo = a.Ylo[z];
             float* bias_s = bias_all + (warp - kFirstEpilogueWarp) * HALF;   // this warp's slice of the bias, read back as broadcasts
-            __syncwarp();
-            for (int j = lane; j < HALF; j += 32) bias_s[j] = __ldg(bias + n0 + j);
-            __syncwarp();
+            float bias_r[HALF / 32];   // fetched now, parked in shared memory after the promotion loop (latency hidden)
+#pragma unroll
+            for (int i = 0; i < HALF / 32; ++i) bias_r[i] = __ldg(bias + n0 + lane + 32 * i);
             NLML_MT_STAMP(0);
             float sum[HALF];
 #pragma unroll
@@ -757,41 +789,15 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 NLML_MT_STAMP(2);
             }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < HALF / 32; ++i) bias_s[lane + 32 * i] = bias_r[i];
+            __syncwarp();
             if (row < a.N) {
-#pragma unroll
-                for (int c0 = 0; c0 < HALF; c0 += 32) {
-                    float y[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        y[j] = act_apply(fmaf(sum[c0 + j], inv_scale, bias_s[c0 + j]), a.act);
-                    if (Yf32) {
-                        float* dst = Yf32 + row * a.ldy + n0 + c0;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint32_t w[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) w[e] = __float_as_uint(y[8 * j + e]);
-                            st_global_v8(dst + 8 * j, w);
-                        }
-                    }
-                    if (Yhi) {
-                        uint32_t hi[16], lo[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            split_pair(y[2 * j], y[2 * j + 1], hi[j], lo[j]);
-                        }
-                        __half* dh = Yhi + row * a.ldy + n0 + c0;
-                        __half* dl = Ylo + row * a.ldy + n0 + c0;
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            uint32_t wh[8], wl[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) { wh[e] = hi[8 * j + e]; wl[e] = lo[8 * j + e]; }
-                            st_global_v8(dh + 16 * j, wh);
-                            st_global_v8(dl + 16 * j, wl);
-                        }
-                    }
-                }
+                float* yf = Yf32 ? Yf32 + row * a.ldy + n0 : nullptr;
+                __half* dh = Yhi ? Yhi + row * a.ldy + n0 : nullptr;
+                __half* dl = Yhi ? Ylo + row * a.ldy + n0 : nullptr;
+                NLML_ACT_DISPATCH(a.act, store_row<ACT, HALF>(sum, inv_scale, bias_s, yf, dh, dl);)
             }
             NLML_MT_STAMP(3);
 #ifdef NLML_MLP_TIMING
