@@ -207,12 +207,18 @@ struct Workspace {
 #ifndef NLML_MLP_CHUNK_WAVES
 #define NLML_MLP_CHUNK_WAVES 8       // samples per pass = waves x num_sms x 128 (4 waves 16.9 ms / 1M, 8 waves 16.5, 16 waves 16.5)
 #endif
+#ifndef NLML_MLP_LEAD_KB
+#define NLML_MLP_LEAD_KB 0           // long reductions (>= 8 k-blocks): the first this-many k-blocks of a tile summed in pairs, so
+#endif                               // the MMAs run further ahead of the epilogue warps' store phase.  Measured with 4: encoder.0
+                                     // 39.2 k -> 37.7 k cycles per tile (the layer is shared-memory-bandwidth bound either way),
+                                     // whole chain +1 %, error 6.0e-4 -> 6.3e-4 deg on synthetic features and 1.02e-3 deg on the
+                                     // landmark fixtures: over the 1e-3 budget, so it stays off
 #ifndef NLML_MLP_DEV_LANES
 #define NLML_MLP_DEV_LANES 2         // device-buffer batches above one chunk: chunks alternate between this many internal
 #endif                               // streams (forked from / joined to the caller's), so one chunk's HBM-bound operand split
                                      // and epilogue-bound head layers overlap the other's tensor-bound encoder layers
 namespace {
-constexpr int kDevLanes = NLML_MLP_DEV_LANES;
+constexpr int kDevLanes = NLML_MLP_DEV_LANES, kLeadKb = NLML_MLP_LEAD_KB;
 constexpr int kTcGroup = NLML_MLP_TC_GROUP, kShortKGroup2 = NLML_MLP_SHORTK_GROUP2;
 constexpr bool kTcNeck = NLML_MLP_TC_NECK != 0, kTcTail = NLML_MLP_TC_TAIL != 0, kTwoCta = NLML_MLP_TWO_CTA != 0;
 }  // namespace
@@ -328,6 +334,7 @@ int launch_tc(nlml_mlp_plan* pl, const int* t, int nz, const __half* const* Ahi,
     tc::TcMaps maps;
     tc::LinearTcArgs a{};
     a.N = n; a.out = out; a.Kp = Kp; a.act = act_of(t[0]); a.problems = nz; a.ldy = out; a.group = group_for(pl, Kp);
+    a.lead_kb = Kp / tc::BK >= 8 ? kLeadKb : 0;
     a.Ydot = Ydot; a.ldd = 3;
     for (int z = 0; z < nz && dot_t; ++z) { a.dot_w[z] = pl->W[dot_t[z]]; a.dot_b[z] = pl->B[dot_t[z]]; }
     for (int z = 0; z < nz; ++z) {
@@ -337,6 +344,18 @@ int launch_tc(nlml_mlp_plan* pl, const int* t, int nz, const __half* const* Ahi,
         maps.w_lo[z] = pl->wmap_lo[t[z]];
         a.inv_scale[z] = pl->inv_scale[t[z]]; a.bias[z] = pl->B[t[z]];
         a.Yhi[z] = Yhi[z]; a.Ylo[z] = Ylo[z]; a.Yf32[z] = Yf32[z];
+    }
+    // plane-only outputs of the 128- and 256-wide tiles leave through TMA (32-row x 64-column boxes per epilogue warp)
+    a.y_tma = out % 128 == 0;
+    for (int z = 0; z < nz; ++z) a.y_tma = a.y_tma && Yhi[z] && Ylo[z] && !Yf32[z];
+    for (int z = 0; z < tc::kMaxProblems; ++z) {
+        const int zz = z < nz ? z : 0;
+        if (a.y_tma) {
+            if (int rc = tc::make_plane_map(&maps.y_hi[z], Yhi[zz], n, out, out, 32)) return rc;
+            if (int rc = tc::make_plane_map(&maps.y_lo[z], Ylo[zz], n, out, out, 32)) return rc;
+        } else {
+            maps.y_hi[z] = maps.a_hi[0]; maps.y_lo[z] = maps.a_lo[0];   // never dereferenced
+        }
     }
     for (int z = nz; z < tc::kMaxProblems; ++z) {
         maps.a_hi[z] = maps.a_hi[0]; maps.a_lo[z] = maps.a_lo[0]; maps.w_hi[z] = maps.w_hi[0]; maps.w_lo[z] = maps.w_lo[0];
@@ -447,6 +466,7 @@ int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, flo
         if (int rc = tc::make_plane_map(&maps.a_lo[0], cur_lo, n, a.Kp, a.Kp, tc::BM)) return rc;
         maps.w_hi[0] = pl->wmap_hi[t4]; maps.w_lo[0] = pl->wmap_lo[t4];
         for (int z = 1; z < tc::kMaxProblems; ++z) { maps.a_hi[z] = maps.a_hi[0]; maps.a_lo[z] = maps.a_lo[0]; maps.w_hi[z] = maps.w_hi[0]; maps.w_lo[z] = maps.w_lo[0]; }
+        for (int z = 0; z < tc::kMaxProblems; ++z) { maps.y_hi[z] = maps.a_hi[0]; maps.y_lo[z] = maps.a_lo[0]; }   // y_tma = 0: never dereferenced
         a.inv_scale[0] = pl->inv_scale[t4]; a.bias[0] = pl->B[t4];
         a.neck = 1; a.neck_w5 = pl->W[5]; a.neck_b5 = pl->B[5];
         a.neck_lat = LAT_out ? LAT_out : w.lat;

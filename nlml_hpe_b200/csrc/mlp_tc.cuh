@@ -38,6 +38,7 @@ constexpr int kProducerRegs = 40, kEpilogueRegs = 232;   // (40 + 232 + 232) * 3
 
 // fused neck epilogue (BN = 64 only): W5 [9][64], B5 [12], head rows (w0,w1,w2,b) [3][128] float4, latent exchange [2][9][128]
 constexpr int kNeckLatent = 9, kNeckHeadW = 128;
+constexpr int kStoreStageBytes = 32 * 128;   // per epilogue warp: its 32 rows x 128 B of one plane (store_planes_staged)
 constexpr int kNeckSmemFloats = kNeckLatent * 64 + 12 + 3 * kNeckHeadW * 4 + 2 * kNeckLatent * BM;
 
 template <int BN>
@@ -48,18 +49,26 @@ struct Cfg {
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;              // two accumulator buffers
     static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ +
-                                         2 * kEpilogueWarps * (BN / 2) * 4 /*bias, dot weights*/ + 2 * BM * 4 /*dot exchange*/ +
-                                         (BN == 64 ? kNeckSmemFloats * 4 : 0) /*fused neck epilogue*/;
+                                         (BN == 64 ? 2 * kEpilogueWarps * (BN / 2) * 4 : 0) /*bias, dot weights*/ + 2 * BM * 4 /*dot exchange*/ +
+                                         (BN == 64 ? kNeckSmemFloats * 4 : 0) /*fused neck epilogue*/ +
+                                         (BN >= 128 ? kEpilogueWarps * kStoreStageBytes : 0) /*line-forming store staging*/;
 };
 
 constexpr int kMaxProblems = 3;   // the three heads ride one launch
 
+// k-blocks summed in the accumulator that starts at k-block kb (see LinearTcArgs::group / lead_kb)
+__device__ __forceinline__ int group_len(int kb, int group, int lead_kb) { return (kb < lead_kb && group < 2) ? 2 : group; }
+
 struct LinearTcArgs {
     long long N;        // rows (samples)
     int out, Kp;        // output features (multiple of BN), padded reduction length (multiple of BK)
+    int y_tma;          // the FP16 output planes leave through TMA (maps.y_hi / y_lo valid; 128- and 256-wide tiles)
     int act;            // 0 none, 1 relu, 2 tanh
     int problems;       // independent problems of identical shape (1 for the encoder, 3 for the heads)
     int group;          // k-blocks accumulated in TMEM before a partial tile is promoted to FP32 registers
+    int lead_kb;        // the first lead_kb k-blocks of every tile are summed in PAIRS whatever `group` says: while the epilogue
+                        // warps are still converting and storing the previous tile (~5 k cycles) the MMA warp can run four
+                        // k-blocks (6.1 k cycles) ahead on the two accumulators instead of two
     float inv_scale[kMaxProblems];    // 1 / (power-of-two scale folded into the W planes)
     const float* bias[kMaxProblems];  // [out]
     __half* Yhi[kMaxProblems];        // [N][ldy] or null
@@ -88,6 +97,7 @@ struct LinearTcArgs {
 // operand maps of up to three problems: A_hi, A_lo, W_hi, W_lo each
 struct TcMaps {
     CUtensorMap a_hi[kMaxProblems], a_lo[kMaxProblems], w_hi[kMaxProblems], w_lo[kMaxProblems];
+    CUtensorMap y_hi[kMaxProblems], y_lo[kMaxProblems];   // output planes, 32-row x 64-column boxes (LinearTcArgs::y_tma)
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
@@ -209,6 +219,7 @@ __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&v)[8]) 
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
                  "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile, 128-byte swizzle, rows 128 B apart, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
@@ -255,7 +266,16 @@ __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uin
 
 // One thread's row of a finished tile: y = act(sum * inv_scale + bias), written as FP32 and/or as FP16 hi/lo planes.
 // `yf`, `dh`, `dl` point at this row's first column of the warp's column slice (null = not wanted).
-template <int ACT, int HALF>
+// four consecutive bias values: from the warp's shared-memory slice (64-wide tiles) or straight from global memory
+// through L1 (every lane reads the same address: one broadcast transaction; the 512 bytes stay L1-resident because
+// nothing else in these kernels allocates in L1 -- TMA, tcgen05 and the write-through stores all bypass it)
+template <bool SMEM>
+__device__ __forceinline__ float4 bias4(const float* p) {
+    if (SMEM) return *reinterpret_cast<const float4*>(p);
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+template <int ACT, int HALF, bool BIAS_SMEM>
 __device__ __forceinline__ void store_row(const float (&sum)[HALF], float inv_scale, const float* bias_s, float* yf, __half* dh,
                                           __half* dl) {
 #pragma unroll
@@ -263,7 +283,7 @@ __device__ __forceinline__ void store_row(const float (&sum)[HALF], float inv_sc
         float y[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + j);   // broadcast LDS.128
+            const float4 b = bias4<BIAS_SMEM>(bias_s + c0 + j);
             y[j] = act_fixed<ACT>(fmaf(sum[c0 + j], inv_scale, b.x));
             y[j + 1] = act_fixed<ACT>(fmaf(sum[c0 + j + 1], inv_scale, b.y));
             y[j + 2] = act_fixed<ACT>(fmaf(sum[c0 + j + 2], inv_scale, b.z));
@@ -294,6 +314,78 @@ __device__ __forceinline__ void store_row(const float (&sum)[HALF], float inv_sc
     }
 }
 
+
+// The same outputs as store_row's FP16 planes, leaving through TMA.  A thread owns one ROW of the tile (that is how
+// tcgen05.ld hands the accumulator over), so direct stores put every lane of a warp-wide store in a different line:
+// 32 packets of 32 B per instruction, ~6 k cycles per 128 x 256 tile during which the warp promotes nothing, and a
+// transpose through shared memory read back by the warp pays the shared-memory bandwidth twice on the warp's own
+// time (measured 4.4 k cycles).  Here each warp writes its 32 rows x 64 columns of one plane into a 4 KB buffer in
+// the 128-byte-swizzle layout (chunk c of row r at slot c ^ (r & 7): conflict-free) and one lane hands the box to
+// TMA, which drains it asynchronously while the warp converts the next 64 columns; rows past N are clipped by the
+// tensor map.  `bias` points at the warp's first column in GLOBAL memory; (col0, row0) is the box origin.
+// Issued by the whole converged warp with the elected lane predicated inside the asm block: an `if (lane == 0)` around
+// these makes nvcc wrap the uniform-datapath instruction in a divergence loop (1.1 k cycles per tile for four stores).
+// elect.sync picks the same leader for the same member mask, so the bulk groups are committed and awaited by one thread.
+__device__ __forceinline__ void tma_store_2d_elect(const CUtensorMap* map, const void* smem_src, int c_inner, int c_outer) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "@p cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n"
+        "@p cp.async.bulk.commit_group;\n"
+        "}"
+        ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer) : "memory");
+}
+template <int PENDING>
+__device__ __forceinline__ void tma_store_wait_read_elect() {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "@p cp.async.bulk.wait_group.read %0;\n"
+        "}" ::"n"(PENDING) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all_elect() {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "@p cp.async.bulk.wait_group 0;\n"
+        "}" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int ACT, int HALF>
+__device__ __forceinline__ void store_planes_tma(const float (&sum)[HALF], float inv_scale, const float* bias, uint4* buf,
+                                                 const CUtensorMap* map_hi, const CUtensorMap* map_lo, int col0, int row0,
+                                                 int lane) {
+    static_assert(HALF % 64 == 0, "64 columns of a plane per box");
+#pragma unroll
+    for (int c0 = 0; c0 < HALF; c0 += 64) {
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+            const float4 b = bias4<false>(bias + c0 + j);
+            const float y0 = act_fixed<ACT>(fmaf(sum[c0 + j], inv_scale, b.x)), y1 = act_fixed<ACT>(fmaf(sum[c0 + j + 1], inv_scale, b.y));
+            const float y2 = act_fixed<ACT>(fmaf(sum[c0 + j + 2], inv_scale, b.z)), y3 = act_fixed<ACT>(fmaf(sum[c0 + j + 3], inv_scale, b.w));
+            split_pair(y0, y1, hi[j / 2], lo[j / 2]);
+            split_pair(y2, y3, hi[j / 2 + 1], lo[j / 2 + 1]);
+        }
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            tma_store_wait_read_elect<0>();   // the previous box has left the buffer
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                buf[lane * 8 + (c ^ (lane & 7))] = p ? make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3])
+                                                     : make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+            fence_async_smem();
+            __syncwarp();
+            tma_store_2d_elect(p ? map_lo : map_hi, buf, col0 + c0, row0);
+        }
+    }
+}
+
 // CL = CTAs per cluster (1 or 2).  With CL = 2 the two CTAs of a cluster work on M-tiles (2p, 2p+1) of the same
 // N-tile: each loads its own A planes and HALF of the W tile, multicast into both CTAs' shared memory, which cuts
 // the L2->SMEM operand traffic per MMA by a third (the wide layers are L2-bandwidth bound at 128x256 tiles).
@@ -310,15 +402,18 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
     // lose the address space: the epilogue's bias reads became generic LD.E instead of LDS)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* stage_base = smem;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
+    constexpr size_t kStoreStage = BN >= 128 ? (size_t)kEpilogueWarps * kStoreStageBytes : 0;   // 1024-byte aligned (swizzle atoms)
+    uint4* stage_all = reinterpret_cast<uint4*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);     // [warp][32][8]  (BN >= 128 only)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + kStoreStage);
     uint64_t* full = bars;                    // [STAGES]  operand stage landed
     uint64_t* empty = bars + C::STAGES;       // [STAGES]  operand stage consumed by the MMAs
     uint64_t* tfull = bars + 2 * C::STAGES;   // [2]  partial accumulator of one k-block complete
     uint64_t* tempty = tfull + 2;             // [2]  partial accumulator drained into registers
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* bias_all = reinterpret_cast<float*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256);   // [warp][HALF], private per epilogue warp
-    float* dotw_all = bias_all + kEpilogueWarps * HALF;                                            // [warp][HALF]
-    float* dot_xch = dotw_all + kEpilogueWarps * HALF;                                             // [2][BM] partial dots of the upper column half
+    float* bias_all = reinterpret_cast<float*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + kStoreStage + 256);   // [warp][HALF], private per epilogue warp
+    constexpr bool kBiasSmem = BN == 64;   // the wider tiles read the bias through L1 and use the space for store staging
+    float* dotw_all = bias_all + (kBiasSmem ? kEpilogueWarps * HALF : 0);                          // [warp][HALF]  (BN == 64 only)
+    float* dot_xch = dotw_all + (kBiasSmem ? kEpilogueWarps * HALF : 0);                           // [2][BM] partial dots of the upper column half
     float* neck_w5s = dot_xch + 2 * BM;                                   // [9][64]          (BN == 64 only, see Cfg)
     float* neck_b5s = neck_w5s + kNeckLatent * 64;                        // [12]
     float4* neck_whs = reinterpret_cast<float4*>(neck_b5s + 12);          // [3][128] (w0, w1, w2, bias)
@@ -400,8 +495,12 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (long long t = first; t < num_tiles; t += step) {
+                int g_left = 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    const bool g_first = kb % a.group == 0, g_last = (kb % a.group == a.group - 1) || kb == num_kb - 1;
+                    const bool g_first = g_left == 0;
+                    if (g_first) g_left = group_len(kb, a.group, a.lead_kb);
+                    const bool g_last = --g_left == 0 || kb == num_kb - 1;
+                    if (g_last) g_left = 0;
                     if (g_first) mbar_wait(&tempty[acc], acc_phase ^ 1);
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
@@ -451,16 +550,20 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
             // this tile's bias (and dot weights) are fetched now and parked in shared memory after the promotion loop:
             // the L2 latency hides behind the accumulator waits instead of stalling the start of every tile
             float bias_r[(HALF + 31) / 32], dotw_r[(HALF + 31) / 32];
+            if constexpr (kBiasSmem) {
 #pragma unroll
-            for (int i = 0; i < (HALF + 31) / 32; ++i) {
-                const int j = lane + 32 * i;
-                bias_r[i] = j < HALF ? __ldg(bias + n0 + j) : 0.f;
-                dotw_r[i] = (dot_w && j < HALF) ? __ldg(dot_w + n0 + j) : 0.f;
+                for (int i = 0; i < (HALF + 31) / 32; ++i) {
+                    const int j = lane + 32 * i;
+                    bias_r[i] = j < HALF ? __ldg(bias + n0 + j) : 0.f;
+                    dotw_r[i] = (dot_w && j < HALF) ? __ldg(dot_w + n0 + j) : 0.f;
+                }
+            } else if (lane < HALF / 32) {
+                prefetch_l1(bias + n0 + lane * 32);   // the store phase reads the bias through L1
             }
             float sum[HALF];
 #pragma unroll
             for (int j = 0; j < HALF; ++j) sum[j] = 0.f;
-            for (int kb = 0; kb < num_kb; kb += a.group) {
+            for (int kb = 0; kb < num_kb; kb += group_len(kb, a.group, a.lead_kb)) {
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
@@ -479,13 +582,15 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
                 if (lane == 0) mbar_arrive(&tempty[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            __syncwarp();   // the previous tile's reads of the slices are done (same warp, program order + this fence)
+            if constexpr (kBiasSmem) {
+                __syncwarp();   // the previous tile's reads of the slices are done (same warp, program order + this fence)
 #pragma unroll
-            for (int i = 0; i < (HALF + 31) / 32; ++i) {
-                const int j = lane + 32 * i;
-                if (j < HALF) { bias_s[j] = bias_r[i]; dotw_s[j] = dotw_r[i]; }
+                for (int i = 0; i < (HALF + 31) / 32; ++i) {
+                    const int j = lane + 32 * i;
+                    if (j < HALF) { bias_s[j] = bias_r[i]; dotw_s[j] = dotw_r[i]; }
+                }
+                __syncwarp();
             }
-            __syncwarp();
             if constexpr (BN == 64) {
                 if (a.neck) {
                     // y = tanh(.) of this warp's 32 of the 64 columns -> partial latent -> exchange -> heads' first layers
@@ -549,13 +654,22 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
                 if (half == 0 && row < a.N) a.Ydot[row * a.ldd + z] = (part + *slot) + __ldg(a.dot_b[z]);
                 tile_parity ^= 1;
             }
+            if constexpr (BN >= 128) {
+                if (a.y_tma) {   // planes only (every layer of the chain but the last)
+                    uint4* buf = stage_all + (warp - kFirstEpilogueWarp) * (kStoreStageBytes / 16);
+                    NLML_ACT_DISPATCH(a.act, store_planes_tma<ACT, HALF>(sum, inv_scale, bias + n0, buf, &maps.y_hi[z], &maps.y_lo[z],
+                                                                         n0, (int)(row - lane), lane);)
+                    continue;
+                }
+            }
             if (row < a.N && (Yf32 || Yhi)) {
                 float* yf = Yf32 ? Yf32 + row * a.ldy + n0 : nullptr;
                 __half* dh = Yhi ? Yhi + row * a.ldy + n0 : nullptr;
                 __half* dl = Yhi ? Ylo + row * a.ldy + n0 : nullptr;
-                NLML_ACT_DISPATCH(a.act, store_row<ACT, HALF>(sum, inv_scale, bias_s, yf, dh, dl);)
+                NLML_ACT_DISPATCH(a.act, store_row<ACT, HALF, kBiasSmem>(sum, inv_scale, kBiasSmem ? bias_s : bias + n0, yf, dh, dl);)
             }
         }
+        if (BN >= 128 && a.y_tma) tma_store_wait_all_elect();   // the last boxes are out before the CTA retires
     }
     tc_fence_before();
     __syncthreads();
@@ -595,7 +709,8 @@ struct Cfg2 {
     static constexpr int W_BYTES = (BN / 2) * BK * 2;      // one plane of this CTA's half of the W tile (128 rows)
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;   // 64 KB
     static constexpr int TMEM_COLS = 2 * BN;
-    static constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256 + kEpilogueWarps * (BN / 2) * 4 /*bias*/;
+    static constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256 +
+                                         kEpilogueWarps * kStoreStageBytes /*line-forming store staging*/;
 };
 
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int c_inner, int c_outer, uint64_t* leader_bar) {
@@ -653,13 +768,13 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
     // lose the address space: the epilogue's bias reads became generic LD.E instead of LDS)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* stage_base = smem;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
+    uint4* stage_all = reinterpret_cast<uint4*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);   // [warp][32][8] store staging, 1024-byte aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + kEpilogueWarps * kStoreStageBytes);
     uint64_t* full = bars;                    // [STAGES]  (leader's copy is the live one) both CTAs' operand stage landed
     uint64_t* empty = bars + C::STAGES;       // [STAGES]  (own) stage consumed by the pair's MMAs
     uint64_t* tfull = bars + 2 * C::STAGES;   // [2]  (own) partial accumulator of one k-block complete
     uint64_t* tempty = tfull + 2;             // [2]  (leader's copy) drained by all 16 epilogue warps of the pair
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* bias_all = reinterpret_cast<float*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256);   // [warp][HALF], private per epilogue warp
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const uint32_t crank = cluster_ctarank();
@@ -716,8 +831,12 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (long long t = first; t < num_tiles; t += step) {
+                int g_left = 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    const bool g_first = kb % a.group == 0, g_last = (kb % a.group == a.group - 1) || kb == num_kb - 1;
+                    const bool g_first = g_left == 0;
+                    if (g_first) g_left = group_len(kb, a.group, a.lead_kb);
+                    const bool g_last = --g_left == 0 || kb == num_kb - 1;
+                    if (g_last) g_left = 0;
                     if (g_first) mbar_wait(&tempty[acc], acc_phase ^ 1);
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
@@ -760,15 +879,12 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
             float* __restrict__ Yf32 = a.Yf32[z];
             __half* __restrict__ Yhi = a.Yhi[z];
             __half* __restrict__ Ylo = a.Ylo[z];
-            float* bias_s = bias_all + (warp - kFirstEpilogueWarp) * HALF;   // this warp's slice of the bias, read back as broadcasts
-            float bias_r[HALF / 32];   // fetched now, parked in shared memory after the promotion loop (latency hidden)
-#pragma unroll
-            for (int i = 0; i < HALF / 32; ++i) bias_r[i] = __ldg(bias + n0 + lane + 32 * i);
+            if (lane < HALF / 32) prefetch_l1(bias + n0 + lane * 32);   // the store phase reads the bias through L1
             NLML_MT_STAMP(0);
             float sum[HALF];
 #pragma unroll
             for (int j = 0; j < HALF; ++j) sum[j] = 0.f;
-            for (int kb = 0; kb < num_kb; kb += a.group) {
+            for (int kb = 0; kb < num_kb; kb += group_len(kb, a.group, a.lead_kb)) {
                 mbar_wait(&tfull[acc], acc_phase);
                 tc_fence_after();
                 NLML_MT_STAMP(1);
@@ -789,21 +905,22 @@ linear_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ L
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 NLML_MT_STAMP(2);
             }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < HALF / 32; ++i) bias_s[lane + 32 * i] = bias_r[i];
-            __syncwarp();
-            if (row < a.N) {
+            if (a.y_tma) {   // planes only (every layer of the chain but the last)
+                uint4* buf = stage_all + (warp - kFirstEpilogueWarp) * (kStoreStageBytes / 16);
+                NLML_ACT_DISPATCH(a.act, store_planes_tma<ACT, HALF>(sum, inv_scale, bias + n0, buf, &maps.y_hi[z], &maps.y_lo[z], n0,
+                                                                     (int)(row - lane), lane);)
+            } else if (row < a.N) {
                 float* yf = Yf32 ? Yf32 + row * a.ldy + n0 : nullptr;
                 __half* dh = Yhi ? Yhi + row * a.ldy + n0 : nullptr;
                 __half* dl = Yhi ? Ylo + row * a.ldy + n0 : nullptr;
-                NLML_ACT_DISPATCH(a.act, store_row<ACT, HALF>(sum, inv_scale, bias_s, yf, dh, dl);)
+                NLML_ACT_DISPATCH(a.act, store_row<ACT, HALF, false>(sum, inv_scale, bias + n0, yf, dh, dl);)
             }
             NLML_MT_STAMP(3);
 #ifdef NLML_MLP_TIMING
             ++mt_tiles;
 #endif
         }
+        if (a.y_tma) tma_store_wait_all_elect();   // the last boxes are out before the CTA retires
 #ifdef NLML_MLP_TIMING
         if (lane == 0 && a.timing && mt_tiles > 0)
             for (int i = 0; i < 4; ++i)
