@@ -466,7 +466,12 @@ int forward_chunk(nlml_mlp_plan* pl, const float* X, int64_t n, int64_t ldx, flo
         if (int rc = tc::make_plane_map(&maps.a_lo[0], cur_lo, n, a.Kp, a.Kp, tc::BM)) return rc;
         maps.w_hi[0] = pl->wmap_hi[t4]; maps.w_lo[0] = pl->wmap_lo[t4];
         for (int z = 1; z < tc::kMaxProblems; ++z) { maps.a_hi[z] = maps.a_hi[0]; maps.a_lo[z] = maps.a_lo[0]; maps.w_hi[z] = maps.w_hi[0]; maps.w_lo[z] = maps.w_lo[0]; }
-        for (int z = 0; z < tc::kMaxProblems; ++z) { maps.y_hi[z] = maps.a_hi[0]; maps.y_lo[z] = maps.a_lo[0]; }   // y_tma = 0: never dereferenced
+        a.y_tma = 1;   // the heads' first-layer planes leave through TMA (32-row x 64-column boxes, maps per head)
+        for (int h = 0; h < 3; ++h) {
+            const size_t off = (size_t)h * w.rows * kHeadW;
+            if (int rc = tc::make_plane_map(&maps.y_hi[h], w.hi[0] + off, n, kHeadW, kHeadW, 32)) return rc;
+            if (int rc = tc::make_plane_map(&maps.y_lo[h], w.lo[0] + off, n, kHeadW, kHeadW, 32)) return rc;
+        }
         a.inv_scale[0] = pl->inv_scale[t4]; a.bias[0] = pl->B[t4];
         a.neck = 1; a.neck_w5 = pl->W[5]; a.neck_b5 = pl->B[5];
         a.neck_lat = LAT_out ? LAT_out : w.lat;

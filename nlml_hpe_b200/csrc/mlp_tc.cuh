@@ -51,7 +51,7 @@ struct Cfg {
     static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ +
                                          (BN == 64 ? 2 * kEpilogueWarps * (BN / 2) * 4 : 0) /*bias, dot weights*/ + 2 * BM * 4 /*dot exchange*/ +
                                          (BN == 64 ? kNeckSmemFloats * 4 : 0) /*fused neck epilogue*/ +
-                                         (BN >= 128 ? kEpilogueWarps * kStoreStageBytes : 0) /*line-forming store staging*/;
+                                         kEpilogueWarps * kStoreStageBytes /*store staging (TMA)*/;
 };
 
 constexpr int kMaxProblems = 3;   // the three heads ride one launch
@@ -355,6 +355,18 @@ __device__ __forceinline__ void tma_store_wait_all_elect() {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// one 32-row x 64-column box of a plane: this thread's 32 words (64 halves of its row) -> swizzled buffer -> TMA
+__device__ __forceinline__ void stage_box_tma(uint4* buf, const uint32_t (&w)[32], const CUtensorMap* map, int col, int row0,
+                                              int lane) {
+    tma_store_wait_read_elect<0>();   // the previous box has left the buffer
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) buf[lane * 8 + (c ^ (lane & 7))] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+    fence_async_smem();
+    __syncwarp();
+    tma_store_2d_elect(map, buf, col, row0);
+}
+
 template <int ACT, int HALF>
 __device__ __forceinline__ void store_planes_tma(const float (&sum)[HALF], float inv_scale, const float* bias, uint4* buf,
                                                  const CUtensorMap* map_hi, const CUtensorMap* map_lo, int col0, int row0,
@@ -371,18 +383,8 @@ __device__ __forceinline__ void store_planes_tma(const float (&sum)[HALF], float
             split_pair(y0, y1, hi[j / 2], lo[j / 2]);
             split_pair(y2, y3, hi[j / 2 + 1], lo[j / 2 + 1]);
         }
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            tma_store_wait_read_elect<0>();   // the previous box has left the buffer
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                buf[lane * 8 + (c ^ (lane & 7))] = p ? make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3])
-                                                     : make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-            fence_async_smem();
-            __syncwarp();
-            tma_store_2d_elect(p ? map_lo : map_hi, buf, col0 + c0, row0);
-        }
+        stage_box_tma(buf, hi, map_hi, col0 + c0, row0, lane);
+        stage_box_tma(buf, lo, map_lo, col0 + c0, row0, lane);
     }
 }
 
@@ -402,8 +404,8 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
     // lose the address space: the epilogue's bias reads became generic LD.E instead of LDS)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* stage_base = smem;
-    constexpr size_t kStoreStage = BN >= 128 ? (size_t)kEpilogueWarps * kStoreStageBytes : 0;   // 1024-byte aligned (swizzle atoms)
-    uint4* stage_all = reinterpret_cast<uint4*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);     // [warp][32][8]  (BN >= 128 only)
+    constexpr size_t kStoreStage = (size_t)kEpilogueWarps * kStoreStageBytes;                    // 1024-byte aligned (swizzle atoms)
+    uint4* stage_all = reinterpret_cast<uint4*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);     // [warp][32][8]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + kStoreStage);
     uint64_t* full = bars;                    // [STAGES]  operand stage landed
     uint64_t* empty = bars + C::STAGES;       // [STAGES]  operand stage consumed by the MMAs
@@ -612,31 +614,29 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
                     for (int m = 0; m < kNeckLatent; ++m)
                         lat[m] = (neck_xch[m * BM + r] + neck_xch[(kNeckLatent + m) * BM + r]) + neck_b5s[m];
                     asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // exchange buffer free for the next tile
-                    if (row < a.N) {
-                        if (half == 0 && a.neck_lat) {
+                    if (row < a.N && half == 0 && a.neck_lat) {
 #pragma unroll
-                            for (int m = 0; m < kNeckLatent; ++m) a.neck_lat[row * kNeckLatent + m] = lat[m];
-                        }
-                        // 3 x 128 first-hidden-layer outputs per row; each column half takes 192 of them, 16 at a time
+                        for (int m = 0; m < kNeckLatent; ++m) a.neck_lat[row * kNeckLatent + m] = lat[m];
+                    }
+                    // 3 x 128 first-hidden-layer outputs per row; each column half takes 192 of them = three 64-column boxes
+                    // (each inside one head), staged and handed to TMA like the wide tiles' planes (rows past N are clipped)
+                    uint4* buf = stage_all + (warp - kFirstEpilogueWarp) * (kStoreStageBytes / 16);
 #pragma unroll 1
-                        for (int g = 0; g < 12; ++g) {
-                            const int o0 = half * 192 + 16 * g, h = o0 / kNeckHeadW, j0 = o0 % kNeckHeadW;
-                            const float l0 = h == 0 ? lat[0] : (h == 1 ? lat[3] : lat[6]);
-                            const float l1 = h == 0 ? lat[1] : (h == 1 ? lat[4] : lat[7]);
-                            const float l2 = h == 0 ? lat[2] : (h == 1 ? lat[5] : lat[8]);
-                            uint32_t hi[8], lo[8];
+                    for (int bi = 0; bi < 3; ++bi) {
+                        const int o0 = half * 192 + 64 * bi, h = o0 / kNeckHeadW, j0 = o0 % kNeckHeadW;
+                        const float l0 = h == 0 ? lat[0] : (h == 1 ? lat[3] : lat[6]);
+                        const float l1 = h == 0 ? lat[1] : (h == 1 ? lat[4] : lat[7]);
+                        const float l2 = h == 0 ? lat[2] : (h == 1 ? lat[5] : lat[8]);
+                        uint32_t hi[32], lo[32];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float4 w0 = neck_whs[h * kNeckHeadW + j0 + 2 * e], w1 = neck_whs[h * kNeckHeadW + j0 + 2 * e + 1];
-                                const float v0 = fmaxf(fmaf(l2, w0.z, fmaf(l1, w0.y, fmaf(l0, w0.x, w0.w))), 0.f);
-                                const float v1 = fmaxf(fmaf(l2, w1.z, fmaf(l1, w1.y, fmaf(l0, w1.x, w1.w))), 0.f);
-                                split_pair(v0, v1, hi[e], lo[e]);
-                            }
-                            __half* dh = (h == 0 ? a.neck_hi[0] : (h == 1 ? a.neck_hi[1] : a.neck_hi[2])) + row * kNeckHeadW + j0;
-                            __half* dl = (h == 0 ? a.neck_lo[0] : (h == 1 ? a.neck_lo[1] : a.neck_lo[2])) + row * kNeckHeadW + j0;
-                            st_global_v8(dh, hi);
-                            st_global_v8(dl, lo);
+                        for (int e = 0; e < 32; ++e) {
+                            const float4 w0 = neck_whs[h * kNeckHeadW + j0 + 2 * e], w1 = neck_whs[h * kNeckHeadW + j0 + 2 * e + 1];
+                            const float v0 = fmaxf(fmaf(l2, w0.z, fmaf(l1, w0.y, fmaf(l0, w0.x, w0.w))), 0.f);
+                            const float v1 = fmaxf(fmaf(l2, w1.z, fmaf(l1, w1.y, fmaf(l0, w1.x, w1.w))), 0.f);
+                            split_pair(v0, v1, hi[e], lo[e]);
                         }
+                        stage_box_tma(buf, hi, &maps.y_hi[h], j0, (int)(row - lane), lane);
+                        stage_box_tma(buf, lo, &maps.y_lo[h], j0, (int)(row - lane), lane);
                     }
                 }
             }
@@ -669,7 +669,7 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
                 NLML_ACT_DISPATCH(a.act, store_row<ACT, HALF, kBiasSmem>(sum, inv_scale, kBiasSmem ? bias_s : bias + n0, yf, dh, dl);)
             }
         }
-        if (BN >= 128 && a.y_tma) tma_store_wait_all_elect();   // the last boxes are out before the CTA retires
+        if (a.y_tma) tma_store_wait_all_elect();   // the last boxes are out before the CTA retires
     }
     tc_fence_before();
     __syncthreads();

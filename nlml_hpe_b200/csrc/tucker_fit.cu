@@ -939,7 +939,12 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         float acc[RH];
 #pragma unroll
         for (int r = 0; r < RH; ++r) acc[r] = 0.f;
-        for (int f0 = 0; f0 < F; f0 += C::FC) {
+        if (a.Qpre) {   // projected already by tucker_project_tc_kernel: coalesced reads of this CTA's [RPAD][128] slab
+            const float* slab = a.Qpre + (size_t)blockIdx.x * C::RPAD * 128 + (size_t)role * RH * 128 + row;
+#pragma unroll
+            for (int r = 0; r < RH; ++r) acc[r] = __ldg(slab + r * 128);
+        }
+        for (int f0 = 0; f0 < (a.Qpre ? 0 : F); f0 += C::FC) {
             for (int idx = tid; idx < C::THREADS * (C::FC / 4); idx += 256) {
                 const int s = idx / (C::FC / 4), c4 = idx % (C::FC / 4);
                 const long long grow = s0 + s;
@@ -1844,8 +1849,12 @@ int launch_gen(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int
     return 0;
 }
 
+constexpr int64_t kProjMinRows = 4096;   // below this the consumer's own phase A is as fast (one partial wave)
+int project_tc(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, cudaStream_t st, const float** Qout,
+               int64_t min_rows = kProjMinRows);
+
 int launch_fit(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int iters, float lr, float clip,
-               float* P, int64_t ldp, int hint, cudaStream_t st, int ws_slot = 2) {
+               float* P, int64_t ldp, int hint, cudaStream_t st, int ws_slot = 2, int64_t proj_min_rows = kProjMinRows) {
     if (N == 0) return 0;
     // run-time-rank tensor-core kernel: asked for, or the default for every rank set without compiled kernels
     if (hint == 6 && !pl->gen_ok)
@@ -1878,7 +1887,10 @@ int launch_fit(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int
     if ((hint == 1 || hint == 3 || hint == 4 || hint == 5) && !pl->fast)
         return set_error(NLML_E_UNSUPPORTED, "thread/warp-per-sample kernels are built for ranks (5,3,3,3) only");
     if (use_tc) {
+        // phase A (q = W2 x) as a 3xTF32 tcgen05 GEMM of its own when the layout allows TMA; the kernel then only copies its slab
+        if (int rc = project_tc(pl, X, N, ldx, st, &a.Qpre, proj_min_rows)) return rc;
         tucker_fit_tc_kernel<<<(unsigned)ceil_div(N, TcFitCfg::THREADS), 2 * TcFitCfg::THREADS, TcFitCfg::SMEM_BYTES, st>>>(a);
+        if (a.Qpre) NLML_CUDA(cudaEventRecord(pl->q_pre_done, st));
     } else if (use_wps) {
         auto kern = tucker_fit_wps_kernel<5, 3, 3, 3, kWpsWarps>;
         const unsigned grid = (unsigned)ceil_div(N, kWpsWarps);
@@ -1905,8 +1917,7 @@ int launch_fit(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, int
 typedef CUresult (*EncodeTiledFnT)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-constexpr int64_t kProjMinRows = 4096;   // below this the consumer's own phase A is as fast (one partial wave)
-int project_tc(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, cudaStream_t st, const float** Qout, int64_t min_rows = kProjMinRows) {
+int project_tc(nlml_tucker_plan* pl, const float* X, int64_t N, int64_t ldx, cudaStream_t st, const float** Qout, int64_t min_rows) {
     *Qout = nullptr;
     if (!pl->fast || !pl->proj_tiles || N < min_rows || (ldx % 4) != 0 || (reinterpret_cast<uintptr_t>(X) & 15) != 0) return 0;
     static EncodeTiledFnT encode = nullptr;
@@ -2234,8 +2245,9 @@ extern "C" int nlml_tucker_fit_host_f32(nlml_tucker_plan* pl, const float* X_hos
     const int np = 3 + pl->ri;
     // every chunk runs the kernel the whole batch would get (the first chunks of the ramp are below the cross-over)
     const int hint = (pl->fast && N >= tc_crossover(pl)) ? 5 : 0;
+    const int64_t proj_min = hint == 5 ? 1 : kProjMinRows;   // ... and the phase A the whole batch would get
     return host_pipeline(pl, X_host, N, ldx, P_out_host, ldp, [&](const float* x, int64_t n, float* p, cudaStream_t st, int slot) {
-        return launch_fit(pl, x, n, pl->F, iters, lr, clip, p, np, hint, st, slot);
+        return launch_fit(pl, x, n, pl->F, iters, lr, clip, p, np, hint, st, slot, proj_min);
     });
 }
 
