@@ -33,19 +33,21 @@ TUCKER_FMA_PER_ITER = 216 * 33 + 36 * 3 + 52 + 351 + 60
 TUCKER_FLOP_PER_POSE = 2 * (135 * F + T_ITERS * TUCKER_FMA_PER_ITER)
 TUCKER_FLOP_PER_POSE_GRAM = 2 * 135 * F + T_ITERS * (2 * 135 * 135 + 2000)
 TUCKER_FLOP_PER_POSE_REFERENCE = T_ITERS * 2 * 2 * 135 * F
-# tensor-core kernel: issued TF32 flops per pose (two GEMMs per iteration, 3 MMAs per MAC)
+# tensor-core kernel: issued FP16 flops per pose (two GEMMs per iteration, three hi/lo passes per MAC)
 # one Newton evaluation: per S row (216) 15 FMA for T + 4x15 FMA for GU/HY/HP/HR + 20 for the scalar sums,
 # linear term 5*3*(6*9) FMA + assembly
 SOLVE_FLOP_PER_EVAL = 2 * (216 * (15 + 60 + 20) + 5 * 3 * 54 + 400)
-TUCKER_TC_FLOP_PER_POSE = T_ITERS * 2 * 3 * (224 * 16 + 96 * 40)      # ISSUED: 3xTF32 passes and padding included
-TUCKER_TC_USEFUL_FLOP_PER_POSE = T_ITERS * 2 * (2 * 15 * 216)          # USEFUL: the two contractions with the folded Gram tensor
+TUCKER_TC_FLOP_PER_POSE = T_ITERS * 2 * 3 * (224 * 16 + 96 * 48) + 2 * 3 * 144 * 1408   # ISSUED: three FP16 hi/lo passes and padding
+                                                                                          # (+ phase A: 3xTF32 projection, 144 x 1408 padded)
+TUCKER_TC_USEFUL_FLOP_PER_POSE = T_ITERS * 2 * (2 * 15 * 216) + 2 * 135 * F   # USEFUL: the two contractions with the folded Gram tensor + q = W2 x
 TUCKER_BYTES_PER_POSE = F * 4 + 8 * 4
-# DRAM traffic of tucker_fit_tc_kernel per sample, from the committed `ncu --set full` capture (profiles/r01_tucker_tc_ncu.txt:
-# dram__bytes_read 218.43 MB + dram__bytes_write 5.36 MB for a 37 888-sample launch); scaled to the bench launch
-TUCKER_TC_NCU_DRAM_BYTES_PER_POSE = (218.431232e6 + 5.357056e6) / 37888
+# DRAM traffic of the fit (projection GEMM + iteration kernel) per sample, from the committed `ncu --set full` capture of a
+# 37 888-sample batch; scaled to the bench launch
+TUCKER_TC_NCU_SOURCE = "profiles/r02_tucker_tc_final_ncu.txt"
+TUCKER_TC_NCU_DRAM_BYTES_PER_POSE = (222.596608e6 + 14.701824e6 + 20.696064e6 + 0.0) / 37888   # projection read + write, fit read + write
 # DRAM traffic of the Encoder+heads chain per sample: ncu dram__bytes_read.sum + dram__bytes_write.sum over the nine launches of
 # one 151 552-sample chunk (profiles/r02_mlp_launches.txt: 3915.8 MB read + 2593.0 MB written)
-MLP_NCU_DRAM_BYTES_PER_POSE = (3915.81312e6 + 2593.049344e6) / 151552
+MLP_NCU_DRAM_BYTES_PER_POSE = (3897.6e6 + 2588.9e6) / 151552   # profiles/r02_mlp_launches.txt: DRAM read + write of one chunk's nine launches
 MLP_FLOP_PER_POSE = 4_714_240
 MLP_BYTES_PER_POSE = F * 4 + 3 * 4
 
@@ -613,21 +615,23 @@ def run_b200(args):
                 "api": "nlml_tucker_fit_host_f32 (TuckerFitter.fit_host), pinned host X -> host P"},
         "gpu_launches": int(t_launches),
         "roofline": {"bound": "tensor", "achieved": per_gpu_t * TUCKER_TC_USEFUL_FLOP_PER_POSE / 1e12,
-                     "peak": tf32_peak, "unit": "TFLOP/s",
-                     "frac": per_gpu_t * TUCKER_TC_USEFUL_FLOP_PER_POSE / 1e12 / tf32_peak,
-                     "issued_frac": per_gpu_t * TUCKER_TC_FLOP_PER_POSE / 1e12 / tf32_peak, "mma_passes": 3,
+                     "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": per_gpu_t * TUCKER_TC_USEFUL_FLOP_PER_POSE / 1e12 / peaks["bf16_tflops_sustained"],
+                     "issued_frac": per_gpu_t * TUCKER_TC_FLOP_PER_POSE / 1e12 / peaks["bf16_tflops_sustained"], "mma_passes": 3,
                      "traffic": TUCKER_TC_NCU_DRAM_BYTES_PER_POSE * n,
-                     "traffic_note": "bytes per launch = ncu dram__bytes_read+write of a 37 888-sample launch (profiles/r01_tucker_tc_ncu.txt), "
-                                     f"{TUCKER_TC_NCU_DRAM_BYTES_PER_POSE:.0f} B/sample against {TUCKER_BYTES_PER_POSE} algorithmic, x samples per launch",
-                     "kernel": "tucker_fit_tc_kernel",
-                     "peak_source": "measured live: nlml_measure_tf32_tflops (dense TF32 tcgen05 probe, all SMs)",
+                     "traffic_note": "bytes per launch = ncu dram__bytes_read+write of tucker_project_tc_kernel + tucker_fit_tc_kernel on a "
+                                     f"37 888-sample batch ({TUCKER_TC_NCU_SOURCE}), {TUCKER_TC_NCU_DRAM_BYTES_PER_POSE:.0f} B/sample against "
+                                     f"{TUCKER_BYTES_PER_POSE} algorithmic (q = 136 floats per sample crosses HBM between the two kernels), x samples per launch",
+                     "kernel": "tucker_fit_tc_kernel (+ tucker_project_tc_kernel for phase A)",
+                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}): the iteration's MMAs are kind::f16 "
+                                    "(FP16 hi/lo operand split, FP32 accumulate), same tensor rate as bf16",
                      "note": f"frac = USEFUL flops ({TUCKER_TC_USEFUL_FLOP_PER_POSE / 1e6:.1f} MFLOP/pose: T x 2 x (2 x 15 x 216), the two contractions "
-                             "with the folded Gram tensor) / measured TF32 peak -- the same convention as mlp.roofline.frac; issued_frac counts "
-                             "the 3xTF32 passes and the operand padding (per sample-iteration two GEMM rows, 128x224x16 and 128x96x40 per 128 "
-                             f"samples, 3 MMAs per MAC = {TUCKER_TC_FLOP_PER_POSE / 1e6:.1f} MFLOP/pose). The tensor pipe is NOT "
+                             "with the folded Gram tensor, + the projection q = W2 x) / sustained dense 16-bit tensor peak -- the same convention as "
+                             "mlp.roofline.frac; issued_frac counts the three hi/lo passes and the operand padding (per iteration 128x224x16 and "
+                             f"128x96x48 per 128 samples, 3 MMAs per MAC = {TUCKER_TC_FLOP_PER_POSE / 1e6:.1f} MFLOP/pose). The tensor pipe is NOT "
                              "the binding unit of this kernel (ncu: tensor pipe ~31 % active): each iteration is a serial chain "
-                             "features -> operand rows -> GEMMs -> tcgen05.ld -> gradient -> step, and the kernel is bound by that "
-                             "chain's latency plus the FP32 work left on the CUDA cores (roofline_fp32)."},
+                             "features -> operand rows -> GEMMs -> tcgen05.ld -> gradient -> step on two warps per SM sub-partition, and the "
+                             "kernel is bound by that chain's latency plus the FP32 work left on the CUDA cores (roofline_fp32; DESIGN.md 3a)."},
         "roofline_fp32": {"bound": "fp32_fma", "achieved": per_gpu_t * TUCKER_FLOP_PER_POSE / 1e12, "peak": fp32_peak,
                           "unit": "TFLOP/s", "frac": per_gpu_t * TUCKER_FLOP_PER_POSE / 1e12 / fp32_peak,
                           "peak_3reg": fp32_peak_3reg, "frac_3reg": per_gpu_t * TUCKER_FLOP_PER_POSE / 1e12 / fp32_peak_3reg,
