@@ -804,7 +804,7 @@ struct TcFitCfg {
     static constexpr int OFF_Q = OFF_AV + 2 * AV_BYTES;                // phase-A tiles [FC][XSTR] + [FC][RPAD]
     static constexpr int OFF_BAR = OFF_Q + (FC * XSTR + FC * RPAD) * 4;
     static constexpr int OFF_GX = OFF_BAR + 64;                        // exchange between the two roles [NGX][128] floats
-    static constexpr int NGX = 8 + 15;                                 // 8 gradient parts + role 1's partial GR, GP, GY
+    static constexpr int NGX = 9;                                      // 8 gradient parts + the identity thread's part of d/d(yaw)
     static constexpr size_t SMEM_BYTES = OFF_GX + NGX * THREADS * 4;
     static constexpr int TMEM_COLS = 512;
     static constexpr int COL_T = 0, COL_V = 224, COL_Q = 320, COL_A1 = 456;   // A1: the T GEMM's A operand (UU hi | lo, 2 x 8 columns of packed halves)
@@ -878,6 +878,28 @@ __device__ __forceinline__ void tc_reduce_t(uint32_t taddr, const float (&YY)[6]
             GP[c] = fmaf(tr[bl * 6 + c], YY[B0 + bl], GP[c]);
         }
         GY3[bl] = gy;
+    }
+}
+
+// All of T contracted over b first: s[c,d] = sum_b T[b,c,d] * YYk[b] (216 FMAs; YYk carries the inverse operand scales).
+// GR[d] = sum_c PP_c s[c,d] and GP[c] = sum_d RR_d s[c,d] follow from it (72 FMAs); GY comes from the V accumulator
+// (GY[b] = sum_A UU_A V[A,b], on the identity thread).  The earlier form (tr[b,c] = sum_d T RR_d for GY and GP, plus
+// GR on its own) took 504 FMAs on the angle thread.
+__device__ __forceinline__ void tc_reduce_t_b(uint32_t taddr, const float (&YYk)[6], float (&s)[36]) {
+#pragma unroll
+    for (int i = 0; i < 36; ++i) s[i] = 0.f;
+    constexpr int NL = 7;   // 224 columns, 216 used
+    uint32_t buf[2][32];
+    tmem_load32_async(taddr, buf[0]);
+#pragma unroll
+    for (int ci = 0; ci < NL; ++ci) {
+        tmem_load_wait();
+        if (ci + 1 < NL) tmem_load32_async(taddr + 32 * (ci + 1), buf[(ci + 1) & 1]);
+#pragma unroll
+        for (int x = 0; x < 32; ++x) {
+            const int bcd = 32 * ci + x;
+            if (bcd < 216) s[bcd % 36] = fmaf(__uint_as_float(buf[ci & 1][x]), YYk[bcd / 36], s[bcd % 36]);
+        }
     }
 }
 
@@ -1111,14 +1133,20 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         NLML_TSTAMP(2);   // yaw features + linear term
         if (role == 1) {
             // V[A,b] = sum_{c,D} PP_c RR_D S[A,b,c,D]  ->  GU[A] = sum_b YY_b V[A,b]  ->  d/du
-            float GU[15], YYk[6];
+            //                                          and  GY[b] = sum_A UU_A V[A,b]  ->  the quadratic part of d/d(yaw)
+            float GU[15], GYv[6], YYk[6], UUk[15];
             {
                 const float kv = __int_as_float((127 - a.s_exp - a.pr_exp) << 23);   // 2^-(s_exp + pr_exp): the V accumulator's scale off
 #pragma unroll
                 for (int i = 0; i < 6; ++i) YYk[i] = YY[i] * kv;
+                sym_products<5>(u, UUk);
+#pragma unroll
+                for (int i = 0; i < 15; ++i) UUk[i] *= kv;
             }
 #pragma unroll
             for (int i = 0; i < 15; ++i) GU[i] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) GYv[i] = 0.f;
             if (NLML_DBG_MMA) ttc::mbar_wait(bar + 1, phase);   // V GEMM
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             NLML_TSTAMP(3);   // wait for the GEMM
@@ -1132,44 +1160,50 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
 #pragma unroll
                     for (int x = 0; x < 32; ++x) {
                         const int n = 32 * ci + x;
-                        if (n < 90) GU[n / 6] = fmaf(__uint_as_float(vb[ci & 1][x]), YYk[n % 6], GU[n / 6]);
+                        if (n < 90) {
+                            const float v = __uint_as_float(vb[ci & 1][x]);
+                            GU[n / 6] = fmaf(v, YYk[n % 6], GU[n / 6]);
+                            GYv[n % 6] = fmaf(v, UUk[n / 6], GYv[n % 6]);
+                        }
                     }
                 }
             }
-            float du[5];
+            float du[5], dy[3];
             sym_backprop<5>(GU, u, du);
+            sym_backprop<3>(GYv, cy, dy);
 #pragma unroll
             for (int i = 0; i < 5; ++i) gx[(3 + i) * 128 + row] = du[i] - lin_u[i];
+            gx[8 * 128 + row] = fmaf(dy[2], dcy[2], fmaf(dy[1], dcy[1], dy[0] * dcy[0]));   // the angle thread adds -ey.dcy
         } else {
-            // all of T -> GR, GP, GY -> d/d(yaw, pitch, roll)
-            float GR[6], GP[6], GY[6], GR2[6], GP2[6], GY3[3], PPk[6], RRk[8];
+            // all of T -> s[c,d] -> GR, GP -> d/d(pitch, roll); d/d(yaw): the linear part here, the quadratic part on the identity thread
+            float GR[6], GP[6], sc[36], YYk[6];
             {
                 const float kt = __int_as_float((127 - a.s_exp - uu_exp) << 23);   // 2^-(s_exp + uu_exp): the T accumulator's scale off
 #pragma unroll
-                for (int i = 0; i < 6; ++i) { PPk[i] = PP[i] * kt; RRk[i] = RRv[i] * kt; }
-                RRk[6] = RRk[7] = 0.f;
+                for (int i = 0; i < 6; ++i) YYk[i] = YY[i] * kt;
             }
             if (NLML_DBG_MMA) ttc::mbar_wait(bar, phase);       // T GEMM (launched first, long done)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             NLML_TSTAMP(3);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) GR[i] = GP[i] = 0.f;
             if (NLML_DBG_READ) {
-                tc_reduce_t<0>(lane_addr + C::COL_T, YY, PP, PPk, RRk, GR, GP, GY3);
+                tc_reduce_t_b(lane_addr + C::COL_T, YYk, sc);
 #pragma unroll
-                for (int i = 0; i < 3; ++i) GY[i] = GY3[i];
-                tc_reduce_t<3>(lane_addr + C::COL_T, YY, PP, PPk, RRk, GR2, GP2, GY3);
+                for (int c = 0; c < 6; ++c)
 #pragma unroll
-                for (int i = 0; i < 3; ++i) GY[3 + i] = GY3[i];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) { GR[i] += GR2[i]; GP[i] += GP2[i]; }
+                    for (int d = 0; d < 6; ++d) {
+                        GR[d] = fmaf(PP[c], sc[c * 6 + d], GR[d]);
+                        GP[c] = fmaf(RRv[d], sc[c * 6 + d], GP[c]);
+                    }
             }
-            float dy[3], dp[3], dr[3];
-            sym_backprop<3>(GY, cy, dy);
+            float dp[3], dr[3];
             sym_backprop<3>(GP, cp, dp);
             sym_backprop<3>(GR, cr, dr);
             float gy = 0.f, gp = 0.f, gr = 0.f;
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                gy = fmaf(dy[j] - ey[j], dcy[j], gy);
+                gy = fmaf(-ey[j], dcy[j], gy);
                 gp = fmaf(dp[j] - ep[j], dcp[j], gp);
                 gr = fmaf(dr[j] - er[j], dcr[j], gr);
             }
@@ -1185,6 +1219,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         float g[C::NP];
 #pragma unroll
         for (int i = 0; i < C::NP; ++i) g[i] = gx[i * 128 + row];
+        g[0] += gx[8 * 128 + row];   // d/d(yaw) = linear part (angle thread) + quadratic part (identity thread)
         clip_and_step<C::NP>(p, g, lr, clip);
         NLML_TSTAMP(6);   // clip + step
     }
