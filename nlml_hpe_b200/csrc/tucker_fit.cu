@@ -1080,8 +1080,8 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         }
         NLML_TSTAMP(0);   // role 0: UU publish + T GEMM issue
         // pitch and roll features first: they are all the V GEMM's operand needs; yaw follows once it is launched
-        cos_features_fast<3>(p[1], a.rows_p, cp, dcp);
-        cos_features_fast<3>(p[2], a.rows_r, cr, dcr);
+        cos_features_sfu<3>(p[1], a.rows_p, cp, dcp);
+        cos_features_sfu<3>(p[2], a.rows_r, cr, dcr);
         float YY[6], PP[6], RRv[8];
         sym_products<3>(cp, PP);
         sym_products<3>(cr, RRv);
@@ -1117,7 +1117,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             }
         }
         NLML_TSTAMP(1);   // pitch/roll features (+ role 1: PP(x)RR publish + V GEMM issue)
-        cos_features_fast<3>(p[0], a.rows_y, cy, dcy);
+        cos_features_sfu<3>(p[0], a.rows_y, cy, dcy);
         sym_products<3>(cy, YY);
         // the linear term does not depend on the MMAs: it runs while they execute.  Each role keeps only the outputs it
         // needs (the angle thread ey/ep/er, the identity thread lin_u); the other half is dead code in its branch.
