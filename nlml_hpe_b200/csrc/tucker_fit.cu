@@ -1050,10 +1050,11 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             float UU[16], hl[16];
             sym_products<5>(u, UU);
             UU[15] = 0.f;
-            // per-sample power-of-two scale: the largest |UU| lands in [2^12, 2^13) (UU starts at 0 and grows over the fit)
+            // per-sample power-of-two scale: the largest |UU| = (max |u_i|)^2 lands in [2^12, 2^13) (UU starts at 0 and grows over the fit)
             float m = 0.f;
 #pragma unroll
-            for (int k = 0; k < 15; ++k) m = fmaxf(m, fabsf(UU[k]));
+            for (int k = 0; k < 5; ++k) m = fmaxf(m, fabsf(u[k]));
+            m *= m;
             int eu = 12 - (((__float_as_int(m) >> 23) & 0xff) - 127);
             eu = m > 0.f ? max(min(eu, 100), -80) : 0;
             uu_exp = eu;
@@ -1088,15 +1089,20 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         RRv[6] = RRv[7] = 0.f;
         // the identity threads publish the PP (x) RR operand; thread 160 launches the V GEMM (named barrier 2)
         if (role == 1) {
-            const float kPrScale = __int_as_float((127 + a.pr_exp) << 23);
+            float PPs[6];   // the operand's power-of-two scale rides on PP
+            {
+                const float kPrScale = __int_as_float((127 + a.pr_exp) << 23);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) PPs[i] = PP[i] * kPrScale;
+            }
 #pragma unroll
             for (int k8 = 0; k8 < C::KV / 8; ++k8) {   // one 16-byte chunk = 8 halves of this row per plane
                 uint32_t wh[4], wl[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int k0 = 8 * k8 + 2 * e, k1 = k0 + 1;
-                    const float v0 = k0 < 36 ? PP[k0 / 6] * RRv[k0 % 6] * kPrScale : 0.f;
-                    const float v1 = k1 < 36 ? PP[k1 / 6] * RRv[k1 % 6] * kPrScale : 0.f;
+                    const float v0 = k0 < 36 ? PPs[k0 / 6] * RRv[k0 % 6] : 0.f;
+                    const float v1 = k1 < 36 ? PPs[k1 / 6] * RRv[k1 % 6] : 0.f;
                     const __half2 h = __floats2half2_rn(v0, v1);
                     const float2 hf = __half22float2(h);
                     const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
@@ -1220,7 +1226,7 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
 #pragma unroll
         for (int i = 0; i < C::NP; ++i) g[i] = gx[i * 128 + row];
         g[0] += gx[8 * 128 + row];   // d/d(yaw) = linear part (angle thread) + quadratic part (identity thread)
-        clip_and_step<C::NP>(p, g, lr, clip);
+        clip_and_step_fast<C::NP>(p, g, lr, clip);
         NLML_TSTAMP(6);   // clip + step
     }
 #ifdef NLML_TC_TIMING

@@ -166,6 +166,27 @@ NLML_HD void clip_and_step(float* p, float* g, float lr, float clip) {
     for (int i = 0; i < NP; ++i) p[i] = sub_rn(p[i], mul_rn(lr, mul_rn(g[i], coef)));
 }
 
+// The same update with a short dependency chain, for the tensor-core iteration kernel (every warp of the CTA sits in
+// this step at once, right after the CTA barrier, so its latency is exposed): pairwise sum of squares, rsqrt and a
+// reciprocal from the special-function unit (2 ulp on the clip coefficient: a 1e-7 relative change of the step length).
+#if defined(__CUDACC__)
+template <int NP>
+__device__ __forceinline__ void clip_and_step_fast(float* p, const float* g, float lr, float clip) {
+    static_assert(NP == 8, "pairwise tree written for 8 parameters");
+    const float s01 = fmaf(g[1], g[1], g[0] * g[0]), s23 = fmaf(g[3], g[3], g[2] * g[2]);
+    const float s45 = fmaf(g[5], g[5], g[4] * g[4]), s67 = fmaf(g[7], g[7], g[6] * g[6]);
+    const float ss = (s01 + s23) + (s45 + s67);
+    const float lim = clip - 1e-6f;
+    float coef = 1.0f;
+    if (!(lim > 0.f && ss < 0.98f * lim * lim)) {
+        const float norm = ss > 0.f ? ss * rsqrtf(ss) : 0.f;
+        coef = fminf(__fdividef(clip, norm + 1e-6f), 1.0f);
+    }
+#pragma unroll
+    for (int i = 0; i < NP; ++i) p[i] = sub_rn(p[i], mul_rn(lr, mul_rn(g[i], coef)));
+}
+#endif
+
 // q accessor for memory-resident q: element r of sample n at q[n*sample + r*stride] (a shared-memory column on
 // the GPU, a plain array on the host).  The thread-per-sample kernel's other accessor reads q from tensor memory.
 struct QStrided {
