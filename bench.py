@@ -365,8 +365,9 @@ def bench_enlarged(spec, fitter_cls, torch, dist, world, rank, dev, num_sms, tf3
     # issued: padded columns x (KA + NA16) x 3 passes (the kernel's configuration is re-derived as in choose_gen_config)
     rrmax = 5 if rr <= 5 else 8
     ndp = (tri(rrmax) + 7) // 8 * 8
-    KA, NA16 = (nA + 7) // 8 * 8, (nA + 15) // 16 * 16
+    KA = NA16 = (nA + 15) // 16 * 16
     issued_lo = T_ITERS * 2 * 3 * (tri(ry) * tri(rp) * ndp) * (KA + NA16)
+    peak16 = peaks["bf16_tflops_sustained"]
     per_gpu = n / (ms * 1e-3)
     rec = {
         "ranks": list(ranks), "R": R, "F": F, "T": T_ITERS,
@@ -378,12 +379,13 @@ def bench_enlarged(spec, fitter_cls, torch, dist, world, rank, dev, num_sms, tf3
         "e2e": {"value": n * world / (ms_e * 1e-3), "unit": "poses/s", "h2d_bytes_per_step": n * F * 4, "d2h_bytes_per_step": n * np_ * 4,
                 "steps": 1, "api": "nlml_tucker_fit_host_f32 (pinned host X -> host P)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": tf32_peak, "peak_source": "measured live: nlml_measure_tf32_tflops (dense TF32 tcgen05 probe)",
-                     "achieved": per_gpu * useful / 1e12, "frac": per_gpu * useful / 1e12 / tf32_peak,
-                     "issued_frac": per_gpu * issued_lo / 1e12 / tf32_peak, "mma_passes": 3, "traffic": None,
+        "roofline": {"bound": "tensor", "unit": "TFLOP/s", "peak": peak16,
+                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}): kind::f16 MMAs (FP16 hi/lo operand split, FP32 accumulate)",
+                     "achieved": per_gpu * useful / 1e12, "frac": per_gpu * useful / 1e12 / peak16,
+                     "issued_frac": per_gpu * issued_lo / 1e12 / peak16, "mma_passes": 3, "traffic": None,
                      "kernel": "tucker_fit_gen_kernel",
                      "note": f"useful = T x 2 x (2 x {nA} x {nBCD}) flop per pose (both contractions with the folded Gram tensor); "
-                             "issued counts the 3xTF32 passes and the padding of the pair / roll-pair axes"},
+                             "issued counts the three hi/lo passes and the padding of the pair / roll-pair axes"},
         "roofline_hbm": {"bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"], "achieved": per_gpu * (F * 4 + np_ * 4) / 1e9,
                          "frac": per_gpu * (F * 4 + np_ * 4) / 1e9 / peaks["hbm_gbs"]},
     }

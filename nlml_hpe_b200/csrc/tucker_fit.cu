@@ -1767,7 +1767,7 @@ bool choose_gen_config(int ri, int ry, int rp, int rr, tgen::GenCfg& best) {
     tgen::GenCfg b{};
     b.ri = ri; b.ry = ry; b.rp = rp; b.rr = rr; b.R = ri * ry * rp * rr;
     b.rrmax = rr <= 5 ? 5 : 8;
-    b.nA = tri(ri); b.KA = (b.nA + 7) / 8 * 8; b.NA16 = (b.nA + 15) / 16 * 16;
+    b.nA = tri(ri); b.KA = (b.nA + 15) / 16 * 16; b.NA16 = b.KA;   // FP16 MMAs: K in steps of 16
     b.nC = tri(rp); b.nBC = tri(ry) * tri(rp);
     b.nDp = (tri(b.rrmax) + 7) / 8 * 8;
     b.NP = 3 + ri;
@@ -1793,9 +1793,11 @@ bool choose_gen_config(int ri, int ry, int rp, int rr, tgen::GenCfg& best) {
             for (int gbufs = 2; gbufs >= 1; --gbufs) {
                 if ((pin_tb && tbufs != pin_tb) || (pin_gb && gbufs != pin_gb)) continue;
                 for (int ybufs = 2; ybufs >= 1; --ybufs) {
-                    const int cols = gbufs * b.NA16 + 2 * b.KA + tbufs * NB + (ytm ? ybufs * 2 * NB : 0);
+                    // tensor-memory columns: D_G buffers, UU operand (KA/2 packed hi + KA/2 lo), D_T buffers, YPR operand (NB/2 + NB/2)
+                    const int cols = gbufs * b.NA16 + b.KA + tbufs * NB + (ytm ? ybufs * NB : 0);
                     if (cols > 512) continue;
-                    const int tt = NB * b.KA * 8, gt = b.NA16 * NB * 8, ypr = ytm ? 0 : ybufs * NB * tgen::kSamples * 8;
+                    // FP16 hi + lo planes: 4 bytes per element
+                    const int tt = NB * b.KA * 4, gt = b.NA16 * NB * 4, ypr = ytm ? 0 : ybufs * NB * tgen::kSamples * 4;
                     const int avail = kGenSmemMax - 1024 - ypr - tab_bytes - bar_bytes;
                     if (avail < tt + gt) continue;
                     if (pin_yb && ybufs != pin_yb) continue;
@@ -1804,8 +1806,10 @@ bool choose_gen_config(int ri, int ry, int rp, int rr, tgen::GenCfg& best) {
                     int slots = resident ? nblocks : std::min(4, avail / (tt + gt));
                     if (pin_slots) slots = std::min(slots, pin_slots);
                     const double waste = (double)nblocks * NB / ((double)b.nBC * tri(rr)) - 1.0;   // padded columns issued per useful one
+                    // (streamed tiles: the per-block handshakes and TMA round trips amortise over wider blocks -- measured on
+                    // (16,8,8,8): NB = 80 with two ring slots 3226 poses/s, NB = 48 with three 2370)
                     const double score = (resident ? 40.0 : 10.0 * std::min(slots, 3)) + 6.0 * ybufs + 4.0 * tbufs + 3.0 * gbufs + 30.0 * ytm +
-                                         0.25 * std::min(NB, 128) - 20.0 * waste;
+                                         (resident ? 0.25 : 0.6) * std::min(NB, 128) - 20.0 * waste;
                     if (score <= best_score) continue;
                     best_score = score;
                     best = b;
@@ -1813,7 +1817,7 @@ bool choose_gen_config(int ri, int ry, int rp, int rr, tgen::GenCfg& best) {
                     best.tbufs = tbufs; best.gbufs = gbufs; best.ybufs = ybufs; best.ypr_tmem = ytm;
                     best.tslots = best.gslots = slots; best.resident = resident ? 1 : 0;
                     best.tt_bytes = tt; best.gt_bytes = gt;
-                    best.col_g = 0; best.col_a = gbufs * b.NA16; best.col_t = best.col_a + 2 * b.KA; best.col_y = best.col_t + tbufs * NB;
+                    best.col_g = 0; best.col_a = gbufs * b.NA16; best.col_t = best.col_a + b.KA; best.col_y = best.col_t + tbufs * NB;
                     best.off_tring = 0;
                     best.off_gring = slots * tt;
                     best.off_ypr = best.off_gring + slots * gt;
@@ -2226,7 +2230,17 @@ extern "C" int nlml_tucker_plan_create(const float* W_host, int r_id, int r_y, i
                                            (int)pl->cta_smem));
     }
     if (pl->gen_ok) {
-        // tile images of S for the run-time-rank tensor-core kernel (hi/lo TF32 planes in the UMMA operand layout)
+        // power-of-two scale of the tile images (FP16 range): the largest |S| lands in [2^13, 2^14)
+        {
+            std::vector<float> Sh((size_t)pl->nBCD * pl->NAP);
+            NLML_CUDA(cudaMemcpy(Sh.data(), pl->S, sizeof(float) * Sh.size(), cudaMemcpyDeviceToHost));
+            float smax = 0.f;
+            for (float v : Sh) smax = std::max(smax, std::fabs(v));
+            int e = 0;
+            if (smax > 0.f && std::isfinite(smax)) e = 13 - (int)std::floor(std::log2(smax));
+            pl->gen.s_exp = std::max(-40, std::min(e, 40));
+        }
+        // tile images of S for the run-time-rank tensor-core kernel (FP16 hi/lo planes in the UMMA operand layout)
         const size_t bytes = (size_t)pl->gen.nblocks * ((size_t)pl->gen.tt_bytes + pl->gen.gt_bytes);
         NLML_CUDA(cudaMalloc(&pl->gen_tiles, bytes));
         const long long elems = (long long)pl->gen.nblocks * ((long long)pl->gen.NB * pl->gen.KA + (long long)pl->gen.NA16 * pl->gen.NB);

@@ -10,9 +10,11 @@
 // to "resident" when every block fits.  Per iteration and block j, for the CTA's 128 samples (= 128 TMEM lanes):
 //   GEMM-T   D_T[s, col]  = sum_A  UU[s,A] * S[A, col]          128 x NB x KA     A operand (UU hi|lo) in TENSOR MEMORY
 //   GEMM-G   D_G[s, A]    = sum_col YPR[s,col] * S[A, col]      128 x NA16 x NB   A operand written to shared memory
-// with col = (b,c) pair x padded roll pair, YPR = YY_b PP_c RR_d, all 3xTF32 (FP32-grade products).  Accumulation
-// chains inside tensor memory stay short (<= 51 resp. 30 MMAs: the tensor core's FP32 accumulate truncates, which
-// biases long chains); every block's partial D_G is promoted into FP32 registers with round-to-nearest adds.
+// with col = (b,c) pair x padded roll pair, YPR = YY_b PP_c RR_d.  Operands are FP16 hi/lo planes (kind::f16, three of
+// the four cross products: FP32-grade, 22 operand bits) with power-of-two scales: S by 2^s_exp from the plan (max |S|),
+// UU and YPR by per-sample, per-iteration exponents; the scales come off where the accumulators are read.  16-deep MMAs: half the instructions and half the tile bytes of a 3xTF32 split.
+// Accumulation chains inside tensor memory stay short (the tensor core's FP32 accumulate truncates, which biases long
+// chains); every block's partial D_G is promoted into FP32 registers with round-to-nearest adds.
 //
 // 512 threads = four warp groups (setmaxnreg moves the registers to where they are needed):
 //   group 0  warp 0 lane 0: TMA producer.  warp 1: TMEM allocation, lane 0 issues every MMA.
@@ -38,12 +40,12 @@ constexpr int kMaxSlots = 16;
 struct GenCfg {
     int ri, ry, rp, rr, R;
     int rrmax;               // roll-rank class the kernel is instantiated for (5 or 8)
-    int nA, KA, NA16;        // identity pairs; padded to 8 (K of GEMM-T) and to 16 (N of GEMM-G)
+    int nA, KA, NA16;        // identity pairs; padded to 16 (K of GEMM-T, N of GEMM-G)
     int nC, nBC;             // pitch pairs, (yaw pair, pitch pair) combinations
     int nDp;                 // roll pairs of the rrmax triangle padded to 8 = columns per (b,c) pair
     int BCP, NB, nblocks;    // (b,c) pairs per block, columns per block (multiple of 16), blocks per iteration
     int tbufs, gbufs, ybufs; // TMEM buffers of D_T and D_G, buffers of the YPR operand
-    int ypr_tmem;            // the YPR operand lives in tensor memory (hi | lo columns) instead of shared memory
+    int ypr_tmem;            // the YPR operand lives in tensor memory (packed halves: NB/2 hi | NB/2 lo columns) instead of shared memory
     int col_y;               // its first TMEM column
     int tslots, gslots;      // ring slots of T tiles / G tiles
     int resident;            // every tile has its own slot and is loaded once
@@ -51,6 +53,7 @@ struct GenCfg {
     int col_g, col_a, col_t; // TMEM columns: D_G buffers, UU operand (hi | lo), D_T buffers
     int off_tring, off_gring, off_ypr, off_tab, off_bar, smem_bytes;
     int NP;                  // 3 + ri
+    int s_exp;               // the tile images hold S * 2^s_exp
     // rows of the per-sample table (floats, [row][128]):
     int t_p, t_gx, t_gl, t_cy, t_dcy, t_cp, t_dcp, t_rows;
 };
@@ -88,6 +91,20 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
                  ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
                    "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
                    "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                   "r"(__float_as_uint(v[3])) : "memory");
+}
+// two FP32 values -> one word of the hi plane and one of the lo plane (element 0 in the low half: the packed-halves
+// layout of a tensor-memory A operand and of a 16-byte shared-memory operand chunk)
+__device__ __forceinline__ void split_pair16(float v0, float v1, float& hi, float& lo) {
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    hi = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
+    lo = __uint_as_float(*reinterpret_cast<const uint32_t*>(&l));
 }
 __device__ __forceinline__ void tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -217,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
     for (int i = tid; i < c.t_rows * kSamples; i += kThreads) tab[i] = 0.f;
     // the YPR operand's pad columns (NB is rounded up to the MMA's N granularity) are never written again: zero them once
     if (!c.ypr_tmem)
-        for (int i = tid; i < c.ybufs * 2 * NB * kSamples; i += kThreads) reinterpret_cast<float*>(gsm + c.off_ypr)[i] = 0.f;
+        for (int i = tid; i < c.ybufs * NB * kSamples; i += kThreads) reinterpret_cast<float*>(gsm + c.off_ypr)[i] = 0.f;   // 2 planes x 2 bytes
     ttc::fence_async_smem();
     tc_before();
     __syncthreads();
@@ -253,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
         } else if (warp == 1) {
             // ===== MMA issuer: the whole warp runs the loop with warp-uniform values (descriptor arithmetic in the uniform
             // datapath); lane 0 issues the MMAs and commits =====
-            const uint32_t ypr_plane = (uint32_t)NB * kSamples * 4;   // one plane of one YPR operand buffer
+            const uint32_t ypr_plane = (uint32_t)NB * kSamples * 2;   // one FP16 plane of one YPR operand buffer
             Ring ts(c.resident ? nblocks : c.tslots), gs(c.resident ? nblocks : c.gslots), tb(c.tbufs), gb(c.gbufs), yb(c.ybufs);
             GT_DECL
             for (int it = 0; it < a.T; ++it) {
@@ -268,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
                     tc_after();
                     {
                         const uint32_t t_hi = ttc::smem_u32(gsm + c.off_tring) + (uint32_t)ts.idx * (uint32_t)c.tt_bytes;
-                        ttc::gemm3_ts(tmem + c.col_t + tb.idx * NB, tmem + c.col_a, t_hi, t_hi + c.tt_bytes / 2, KA, NB);
+                        ttc::gemm3h_ts(tmem + c.col_t + tb.idx * NB, tmem + c.col_a, t_hi, t_hi + c.tt_bytes / 2, KA, NB);
                     }
                     ttc::umma_commit_elect(&tfull[tb.idx]);
                     if (!c.resident) ttc::umma_commit_elect(&emptyT[ts.idx]);
@@ -284,10 +301,10 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
                     {
                         const uint32_t g_hi = ttc::smem_u32(gsm + c.off_gring) + (uint32_t)gs.idx * (uint32_t)c.gt_bytes;
                         if (c.ypr_tmem) {
-                            ttc::gemm3_ts(tmem + c.col_g + gb.idx * NA16, tmem + c.col_y + yb.idx * 2 * NB, g_hi, g_hi + c.gt_bytes / 2, NB, NA16);
+                            ttc::gemm3h_ts(tmem + c.col_g + gb.idx * NA16, tmem + c.col_y + yb.idx * NB, g_hi, g_hi + c.gt_bytes / 2, NB, NA16);
                         } else {
                             const uint32_t y_hi = ttc::smem_u32(gsm + c.off_ypr) + (uint32_t)yb.idx * 2u * ypr_plane;
-                            ttc::gemm3_ss(tmem + c.col_g + gb.idx * NA16, y_hi, y_hi + ypr_plane, g_hi, g_hi + c.gt_bytes / 2, NB, NA16);
+                            ttc::gemm3h_ss(tmem + c.col_g + gb.idx * NA16, y_hi, y_hi + ypr_plane, g_hi, g_hi + c.gt_bytes / 2, NB, NA16);
                         }
                     }
                     ttc::umma_commit_elect(&gfull[gb.idx]);
@@ -319,21 +336,31 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
                     my[(c.t_dcy + j) * kSamples] = -(ra * rb) * s;
                 }
             }
+            int uu_exp;   // this iteration's power-of-two scale of the UU operand: the largest |UU| = (max |u_i|)^2 lands in [2^12, 2^13)
             {
+                float m = 0.f;
+                for (int i = 0; i < c.ri; ++i) m = fmaxf(m, fabsf(my[(c.t_p + 3 + i) * kSamples]));
+                m *= m;
+                int eu = 12 - (((__float_as_int(m) >> 23) & 0xff) - 127);
+                eu = m > 0.f ? max(min(eu, 100), -80) : 0;
+                uu_exp = eu;
+                const float su = __int_as_float((eu + 127) << 23);
                 int i = 0, j = 0;
-                for (int k0 = 0; k0 < KA; k0 += 8) {
+                for (int k0 = 0; k0 < KA; k0 += 16) {   // 16 elements = 8 packed columns per plane
                     float hi[8], lo[8];
 #pragma unroll
                     for (int x = 0; x < 8; ++x) {
-                        float v = 0.f;
-                        if (k0 + x < c.nA) {
-                            v = my[(c.t_p + 3 + i) * kSamples] * my[(c.t_p + 3 + j) * kSamples];
-                            if (++j == c.ri) { ++i; j = i; }
-                        }
-                        ttc::split_tf32_bits(v, hi[x], lo[x]);
+                        float v[2] = {0.f, 0.f};
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            if (k0 + 2 * x + h < c.nA) {
+                                v[h] = my[(c.t_p + 3 + i) * kSamples] * my[(c.t_p + 3 + j) * kSamples] * su;
+                                if (++j == c.ri) { ++i; j = i; }
+                            }
+                        split_pair16(v[0], v[1], hi[x], lo[x]);
                     }
-                    tmem_st8(lane_addr + c.col_a + k0, hi);
-                    tmem_st8(lane_addr + c.col_a + KA + k0, lo);
+                    tmem_st8(lane_addr + c.col_a + k0 / 2, hi);
+                    tmem_st8(lane_addr + c.col_a + KA / 2 + k0 / 2, lo);
                 }
                 tmem_store_wait();
                 tc_before();
@@ -407,9 +434,12 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
                 if (lane == 0) mbar_arrive(&tempty[tb.idx]);
                 GT(3)   // fold
             }
-            my[(c.t_gx + 0) * kSamples] = gy;
-            my[(c.t_gx + 1) * kSamples] = gp;
-            my[(c.t_gx + 2) * kSamples] = gr;
+            {
+                const float kt = __int_as_float((127 - c.s_exp - uu_exp) << 23);   // 2^-(s_exp + uu_exp): the D_T accumulators' scale off
+                my[(c.t_gx + 0) * kSamples] = gy * kt;
+                my[(c.t_gx + 1) * kSamples] = gp * kt;
+                my[(c.t_gx + 2) * kSamples] = gr * kt;
+            }
             named_sync(2, 384);   // gradient parts published (d/du by the G formers, linear term by group 3)
             GT(4)
 
@@ -436,7 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
         // ===== G formers =====
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsG));
         float* my = tab + row;
-        const uint32_t ypr_plane = (uint32_t)NB * kSamples * 4;
+        const uint32_t ypr_plane = (uint32_t)NB * kSamples * 2;   // one FP16 plane
         Ring yb(c.ybufs), gb(c.gbufs);
         GT_DECL
         for (int it = 0; it < a.T; ++it) {
@@ -454,6 +484,24 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
             }
             named_sync(1, 384);
 
+            // per-sample, per-iteration power-of-two scale of the YPR operand: the largest |YY_b PP_c RR_d| =
+            // (max|cy| max|cp| max|cr|)^2 lands in [2^12, 2^13).  (A fixed scale from the rows' bounds leaves the small
+            // products of three monomials in FP16's subnormal range: 0.04 degrees off at T = 3000 on (16,8,8,8).)
+            int y_exp;
+            float kY;
+            {
+                float m = 0.f, mp = 0.f, mr = 0.f;
+                for (int j = 0; j < c.ry; ++j) m = fmaxf(m, fabsf(my[(c.t_cy + j) * kSamples]));
+                for (int k = 0; k < c.rp; ++k) mp = fmaxf(mp, fabsf(my[(c.t_cp + k) * kSamples]));
+#pragma unroll
+                for (int l = 0; l < RRMAX; ++l) mr = fmaxf(mr, fabsf(cr[l]));
+                m = m * mp * mr;
+                m *= m;
+                int e = 12 - (((__float_as_int(m) >> 23) & 0xff) - 127);
+                y_exp = m > 0.f ? max(min(e, 60), -60) : 0;
+                kY = __int_as_float((y_exp + 127) << 23);
+            }
+
             float GU[NA16MAX];
 #pragma unroll
             for (int i = 0; i < NA16MAX; ++i) GU[i] = 0.f;
@@ -468,40 +516,46 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
                 GT(1)   // wait operand buffer
                 uint8_t* yhi = gsm + c.off_ypr + (size_t)yb.idx * 2 * ypr_plane;
                 uint8_t* ylo = yhi + ypr_plane;
-                const int rbase = (row / 8) * ((NB / 4) * 128) + (row % 8) * 16;   // ttc::op_offset(row, k, NB) = rbase + (k/4)*128 + (k%4)*4
-                const uint32_t ybase = lane_addr + c.col_y + yb.idx * 2 * NB;       // tensor-memory form: hi columns, then NB lo columns
+                const int rbase = (row / 8) * ((NB / 8) * 128) + (row % 8) * 16;   // ttc::op16_offset(row, k, NB) = rbase + (k/8)*128 + (k%8)*2
+                const uint32_t ybase = lane_addr + c.col_y + yb.idx * NB;           // tensor-memory form: NB/2 packed hi columns, then NB/2 lo
                 if (c.ypr_tmem) {
                     // the pad columns [BCP * NDP, NB) of this buffer: zero (they multiply zero tile entries, but must be finite)
-                    const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    for (int k0 = c.BCP * NDP; k0 < NB; k0 += 8) {
-                        tmem_st8(ybase + k0, z);
-                        tmem_st8(ybase + NB + k0, z);
+                    const float z[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int w0 = c.BCP * NDP / 2; w0 < NB / 2; w0 += 4) {
+                        tmem_st4(ybase + w0, z);
+                        tmem_st4(ybase + NB / 2 + w0, z);
                     }
                 }
                 for (int pl = 0; pl < c.BCP; ++pl) {
                     float yp = 0.f;
                     if (pair < c.nBC) {
-                        yp = YY * (my[(c.t_cp + pw.ci) * kSamples] * my[(c.t_cp + pw.cj) * kSamples]);
+                        yp = YY * (my[(c.t_cp + pw.ci) * kSamples] * my[(c.t_cp + pw.cj) * kSamples]) * kY;
                         ++pair;
                         if (pw.next(c.ry, c.rp) && pw.bi < c.ry)
                             YY = my[(c.t_cy + pw.bi) * kSamples] * my[(c.t_cy + pw.bj) * kSamples];
                     }
                     if (c.ypr_tmem) {
 #pragma unroll
-                        for (int d8 = 0; d8 < NDP / 8; ++d8) {
+                        for (int w0 = 0; w0 < NDP / 2; w0 += 8) {   // NDP/2 packed words per plane: 8 (roll rank <= 5) or 8 + 8 + 4
                             float h[8], l[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) ttc::split_tf32_bits(yp * RRv[8 * d8 + e], h[e], l[e]);
-                            tmem_st8(ybase + pl * NDP + 8 * d8, h);
-                            tmem_st8(ybase + NB + pl * NDP + 8 * d8, l);
+                            for (int e = 0; e < 8; ++e)
+                                if (w0 + e < NDP / 2) split_pair16(yp * RRv[2 * (w0 + e)], yp * RRv[2 * (w0 + e) + 1], h[e], l[e]);
+                            if (w0 + 8 <= NDP / 2) {
+                                tmem_st8(ybase + pl * (NDP / 2) + w0, h);
+                                tmem_st8(ybase + NB / 2 + pl * (NDP / 2) + w0, l);
+                            } else {
+                                tmem_st4(ybase + pl * (NDP / 2) + w0, h);
+                                tmem_st4(ybase + NB / 2 + pl * (NDP / 2) + w0, l);
+                            }
                         }
                     } else {
 #pragma unroll
-                        for (int d4 = 0; d4 < NDP / 4; ++d4) {
+                        for (int d8 = 0; d8 < NDP / 8; ++d8) {      // one 16-byte chunk = 8 halves of this row per plane
                             float h[4], l[4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) ttc::split_tf32_bits(yp * RRv[4 * d4 + e], h[e], l[e]);
-                            const int off = rbase + ((pl * NDP) / 4 + d4) * 128;
+                            for (int e = 0; e < 4; ++e) split_pair16(yp * RRv[8 * d8 + 2 * e], yp * RRv[8 * d8 + 2 * e + 1], h[e], l[e]);
+                            const int off = rbase + ((pl * NDP) / 8 + d8) * 128;
                             *reinterpret_cast<float4*>(yhi + off) = make_float4(h[0], h[1], h[2], h[3]);
                             *reinterpret_cast<float4*>(ylo + off) = make_float4(l[0], l[1], l[2], l[3]);
                         }
@@ -552,11 +606,12 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
             // d/du_m of sum_A GU_A UU_A: for the pair A = (i,j): i == j -> 2 GU u_i, else GU u_j to i and GU u_i to j
             for (int i = 0; i < c.ri; ++i) my[(c.t_gx + 3 + i) * kSamples] = 0.f;
             {
+                const float kg = __int_as_float((127 - c.s_exp - y_exp) << 23);   // 2^-(s_exp + y_exp): the D_G accumulators' scale off
                 int i = 0, j = 0;
 #pragma unroll
                 for (int A = 0; A < NA16MAX; ++A) {
                     if (A < c.nA) {
-                        const float ui = my[(c.t_p + 3 + i) * kSamples], uj = my[(c.t_p + 3 + j) * kSamples];
+                        const float ui = my[(c.t_p + 3 + i) * kSamples] * kg, uj = my[(c.t_p + 3 + j) * kSamples] * kg;
                         if (i == j) {
                             my[(c.t_gx + 3 + i) * kSamples] += 2.0f * GU[A] * ui;
                         } else {
@@ -721,10 +776,11 @@ __global__ void __launch_bounds__(256) tucker_project_kernel(const float* __rest
 }
 
 // Tile images of the folded Gram tensor: for block j the T tile [NB cols][KA] and the G tile [NA16][NB cols], each as a
-// hi plane followed by a lo plane in the UMMA no-swizzle K-major layout (ttc::op_offset).  Column col = pair * NDP + dd:
+// FP16 hi plane followed by a lo plane (S times 2^s_exp) in the UMMA no-swizzle K-major layout (ttc::op16_offset).  Column col = pair * NDP + dd:
 // pair = b * nC + c, dd = pair_index(i, j, rrmax) of the roll pair (entries with j >= rr are zero).
 __global__ void build_tiles_kernel(const float* __restrict__ S, int NAP, GenCfg c, uint8_t* __restrict__ tiles) {
     const int nD = tri(c.rr);
+    const float s_scale = __int_as_float((127 + c.s_exp) << 23);
     const long long per_block = (long long)c.NB * c.KA + (long long)c.NA16 * c.NB;
     const long long total = per_block * c.nblocks;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -741,17 +797,17 @@ __global__ void build_tiles_kernel(const float* __restrict__ S, int NAP, GenCfg 
             unpair(dd, c.rrmax, &i, &j);
             if (j < c.rr) v = S[((long long)pair * nD + pair_index(i, j, c.rr)) * NAP + A];
         }
-        float hi, lo;
-        ttc::split_tf32(v, hi, lo);
+        __half hi, lo;
+        ttc::split_half(v * s_scale, hi, lo);
         uint8_t* base = tiles + (size_t)blk * ((size_t)c.tt_bytes + c.gt_bytes);
         if (is_t) {
-            const int off = ttc::op_offset(col, A, c.KA);
-            *reinterpret_cast<float*>(base + off) = hi;
-            *reinterpret_cast<float*>(base + c.tt_bytes / 2 + off) = lo;
+            const int off = ttc::op16_offset(col, A, c.KA);
+            *reinterpret_cast<__half*>(base + off) = hi;
+            *reinterpret_cast<__half*>(base + c.tt_bytes / 2 + off) = lo;
         } else {
-            const int off = ttc::op_offset(A, col, c.NB);
-            *reinterpret_cast<float*>(base + c.tt_bytes + off) = hi;
-            *reinterpret_cast<float*>(base + c.tt_bytes + c.gt_bytes / 2 + off) = lo;
+            const int off = ttc::op16_offset(A, col, c.NB);
+            *reinterpret_cast<__half*>(base + c.tt_bytes + off) = hi;
+            *reinterpret_cast<__half*>(base + c.tt_bytes + c.gt_bytes / 2 + off) = lo;
         }
     }
 }
