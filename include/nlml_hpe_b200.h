@@ -140,7 +140,12 @@ int nlml_mlp_plan_create(const float* const* weights, const float* const* biases
 void nlml_mlp_plan_destroy(nlml_mlp_plan* plan);
 
 /* X: DEVICE float32 [N][ldx]; YPR_out: DEVICE float32 [N][3] = (yaw, pitch, roll) radians.
- * Asynchronous on `stream`. */
+ * Asynchronous on `stream`.
+ * Range: the default (tensor-core) path carries every activation as two FP16 planes, so inputs and hidden
+ * activations must stay within +-65504 (IPD-normalised landmarks are O(1)).  Beyond that the hi plane
+ * overflows and the affected rows come back NON-FINITE -- never finite-but-wrong; nlml_mlp_set_path(plan, 1)
+ * (FP32 CUDA-core chain, the reference's arithmetic) serves such inputs.  Pinned by
+ * tests/test_mlp_gpu.py::test_out_of_range_inputs_fail_loudly. */
 int nlml_mlp_forward_f32(nlml_mlp_plan* plan, const float* X_dev, int64_t N, int64_t ldx,
                          float* YPR_out_dev, void* stream);
 /* HOST buffers, chunked and pipelined like nlml_tucker_fit_host_f32. */

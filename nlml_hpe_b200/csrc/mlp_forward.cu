@@ -39,7 +39,11 @@ struct LinearArgs {
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
-    if (act == ACT_RELU) return fmaxf(v, 0.f);
+    if (act == ACT_RELU) {   // NaN-propagating, as torch.relu (see relu_nan in mlp_tc.cuh)
+        float r;
+        asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
+        return r;
+    }
     if (act == ACT_TANH) return tanhf(v);  // accurate tanhf, as torch.tanh on f32 (Model_Builder.py:48)
     return v;
 }

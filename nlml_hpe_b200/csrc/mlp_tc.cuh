@@ -240,9 +240,17 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
 // The activation is a template parameter of everything that runs per element: with a run-time `act` every one of a
 // thread's 128 outputs carried two uniform branches (and the inlined tanh body), ~13 k cycles per tile in which the
 // epilogue warps promoted nothing and the tensor pipe of the long layers idled (29 % of encoder.0's time).
+// ReLU that PROPAGATES NaN, as torch.relu does (fmaxf returns the other operand).  It matters for range errors: an
+// activation beyond FP16's range becomes inf in its hi plane, the next layer's products turn it into NaN, and an
+// fmaxf-ReLU would quietly map that NaN to 0 -- finite-but-wrong angles.  max.NaN costs the same single instruction.
+__device__ __forceinline__ float relu_nan(float v) {
+    float r;
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
+    return r;
+}
 template <int ACT>
 __device__ __forceinline__ float act_fixed(float v) {
-    if (ACT == 1) return fmaxf(v, 0.f);
+    if (ACT == 1) return relu_nan(v);
     if (ACT == 2) return tanhf(v);
     return v;
 }
@@ -631,8 +639,8 @@ linear_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ Li
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
                             const float4 w0 = neck_whs[h * kNeckHeadW + j0 + 2 * e], w1 = neck_whs[h * kNeckHeadW + j0 + 2 * e + 1];
-                            const float v0 = fmaxf(fmaf(l2, w0.z, fmaf(l1, w0.y, fmaf(l0, w0.x, w0.w))), 0.f);
-                            const float v1 = fmaxf(fmaf(l2, w1.z, fmaf(l1, w1.y, fmaf(l0, w1.x, w1.w))), 0.f);
+                            const float v0 = relu_nan(fmaf(l2, w0.z, fmaf(l1, w0.y, fmaf(l0, w0.x, w0.w))));
+                            const float v1 = relu_nan(fmaf(l2, w1.z, fmaf(l1, w1.y, fmaf(l0, w1.x, w1.w))));
                             split_pair(v0, v1, hi[e], lo[e]);
                         }
                         stage_box_tma(buf, hi, &maps.y_hi[h], j0, (int)(row - lane), lane);
@@ -1137,7 +1145,7 @@ __global__ void __launch_bounds__(kNarrowThreads) neck_kernel(const __grid_const
                 float acc = Bs[D_MID + D_LAT + z * HW + j0 + j];
 #pragma unroll
                 for (int i = 0; i < HIN; ++i) acc = fmaf(Whs[(z * HW + j0 + j) * HIN + i], lat[z * HIN + i], acc);
-                y[j] = fmaxf(acc, 0.f);
+                y[j] = relu_nan(acc);
             }
             if (a.Hf32[z]) {
                 float4* d = reinterpret_cast<float4*>(a.Hf32[z] + row * HW + j0);
@@ -1192,7 +1200,7 @@ __global__ void __launch_bounds__(kNarrowThreads) head_tail_kernel(const __grid_
     row_gemv<D_IN, MQ, D_MID>(xs + s * (D_IN + 4), W3t + q * MQ, h);
     float acc = 0.f;
 #pragma unroll
-    for (int j = 0; j < MQ; ++j) acc = fmaf(rest[D_MID + q * MQ + j], fmaxf(h[j], 0.f), acc);
+    for (int j = 0; j < MQ; ++j) acc = fmaf(rest[D_MID + q * MQ + j], relu_nan(h[j]), acc);
     acc = quad_sum(acc) + rest[2 * D_MID];
     if (row < a.N && q == 0) a.YPR[row * 3 + z] = acc;
 }

@@ -138,6 +138,14 @@ def tc_model(state_dicts, cuda_lib):
     return MB.build_combined_model(*state_dicts)
 
 
+def _same_bits(a, b):
+    """Bit-for-bit equality, NaN included (the two degenerate faces of the fixture, IPD = 0, are outside FP16's range and
+    come back NaN on the tensor-core path: see test_out_of_range_inputs_fail_loudly)."""
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    return a.shape == b.shape and np.array_equal(np.ascontiguousarray(a).view(np.int32), np.ascontiguousarray(b).view(np.int32))
+
+
 def test_fused_ipd_normalisation_is_bit_exact(tc_model, prepost_golden):
     """Raw landmarks through the fused load stage == the reference-normalised features through the plain forward,
     bit for bit (so the float64 normalisation on the device reproduces FeatureExtractor.py:30-66 + .float())."""
@@ -145,10 +153,10 @@ def test_fused_ipd_normalisation_is_bit_exact(tc_model, prepost_golden):
     raw = _gpu(g["raw"])                                   # [96,468,3]
     fused = tc_model.predict_landmarks(raw).cpu().numpy()
     plain = tc_model.predict(_gpu(g["norm_X"])).cpu().numpy()
-    assert np.array_equal(fused, plain)
-    assert np.array_equal(tc_model.predict_landmarks(raw.reshape(96, 1404)).cpu().numpy(), plain)
-    assert np.array_equal(tc_model.predict_landmarks(raw[:1]).cpu().numpy(), plain[:1])
-    assert np.array_equal(tc_model.predict_landmarks_host(g["raw"]), plain)                     # host buffers
+    assert _same_bits(fused, plain)
+    assert _same_bits(tc_model.predict_landmarks(raw.reshape(96, 1404)).cpu().numpy(), plain)
+    assert _same_bits(tc_model.predict_landmarks(raw[:1]).cpu().numpy(), plain[:1])
+    assert _same_bits(tc_model.predict_landmarks_host(g["raw"]), plain)                     # host buffers
     # and against the oracle end to end (normalise on the CPU in float64, forward in float32)
     ok = np.abs(g["norm_X"]).max(1) < 10.0                # the two degenerate faces are outside the 1e-3 degree budget's range
     ref = mlp_oracle.forward(*[s for s in tc_model_state(tc_model)], mlp_oracle.ipd_normalize(g["raw"])[ok])
@@ -167,10 +175,10 @@ def test_fused_ipd_normalisation_large_batch_and_strides(tc_model, prepost_golde
     reps = 1700                                            # 163 200 rows: crosses two chunk boundaries
     fused = tc_model.predict_landmarks(base_raw.repeat(reps, 1))
     plain = tc_model.predict(base_norm.repeat(reps, 1))
-    assert torch.equal(fused, plain)
+    assert _same_bits(fused, plain)
     wide = torch.zeros((96, 1500), device="cuda")
     wide[:, 3:1407] = base_raw                             # unaligned rows, row stride != 1404
-    assert torch.equal(tc_model.predict_landmarks(wide[:, 3:1407]), plain[:96])
+    assert _same_bits(tc_model.predict_landmarks(wide[:, 3:1407]), plain[:96])
 
 
 def test_fused_ipd_normalisation_fp32_path_fails_loudly(state_dicts, prepost_golden, cuda_lib):
@@ -194,3 +202,23 @@ def test_degrees_rounding_and_ema_are_bit_exact(tc_model, prepost_golden):
     assert np.array_equal(out, np.round(np.degrees(big.cpu().numpy().astype(np.float64)), 3))
     with pytest.raises(Exception):
         tc_model.to_degrees(rad, 3, ema_alpha=1.5)
+
+
+def test_out_of_range_inputs_fail_loudly(tc_model, state_dicts, X1k):
+    """Inputs beyond FP16's range (e.g. raw pixel coordinates times a large factor): the tensor-core path returns
+    NON-FINITE rows for them -- not finite-but-wrong angles (the ReLUs propagate NaN, as torch.relu does) -- and leaves
+    the in-range rows of the same batch intact; the FP32 path stays finite like the reference's FP32 forward."""
+    X = X1k[:256].copy()
+    X[::2] *= 3.0e5                                        # every other row far outside +-65504
+    out = tc_model.predict(_gpu(X)).cpu().numpy()
+    assert (~np.isfinite(out[::2])).any(axis=1).all()      # every out-of-range row is flagged by a non-finite value
+    ref_in = mlp_oracle.forward(*state_dicts, X[1::2])
+    assert np.abs(out[1::2] - ref_in).max() * DEG < TOL_DEG
+    tc_model.set_path("fp32")
+    try:
+        full = tc_model.predict(_gpu(X)).cpu().numpy()
+    finally:
+        tc_model.set_path("tensor_core")
+    ref = mlp_oracle.forward(*state_dicts, X)
+    assert np.isfinite(ref).all() and np.isfinite(full).all()
+    assert np.abs(full[1::2] - ref[1::2]).max() * DEG < TOL_DEG
