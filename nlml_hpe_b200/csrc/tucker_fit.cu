@@ -839,48 +839,6 @@ __global__ void build_tc_operands_kernel(const float* __restrict__ S, float s_sc
     }
 }
 
-// Half of T (3 of the 6 b's = 108 columns) -> partial GR[6], GP[6] and the 3 GY of those b's
-template <int B0>
-// PPk / RRk: PP and RR times the inverse operand scales (the T accumulator holds T times the scales of S and UU)
-__device__ __forceinline__ void tc_reduce_t(uint32_t taddr, const float (&YY)[6], const float (&PP)[6], const float (&PPk)[6],
-                                            const float (&RRk)[8], float (&GR)[6], float (&GP)[6], float (&GY3)[3]) {
-    float tr[18];   // sum_d T[b,c,d] * RR_d for the 3 b's
-#pragma unroll
-    for (int i = 0; i < 18; ++i) tr[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) GR[i] = GP[i] = 0.f;
-    constexpr int C0 = B0 * 36;            // first column of this half
-    constexpr int L0 = C0 / 32 * 32;       // aligned start of the 32-column loads covering [C0, C0 + 108)
-    constexpr int NL = (C0 + 108 - L0 + 31) / 32;
-    uint32_t buf[2][32];
-    tmem_load32_async(taddr + L0, buf[0]);
-#pragma unroll
-    for (int ci = 0; ci < NL; ++ci) {
-        tmem_load_wait();
-        if (ci + 1 < NL) tmem_load32_async(taddr + L0 + 32 * (ci + 1), buf[(ci + 1) & 1]);
-#pragma unroll
-        for (int x = 0; x < 32; ++x) {
-            const int bcd = L0 + 32 * ci + x;
-            if (bcd >= C0 && bcd < C0 + 108) {
-                const int b = bcd / 36, c = (bcd / 6) % 6, d = bcd % 6;
-                const float t = __uint_as_float(buf[ci & 1][x]);
-                GR[d] = fmaf(t, YY[b] * PPk[c], GR[d]);
-                tr[(b - B0) * 6 + c] = fmaf(t, RRk[d], tr[(b - B0) * 6 + c]);
-            }
-        }
-    }
-#pragma unroll
-    for (int bl = 0; bl < 3; ++bl) {
-        float gy = 0.f;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-            gy = fmaf(tr[bl * 6 + c], PP[c], gy);
-            GP[c] = fmaf(tr[bl * 6 + c], YY[B0 + bl], GP[c]);
-        }
-        GY3[bl] = gy;
-    }
-}
-
 // All of T contracted over b first: s[c,d] = sum_b T[b,c,d] * YYk[b] (216 FMAs; YYk carries the inverse operand scales).
 // GR[d] = sum_c PP_c s[c,d] and GP[c] = sum_d RR_d s[c,d] follow from it (72 FMAs); GY comes from the V accumulator
 // (GY[b] = sum_A UU_A V[A,b], on the identity thread).  The earlier form (tr[b,c] = sum_d T RR_d for GY and GP, plus
