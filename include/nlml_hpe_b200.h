@@ -57,7 +57,8 @@ void nlml_tucker_plan_destroy(nlml_tucker_plan* plan);
  * kernel_hint: 0 = choose by N and ranks, 1 = thread-per-sample kernel (throughput, ranks 5,3,3,3),
  * 2 = CTA-per-sample kernel (run-time ranks), 3 = warp-per-sample kernel (latency, ranks 5,3,3,3),
  * 4 = thread-per-sample kernel with q resident in tensor memory (12 warps per SM; measured equal to 1),
- * 5 = tensor-core iteration kernel (3xTF32 tcgen05 GEMMs for the folded-Gram contractions; the large-batch default),
+ * 5 = tensor-core iteration kernel (FP16 hi/lo tcgen05 GEMMs, FP32-grade, for the folded-Gram contractions; the default
+ *     from 1536 samples: one wave of up to 128 samples per SM takes 4.4-4.7 ms at T = 3000 whatever its size),
  * 6 = run-time-rank tensor-core kernel (any ranks up to 16 per mode with a roll rank <= 8; the folded Gram tensor is
  *     streamed through a shared-memory ring by TMA when it exceeds one tile; the default for every rank set other than
  *     (5,3,3,3), i.e. the enlarged cores of BASELINE.json configs[4]; the reference takes the ranks from the arrays,

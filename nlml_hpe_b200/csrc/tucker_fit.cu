@@ -2,9 +2,11 @@
 // (/root/reference/TD_Tester.py:127-159) and the converged fit TD_Tester.Test searches for (:191-199), for a whole
 // batch of feature vectors.  Same arithmetic everywhere (tucker_math.h); kernels chosen by batch size and ranks:
 //
-//   tucker_fit_tc_kernel   large batches (the default from 37 888 samples): 128 samples per CTA, two threads per
-//                          sample; the two contractions with the folded Gram tensor run as 3xTF32 tcgen05 GEMMs,
-//                          tensor memory holds the accumulators, each sample's q = W2 x and one MMA operand.
+//   tucker_fit_tc_kernel   the default from 1536 samples: 128 samples per CTA, two threads per sample; the two
+//                          contractions with the folded Gram tensor run as FP16 hi/lo tcgen05 GEMMs (FP32-grade),
+//                          tensor memory holds the accumulators, each sample's q = W2 x and one MMA operand;
+//                          q comes from tucker_project_tc_kernel (3xTF32 tcgen05 GEMM) for batches of 4096+ rows.
+//   tucker_fit_gen_kernel  the same formulation for run-time ranks (tucker_gen.cuh): enlarged cores.
 //   tucker_fit_tps_kernel  thread-per-sample, FP32 only, ranks fixed at compile time (5,3,3,3 = the shipped /
 //                          configured ranks, configs/config_TD_main.yaml:8-13).  A CTA owns THREADS consecutive
 //                          samples: phase A streams their rows of X once from HBM and leaves q in shared memory;
@@ -13,7 +15,7 @@
 //                          converged fit instead of the T iterations.
 //   tucker_fit_wps_kernel  warp-per-sample: small batches and the single-image case of TD_Inference.py, where the
 //                          latency of the 3000-step chain matters more than throughput.
-//   tucker_fit_cta_kernel  CTA-per-sample, ranks at run time (enlarged cores, BASELINE.json config 5).
+//   tucker_fit_cta_kernel  CTA-per-sample, ranks at run time, FP32: tiny batches of other rank sets, roll rank > 8.
 // No kernel touches global memory between iterations.
 #include <cuda.h>
 
@@ -1711,9 +1713,13 @@ constexpr int kTpsBigThreads = 384;  // TMEM-resident-q variant: one 12-warp CTA
 // is bound by the 3-register-operand FFMA rate, not by latency -- so the variant is opt-in (kernel_hint 4) only
 constexpr int kCtaThreads = 128;
 constexpr int kWpsWarps = 4;
-// the tensor-core kernel takes over from two full waves (128 samples per SM): 37 888 samples on a 148-SM B200
-inline int64_t tc_crossover(const nlml_tucker_plan* pl) { return 2 * (int64_t)pl->num_sms * 128; }
-constexpr int64_t kWpsCrossover = 8192;  // below this the warp-per-sample kernel finishes sooner (profiles/)
+// The tensor-core kernel runs a whole wave (up to 128 samples on each SM) in the time of its 3000-step chain: 4.4-4.7 ms for
+// ANY batch up to 18 944 samples on a 148-SM B200 (round 2 kernel), against 2.8 / 3.6 / 7.2 / 14.4 ms for 256 / 1024 / 2048 /
+// 4096 samples in the warp-per-sample kernel and 23.5 ms per wave in the FP32 thread-per-sample kernel.  So it takes over
+// from 1536 samples (round 1: from two full waves, when its wave took 17 ms); below that the warp-per-sample kernel
+// finishes sooner, and the thread-per-sample kernel is the FP32 reference on request (kernel_hint 1).
+inline int64_t tc_crossover(const nlml_tucker_plan*) { return 1536; }
+constexpr int64_t kWpsCrossover = 8192;  // (only reachable when the tensor-core kernel is not eligible)
 using TpsDefault = TpsCfg<5, 3, 3, 3, kTpsThreads, kTpsSamples>;
 using TpsBig = TpsCfg<5, 3, 3, 3, kTpsBigThreads, 1, true>;
 size_t wps_smem_bytes(int F) { return sizeof(float) * kWpsWarps * ((F + 3) / 4 * 4 + 64); }
