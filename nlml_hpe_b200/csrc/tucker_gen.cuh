@@ -652,9 +652,17 @@ __global__ void __launch_bounds__(kThreads, 1) tucker_fit_gen_kernel(const __gri
             GT(0)
             float ly = 0.f, lp = 0.f, lr_ = 0.f;
             const float* qi = q;
+            const int blk_lines = c.rp * c.rr * 4;   // one (i,j) block of the slab = rp*rr rows of 128 floats = 4 lines each
             for (int i = 0; i < c.ri; ++i) {
                 float lin = 0.f, gyi = 0.f, gpi = 0.f, gri = 0.f;
                 for (int j = 0; j < c.ry; ++j) {
+                    // the NEXT (i,j) block into L1 while this one is contracted: the group's 128 threads touch its lines once, so
+                    // the loads below hit L1 instead of paying the L2 round trip twice per block (they are the group's critical path)
+                    if (i * c.ry + j + 1 < c.ri * c.ry) {
+                        const float* nxt = (qi - row) + (size_t)(blk_lines / 4) * kSamples;
+                        for (int t = row; t < blk_lines; t += kSamples)
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + (size_t)(t >> 2) * kSamples + (t & 3) * 32));
+                    }
                     float A0 = 0.f, A1 = 0.f, A2 = 0.f;
 #pragma unroll 4
                     for (int k = 0; k < c.rp; ++k) {
