@@ -1008,8 +1008,6 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             // the UU operand goes to TENSOR MEMORY (one 32-column store: hi | lo), not through shared memory: no operand
             // stores, no generic->async proxy fence, and the MMA reads A without touching the shared-memory ports
             float UU[16], hl[16];
-            sym_products<5>(u, UU);
-            UU[15] = 0.f;
             // per-sample power-of-two scale: the largest |UU| = (max |u_i|)^2 lands in [2^12, 2^13) (UU starts at 0 and grows over the fit)
             float m = 0.f;
 #pragma unroll
@@ -1018,10 +1016,20 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
             int eu = 12 - (((__float_as_int(m) >> 23) & 0xff) - 127);
             eu = m > 0.f ? max(min(eu, 100), -80) : 0;
             uu_exp = eu;
-            const float su = __int_as_float((eu + 127) << 23);
+            {
+                const float su = __int_as_float((eu + 127) << 23);
+                float us[5];   // the scale rides on one factor of every product (exact: a power of two)
+#pragma unroll
+                for (int i = 0; i < 5; ++i) us[i] = u[i] * su;
+#pragma unroll
+                for (int i = 0; i < 5; ++i)
+#pragma unroll
+                    for (int j = i; j < 5; ++j) UU[pair_index(i, j, 5)] = us[i] * u[j];
+                UU[15] = 0.f;
+            }
 #pragma unroll
             for (int k2 = 0; k2 < 8; ++k2) {   // packed pairs: element 2c in the low half of column c
-                const float v0 = UU[2 * k2] * su, v1 = UU[2 * k2 + 1] * su;
+                const float v0 = UU[2 * k2], v1 = UU[2 * k2 + 1];
                 const __half2 h = __floats2half2_rn(v0, v1);
                 const float2 hf = __half22float2(h);
                 const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
@@ -1041,8 +1049,15 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
         }
         NLML_TSTAMP(0);   // role 0: UU publish + T GEMM issue
         // pitch and roll features first: they are all the V GEMM's operand needs; yaw follows once it is launched
-        cos_features_sfu<3>(p[1], a.rows_p, cp, dcp);
-        cos_features_sfu<3>(p[2], a.rows_r, cr, dcr);
+        if (role == 0) {   // only the angle thread differentiates along pitch and roll
+            cos_features_sfu<3>(p[1], a.rows_p, cp, dcp);
+            cos_features_sfu<3>(p[2], a.rows_r, cr, dcr);
+        } else {
+            cos_values_sfu<3>(p[1], a.rows_p, cp);
+            cos_values_sfu<3>(p[2], a.rows_r, cr);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) dcp[j] = dcr[j] = 0.f;
+        }
         float YY[6], PP[6], RRv[8];
         sym_products<3>(cp, PP);
         sym_products<3>(cr, RRv);
@@ -1105,9 +1120,13 @@ __global__ void __launch_bounds__(256, 1) tucker_fit_tc_kernel(const __grid_cons
                 const float kv = __int_as_float((127 - a.s_exp - a.pr_exp) << 23);   // 2^-(s_exp + pr_exp): the V accumulator's scale off
 #pragma unroll
                 for (int i = 0; i < 6; ++i) YYk[i] = YY[i] * kv;
-                sym_products<5>(u, UUk);
+                float uk[5];   // the scale rides on one factor of every product
 #pragma unroll
-                for (int i = 0; i < 15; ++i) UUk[i] *= kv;
+                for (int i = 0; i < 5; ++i) uk[i] = u[i] * kv;
+#pragma unroll
+                for (int i = 0; i < 5; ++i)
+#pragma unroll
+                    for (int j = i; j < 5; ++j) UUk[pair_index(i, j, 5)] = uk[i] * u[j];
             }
 #pragma unroll
             for (int i = 0; i < 15; ++i) GU[i] = 0.f;

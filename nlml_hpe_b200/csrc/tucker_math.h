@@ -108,6 +108,12 @@ __device__ __forceinline__ void cos_features_sfu(float w, const float* rows, flo
         dc[j] = -(a * b) * __sinf(arg);
     }
 }
+// values only (the caller does not differentiate along this angle)
+template <int R>
+__device__ __forceinline__ void cos_values_sfu(float w, const float* rows, float* c) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) c[j] = fmaf(rows[4 * j + 0], __cosf(fmaf(rows[4 * j + 1], w, rows[4 * j + 2])), rows[4 * j + 3]);
+}
 #endif
 
 template <int R>
