@@ -142,6 +142,15 @@ def test_host_path_ramped_chunks(fitter, X1k):
     assert np.array_equal(fitter.solve_host(X), sdev)
 
 
+def test_auto_dispatch_thresholds(fitter, X1k):
+    """kernel="auto": the warp-per-sample kernel below 1536 samples, the tensor-core kernel from there (one tensor-core wave
+    takes 4.4-4.7 ms at T = 3000 whatever its size, profiles/r02_tucker_small_batches.txt): same bits as the explicit choice."""
+    X = _gpu(np.tile(X1k, (3, 1)))
+    for n, kernel in ((1, "warp_per_sample"), (1000, "warp_per_sample"), (1535, "warp_per_sample"), (1536, "tensor_core"),
+                      (3000, "tensor_core")):
+        assert torch.equal(fitter.fit(X[:n], 30), fitter.fit(X[:n], 30, kernel=kernel)), (n, kernel)
+
+
 def test_reference_entry_points(art, rows, X1k, tucker_golden, cuda_lib, monkeypatch):
     """TD_Tester.optimize_with_sgd / Test with the reference's signatures and conventions."""
     from nlml_hpe_b200 import TD_Tester
